@@ -1,0 +1,451 @@
+// pskd_api.cu -- host runtime behind the C ABI of include/pskd.h.
+//
+// Plays the role of the reference's packet prologue/epilogue (cpp/psk_soft.cpp:346-427,
+// 605-618) for a whole bank of channels: latches properties per call, applies the reset /
+// listener logic (:353-372, :638-651), works out how many symbols every channel emits and where
+// the emulated BULKIO packet boundaries fall, then launches the kernels.  No CPU demodulation
+// exists here: without a CUDA device every entry point returns PSKD_ERR_CUDA.
+#include "../../include/pskd.h"
+#include "pskd_internal.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace pskd;
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA,     \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+        if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc((void**)&p, n * sizeof(T)); want = n; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct ChanHost {
+    pskd_props props;          // as configured (live)
+    pskd_props latched;        // as used by the last process call
+    long long tail_len = 0;    // samples.size() between calls
+    bool resetNumSymbols = true, resetPhaseAvg = true, resetSamplesPerBaud = true;   // cpp/psk_soft.cpp:191-193
+    size_t symbolEnergySize = 10;   // symbolEnergy.size() (cpp/psk_soft.cpp:189), for the listener at :640
+    bool first_packet = true;
+    long long tail_off = 0;    // element offset of this channel's tail region
+    long long tail_cap = 0;
+    pskd_sri_out sri{};
+};
+
+struct pskd_bank {
+    int device = 0;
+    int n_channels = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<ChanHost> ch;
+    // device
+    ChanDesc* d_desc = nullptr;
+    ChanDesc* h_desc_slot[2] = {nullptr, nullptr};   // pinned, double-buffered so NO_SYNC calls can overlap
+    cudaEvent_t desc_ev[2] = {nullptr, nullptr};     // upload of slot i consumed
+    int desc_slot = 0;
+    ChanDesc* h_desc = nullptr;       // slot in use by the current call
+    ChanState* d_state = nullptr;
+    DevCounters* d_counters = nullptr;
+    float* d_ring = nullptr;  int ring_cap = 0;     // floats per channel (2x the max phaseAvg)
+    float2* d_tail[2] = {nullptr, nullptr}; long long tail_total = 0; int tail_cur = 0;
+    DevBuf<float2> sel; DevBuf<float> theta; DevBuf<float> phase_tmp; DevBuf<int16_t> sidx_tmp;
+    // host-buffer staging
+    DevBuf<float> st_in; DevBuf<float> st_soft; DevBuf<float> st_phase; DevBuf<int16_t> st_bits; DevBuf<int16_t> st_sidx;
+    unsigned long long launches = 0;
+    pskd_stats stats{};
+};
+
+static void default_props(pskd_props* p) {
+    p->samplesPerBaud = 10; p->numAvg = 100; p->constelationSize = 4; p->phaseAvg = 50;
+    p->differentialDecoding = 0; p->resetState = 0;
+}
+
+static int check_props(const pskd_props& p) {
+    if (p.samplesPerBaud < 2) return fail(PSKD_ERR_UNSUPPORTED, "samplesPerBaud=%u: the GPU path needs >= 2 (the reference's sps==1 branch only emits with numAvg==0)", p.samplesPerBaud);
+    if (p.samplesPerBaud > 64) return fail(PSKD_ERR_UNSUPPORTED, "samplesPerBaud=%u > 64", p.samplesPerBaud);
+    if (p.numAvg < 1) return fail(PSKD_ERR_UNSUPPORTED, "numAvg=0 never emits a symbol in the reference");
+    if ((unsigned long long)p.numAvg * p.samplesPerBaud > (1ull << 22)) return fail(PSKD_ERR_UNSUPPORTED, "numAvg*samplesPerBaud too large");
+    if (p.phaseAvg < 1) return fail(PSKD_ERR_UNSUPPORTED, "phaseAvg=0 is undefined behaviour in the reference (front() of an empty deque)");
+    if (p.constelationSize < 1) return fail(PSKD_ERR_UNSUPPORTED, "constelationSize=0");
+    return PSKD_OK;
+}
+
+static int bpb_of(int M) { return M == 2 ? 1 : M == 4 ? 2 : M == 8 ? 3 : 0; }
+
+// (re)allocate the carried-tail regions so every channel can hold S*A samples (+ one symbol of slack)
+static int ensure_tails(pskd_bank* b) {
+    bool grow = false;
+    for (auto& c : b->ch) {
+        long long need = (long long)c.props.samplesPerBaud * c.props.numAvg + c.props.samplesPerBaud;
+        if (need > c.tail_cap) grow = true;
+    }
+    if (!grow) return PSKD_OK;
+    std::vector<long long> new_off(b->n_channels), new_cap(b->n_channels);
+    long long total = 0;
+    for (int i = 0; i < b->n_channels; i++) {
+        auto& c = b->ch[i];
+        long long need = (long long)c.props.samplesPerBaud * c.props.numAvg + c.props.samplesPerBaud;
+        new_cap[i] = std::max(need, c.tail_cap);
+        new_off[i] = total;
+        total += (new_cap[i] + 1) & ~1LL;     // keep 16-byte alignment of every region
+    }
+    float2* nt[2] = {nullptr, nullptr};
+    CUDA_TRY(cudaMalloc((void**)&nt[0], std::max<long long>(total, 1) * sizeof(float2)));
+    CUDA_TRY(cudaMalloc((void**)&nt[1], std::max<long long>(total, 1) * sizeof(float2)));
+    if (b->d_tail[0]) {
+        for (int i = 0; i < b->n_channels; i++) {
+            auto& c = b->ch[i];
+            if (c.tail_len > 0)
+                CUDA_TRY(cudaMemcpyAsync(nt[b->tail_cur] + new_off[i], b->d_tail[b->tail_cur] + c.tail_off,
+                                         c.tail_len * sizeof(float2), cudaMemcpyDeviceToDevice, b->stream));
+        }
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]);
+    }
+    b->d_tail[0] = nt[0]; b->d_tail[1] = nt[1]; b->tail_total = total;
+    for (int i = 0; i < b->n_channels; i++) { b->ch[i].tail_off = new_off[i]; b->ch[i].tail_cap = new_cap[i]; }
+    return PSKD_OK;
+}
+
+static int ensure_rings(pskd_bank* b) {
+    int maxP = 1;
+    for (auto& c : b->ch) maxP = std::max<int>(maxP, c.props.phaseAvg);
+    int need = 2 * maxP;                       // second half is the repack spare (GlobalRing::repack)
+    if (need <= b->ring_cap) return PSKD_OK;
+    float* nr = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&nr, (size_t)need * b->n_channels * sizeof(float)));
+    CUDA_TRY(cudaMemsetAsync(nr, 0, (size_t)need * b->n_channels * sizeof(float), b->stream));
+    if (b->d_ring) {
+        CUDA_TRY(cudaMemcpy2DAsync(nr, (size_t)need * sizeof(float), b->d_ring, (size_t)b->ring_cap * sizeof(float),
+                                   (size_t)b->ring_cap * sizeof(float), b->n_channels, cudaMemcpyDeviceToDevice, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_ring);
+    }
+    b->d_ring = nr; b->ring_cap = need;
+    return PSKD_OK;
+}
+
+extern "C" {
+
+int pskd_abi_version(void) { return PSKD_ABI_VERSION; }
+const char* pskd_last_error(void) { return g_last_error.c_str(); }
+void pskd_default_props(pskd_props* p) { if (p) default_props(p); }
+
+int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* props) {
+    if (!out || n_channels < 1) return fail(PSKD_ERR_ARG, "pskd_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PSKD_ERR_CUDA, "pskd_create: CUDA device %d not present (%d devices); there is no CPU path", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    pskd_bank* b = new (std::nothrow) pskd_bank();
+    if (!b) return fail(PSKD_ERR_NOMEM, "out of host memory");
+    b->device = device; b->n_channels = n_channels;
+    b->ch.resize(n_channels);
+    for (int i = 0; i < n_channels; i++) {
+        if (props) b->ch[i].props = props[i]; else default_props(&b->ch[i].props);
+        int rc = check_props(b->ch[i].props);
+        if (rc != PSKD_OK) { delete b; return rc; }
+        b->ch[i].latched = b->ch[i].props;
+    }
+    cudaError_t e;
+#define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
+    CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CT(cudaMalloc((void**)&b->d_desc, sizeof(ChanDesc) * n_channels));
+    for (int i = 0; i < 2; i++) {
+        CT(cudaMallocHost((void**)&b->h_desc_slot[i], sizeof(ChanDesc) * n_channels));
+        CT(cudaEventCreateWithFlags(&b->desc_ev[i], cudaEventDisableTiming));
+    }
+    b->h_desc = b->h_desc_slot[0];
+    CT(cudaMalloc((void**)&b->d_state, sizeof(ChanState) * n_channels));
+    CT(cudaMalloc((void**)&b->d_counters, sizeof(DevCounters)));
+    CT(cudaMemsetAsync(b->d_counters, 0, sizeof(DevCounters), b->stream));
+    {   // initial state: LinearFit(phaseAvg, 1.0), phaseEstimate 0, sampleRate 1.0 (cpp/psk_soft.cpp:35-46,187-199)
+        std::vector<ChanState> init(n_channels);
+        for (int i = 0; i < n_channels; i++) {
+            ChanState& s = init[i];
+            memset(&s, 0, sizeof(s));
+            s.fit.n = b->ch[i].props.phaseAvg;
+            s.fit.xdelta = 1.0f; s.fit.denominator = 1.0f;
+            s.est = 0.0f; s.sampleRate = 1.0f; s.last = make_float2(0.f, 0.f);
+        }
+        CT(cudaMemcpyAsync(b->d_state, init.data(), sizeof(ChanState) * n_channels, cudaMemcpyHostToDevice, b->stream));
+        CT(cudaStreamSynchronize(b->stream));
+    }
+#undef CT
+    int rc = ensure_tails(b);
+    if (rc == PSKD_OK) rc = ensure_rings(b);
+    if (rc != PSKD_OK) { pskd_destroy(b); return rc; }
+    *out = b;
+    return PSKD_OK;
+}
+
+int pskd_destroy(pskd_handle b) {
+    if (!b) return PSKD_OK;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_desc);
+    for (int i = 0; i < 2; i++) { if (b->h_desc_slot[i]) cudaFreeHost(b->h_desc_slot[i]); if (b->desc_ev[i]) cudaEventDestroy(b->desc_ev[i]); }
+    cudaFree(b->d_state); cudaFree(b->d_counters); cudaFree(b->d_ring);
+    cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]);
+    b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
+    b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release();
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return PSKD_OK;
+}
+
+int pskd_set_props(pskd_handle b, int ch, const pskd_props* p) {
+    if (!b || !p || ch < -1 || ch >= b->n_channels) return fail(PSKD_ERR_ARG, "pskd_set_props: bad arguments");
+    int rc = check_props(*p);
+    if (rc != PSKD_OK) return rc;
+    int lo = ch < 0 ? 0 : ch, hi = ch < 0 ? b->n_channels : ch + 1;
+    for (int i = lo; i < hi; i++) {
+        ChanHost& c = b->ch[i];
+        // change listeners fire only when the value changed (cpp/psk_soft.cpp:638-651)
+        if (p->samplesPerBaud != c.props.samplesPerBaud)
+            c.resetSamplesPerBaud = (p->samplesPerBaud != c.symbolEnergySize);         // :640
+        if (p->constelationSize != c.props.constelationSize) c.resetNumSymbols = true; // :645
+        if (p->phaseAvg != c.props.phaseAvg) c.resetPhaseAvg = true;                   // :650
+        c.props = *p;
+    }
+    return PSKD_OK;
+}
+
+int pskd_get_props(pskd_handle b, int ch, pskd_props* p) {
+    if (!b || !p || ch < 0 || ch >= b->n_channels) return fail(PSKD_ERR_ARG, "pskd_get_props: bad arguments");
+    *p = b->ch[ch].props;
+    return PSKD_OK;
+}
+
+size_t pskd_max_symbols(pskd_handle b, int ch, size_t n_complex) {
+    if (!b || ch < 0 || ch >= b->n_channels) return 0;
+    const ChanHost& c = b->ch[ch];
+    return (size_t)((n_complex + (size_t)c.tail_len) / std::max<int>(1, c.props.samplesPerBaud)) + 1;
+}
+
+void* pskd_stream(pskd_handle b) { return b ? (void*)b->stream : nullptr; }
+uint64_t pskd_launch_count(pskd_handle b) { return b ? b->launches : 0; }
+
+int pskd_sync(pskd_handle b) {
+    if (!b) return fail(PSKD_ERR_ARG, "null handle");
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return PSKD_OK;
+}
+
+int pskd_get_sri(pskd_handle b, int ch, pskd_sri_out* sri) {
+    if (!b || !sri || ch < 0 || ch >= b->n_channels) return fail(PSKD_ERR_ARG, "pskd_get_sri: bad arguments");
+    *sri = b->ch[ch].sri;
+    return PSKD_OK;
+}
+
+int pskd_get_stats(pskd_handle b, pskd_stats* st) {
+    if (!b || !st) return fail(PSKD_ERR_ARG, "pskd_get_stats: bad arguments");
+    CUDA_TRY(cudaSetDevice(b->device));
+    DevCounters c;
+    CUDA_TRY(cudaMemcpyAsync(&c, b->d_counters, sizeof(c), cudaMemcpyDeviceToHost, b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    *st = b->stats;
+    st->wraps = c.wraps; st->spec_chunks = c.spec_chunks; st->spec_misses = c.spec_misses; st->seq_channels = c.seq_channels;
+    return PSKD_OK;
+}
+
+int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
+    if (!b || !in || !out) return fail(PSKD_ERR_ARG, "pskd_process: null argument");
+    if (!in->iq && (in->n_complex || in->n_complex_all)) return fail(PSKD_ERR_ARG, "pskd_process: iq is NULL");
+    const int nch = b->n_channels;
+    const bool host_bufs = (in->flags & PSKD_FLAG_HOST_BUFFERS) != 0;
+    if (host_bufs && (in->flags & PSKD_FLAG_NO_SYNC)) return fail(PSKD_ERR_ARG, "PSKD_FLAG_NO_SYNC needs device buffers");
+    CUDA_TRY(cudaSetDevice(b->device));
+
+    // ---- packet prologue, bank-wide (cpp/psk_soft.cpp:353-372) -------------------------------
+    if (in->flags & PSKD_FLAG_QUEUE_FLUSHED)
+        for (auto& c : b->ch) c.props.resetState = 1;                                  // :353-357
+    if (in->sri_mode != 1) {                                                           // :359-363
+        if (out->n_symbols) std::fill(out->n_symbols, out->n_symbols + nch, (size_t)0);
+        if (out->n_bits) std::fill(out->n_bits, out->n_bits + nch, (size_t)0);
+        return PSKD_IGNORED_REAL_DATA;
+    }
+    if (!(in->sri_xdelta > 0.0)) return fail(PSKD_ERR_ARG, "pskd_process: sri_xdelta must be > 0");
+    for (auto& c : b->ch) {
+        if (c.props.resetState) {                                                      // :365-372
+            c.resetSamplesPerBaud = c.resetNumSymbols = c.resetPhaseAvg = true;
+            c.props.resetState = 0;
+        }
+    }
+    int rc = ensure_tails(b);
+    if (rc != PSKD_OK) return rc;
+    rc = ensure_rings(b);
+    if (rc != PSKD_OK) return rc;
+
+    // ---- per-channel geometry ---------------------------------------------------------------
+    b->desc_slot ^= 1;
+    b->h_desc = b->h_desc_slot[b->desc_slot];
+    CUDA_TRY(cudaEventSynchronize(b->desc_ev[b->desc_slot]));   // previous upload from this slot is done
+    long long Kmax = 0, scr_total = 0, nmax = 0;
+    int Smax = 2, Amax = 1;
+    bool any_nobits = false;
+    const int next_tail = b->tail_cur ^ 1;
+    for (int i = 0; i < nch; i++) {
+        ChanHost& c = b->ch[i];
+        const long long n_in = (long long)(in->n_complex ? in->n_complex[i] : in->n_complex_all);
+        if ((size_t)n_in > in->iq_stride && nch > 1) return fail(PSKD_ERR_ARG, "channel %d: n_complex > iq_stride", i);
+        const int S = c.props.samplesPerBaud, A = (int)c.props.numAvg, M = c.props.constelationSize, P = c.props.phaseAvg;
+        const long long numDataPts = (long long)S * A;
+        // resyncEnergy (cpp/psk_soft.cpp:619-636): runs when asked for, or whenever the window is not
+        // full (:380-383, i.e. every packet in steady state).  Its only observable effects here are
+        // the truncation of an over-full window and symbolEnergy.size().
+        if (c.resetSamplesPerBaud || numDataPts > c.tail_len) {
+            if (c.tail_len > numDataPts) c.tail_len = numDataPts;
+            c.symbolEnergySize = S;
+            c.resetSamplesPerBaud = false;
+        }
+        if (c.tail_len >= numDataPts && n_in > 0)
+            return fail(PSKD_ERR_UNSUPPORTED, "channel %d: window over-full after a numAvg/samplesPerBaud decrease; the reference stalls "
+                        "forever here (cpp/psk_soft.cpp:457 never true again) -- not carried on the GPU path", i);
+        const long long total = c.tail_len + n_in;
+        long long K = total / S - A + 1;
+        if (K < 0) K = 0;
+        const long long pkt = in->packet_len ? (long long)in->packet_len : std::max<long long>(n_in, 1);
+        const long long npk = n_in > 0 ? (n_in + pkt - 1) / pkt : 0;
+        if (npk > 0x7fffffffLL) return fail(PSKD_ERR_ARG, "too many packets");
+        ChanDesc& d = b->h_desc[i];
+        d.in = host_bufs ? nullptr : reinterpret_cast<const float2*>(in->iq) + (size_t)i * in->iq_stride;
+        d.tail = b->d_tail[b->tail_cur] + c.tail_off;
+        d.tail_next = b->d_tail[next_tail] + c.tail_off;
+        d.n_in = n_in; d.tail_len = c.tail_len; d.K = K;
+        d.next_tail_len = total - K * S;
+        if (d.next_tail_len > c.tail_cap) return fail(PSKD_ERR_UNSUPPORTED, "channel %d: carried window exceeds its capacity", i);
+        d.sym_off = (long long)i * (long long)out->sym_stride;
+        d.bits_off = (long long)i * (long long)out->bits_stride;
+        d.scr_off = scr_total;
+        d.pkt_len = pkt; d.n_pkts = (int)npk;
+        d.S = S; d.A = A; d.M = M; d.P = P; d.D = c.props.differentialDecoding ? 1 : 0; d.bpb = bpb_of(M);
+        d.ring_off = i * b->ring_cap;
+        d.flags = (c.resetNumSymbols ? CH_RESET_NUMSYMS : 0) | (c.resetPhaseAvg ? CH_RESET_PHASEAVG : 0);
+        if (d.bpb == 0) any_nobits = true;
+        if ((size_t)K > out->sym_stride && (out->soft || out->phase || out->sample_index))
+            return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld symbols > sym_stride %zu", i, K, out->sym_stride);
+        if (out->bits && (size_t)(K * d.bpb) > out->bits_stride)
+            return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld bits > bits_stride %zu", i, K * d.bpb, out->bits_stride);
+        scr_total += (K + 3) & ~3LL;
+        Kmax = std::max(Kmax, K); nmax = std::max(nmax, n_in);
+        Smax = std::max(Smax, S); Amax = std::max(Amax, A);
+    }
+
+    // ---- buffers ------------------------------------------------------------------------------
+    CUDA_TRY(b->sel.reserve((size_t)scr_total + 4));
+    CUDA_TRY(b->theta.reserve((size_t)scr_total + 4));
+    float* dev_soft = out->soft; float* dev_phase = out->phase; int16_t* dev_bits = out->bits; int16_t* dev_sidx = out->sample_index;
+    size_t sym_stride = out->sym_stride, bits_stride = out->bits_stride;
+    if (host_bufs) {
+        // stage through device buffers with the caller's strides squeezed to what this call needs
+        sym_stride = (size_t)((Kmax + 7) & ~7LL); bits_stride = sym_stride * 3;
+        const size_t in_stride = (size_t)((nmax + 1) & ~1LL);
+        CUDA_TRY(b->st_in.reserve(2 * in_stride * nch + 4));
+        if (nmax > 0)
+            CUDA_TRY(cudaMemcpy2DAsync(b->st_in.p, in_stride * 8, in->iq, in->iq_stride * 8, (size_t)nmax * 8, nch,
+                                       cudaMemcpyHostToDevice, b->stream));
+        if (out->soft) { CUDA_TRY(b->st_soft.reserve(2 * sym_stride * nch + 4)); dev_soft = b->st_soft.p; }
+        if (out->phase) { CUDA_TRY(b->st_phase.reserve(sym_stride * nch + 4)); dev_phase = b->st_phase.p; }
+        if (out->bits) { CUDA_TRY(b->st_bits.reserve(bits_stride * nch + 4)); dev_bits = b->st_bits.p; }
+        if (out->sample_index) { CUDA_TRY(b->st_sidx.reserve(sym_stride * nch + 4)); dev_sidx = b->st_sidx.p; }
+        for (int i = 0; i < nch; i++) {
+            ChanDesc& d = b->h_desc[i];
+            d.in = reinterpret_cast<const float2*>(b->st_in.p) + (size_t)i * in_stride;
+            d.sym_off = (long long)i * (long long)sym_stride;
+            d.bits_off = (long long)i * (long long)bits_stride;
+        }
+    }
+    if (!dev_phase) { CUDA_TRY(b->phase_tmp.reserve(sym_stride * nch + 4)); }
+    if (!dev_sidx) { CUDA_TRY(b->sidx_tmp.reserve(sym_stride * nch + 4)); dev_sidx = b->sidx_tmp.p; }
+
+    CUDA_TRY(cudaMemcpyAsync(b->d_desc, b->h_desc, sizeof(ChanDesc) * nch, cudaMemcpyHostToDevice, b->stream));
+    CUDA_TRY(cudaEventRecord(b->desc_ev[b->desc_slot], b->stream));
+
+    LaunchCtx L{};
+    L.stream = b->stream; L.n_channels = nch; L.Kmax = Kmax; L.Smax = Smax; L.Amax = Amax;
+    L.d_desc = b->d_desc; L.d_state = b->d_state; L.d_ring = b->d_ring;
+    L.d_sel = b->sel.p; L.d_theta = b->theta.p; L.d_phase_tmp = b->phase_tmp.p;
+    L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;
+    L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches;
+
+    CUDA_TRY(launch_front(L));
+    CUDA_TRY(launch_chain_seq(L));
+    CUDA_TRY(launch_back(L));
+    CUDA_TRY(launch_finish(L));
+
+    // ---- host-side bookkeeping (what the reference's members hold after the packets) ------------
+    for (int i = 0; i < nch; i++) {
+        ChanHost& c = b->ch[i];
+        const ChanDesc& d = b->h_desc[i];
+        c.tail_len = d.next_tail_len;
+        c.latched = c.props;
+        if (d.n_pkts > 0) {
+            c.resetNumSymbols = false; c.resetPhaseAvg = false;
+            // out-port SRIs (cpp/psk_soft.cpp:399-404), pushed on every packet
+            double xd = in->sri_xdelta * (double)d.S;
+            c.sri.soft_xdelta = xd; c.sri.soft_mode = 1;
+            c.sri.phase_xdelta = xd; c.sri.phase_mode = 0;
+            c.sri.bits_xdelta = xd / (double)d.bpb; c.sri.bits_mode = 0;
+            c.sri.sri_pushes += d.n_pkts;
+        }
+        if (out->n_symbols) out->n_symbols[i] = (size_t)d.K;
+        if (out->n_bits) out->n_bits[i] = (size_t)(d.K * d.bpb);
+        b->stats.symbols_out += (uint64_t)d.K;
+        b->stats.samples_in += (uint64_t)d.n_in;
+        b->stats.packets += (uint64_t)d.n_pkts;
+    }
+    b->tail_cur = next_tail;
+
+    if (host_bufs) {
+        if (Kmax > 0) {
+            if (out->soft) CUDA_TRY(cudaMemcpy2DAsync(out->soft, out->sym_stride * 8, dev_soft, sym_stride * 8, (size_t)Kmax * 8, nch, cudaMemcpyDeviceToHost, b->stream));
+            if (out->phase) CUDA_TRY(cudaMemcpy2DAsync(out->phase, out->sym_stride * 4, dev_phase, sym_stride * 4, (size_t)Kmax * 4, nch, cudaMemcpyDeviceToHost, b->stream));
+            if (out->sample_index) CUDA_TRY(cudaMemcpy2DAsync(out->sample_index, out->sym_stride * 2, dev_sidx, sym_stride * 2, (size_t)Kmax * 2, nch, cudaMemcpyDeviceToHost, b->stream));
+            if (out->bits) {
+                size_t w = std::min((size_t)Kmax * 3, out->bits_stride);
+                CUDA_TRY(cudaMemcpy2DAsync(out->bits, out->bits_stride * 2, dev_bits, bits_stride * 2, w * 2, nch, cudaMemcpyDeviceToHost, b->stream));
+            }
+        }
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    } else if (!(in->flags & PSKD_FLAG_NO_SYNC)) {
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    return any_nobits ? PSKD_NO_BITS : PSKD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// pskd_internal.h -- structures shared by the host runtime (pskd_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pskd_exact.cuh"
+
+namespace pskd {
+
+// Per-channel, per-call descriptor.  Filled on the host, read by every kernel of the call.
+// The channel's logical input is the VIRTUAL stream  tail ++ in  (tail = the samples the
+// reference would still hold in its `samples` deque, cpp/psk_soft.h:66).
+struct ChanDesc {
+    const float2* in;        // this call's new samples
+    const float2* tail;      // carried samples (device, owned by the bank)
+    float2*       tail_next; // where the samples to carry into the next call are written
+    long long n_in;          // new complex samples
+    long long tail_len;      // carried complex samples (< S*A in steady state)
+    long long K;             // symbols emitted by this call
+    long long next_tail_len; // tail_len + n_in - K*S
+    long long sym_off;       // element offset of this channel in soft/phase/sample_index
+    long long bits_off;      // element offset of this channel in bits
+    long long scr_off;       // element offset of this channel in the scratch arrays
+    long long pkt_len;       // emulated BULKIO packet length in complex samples
+    int n_pkts;              // emulated packets in this call
+    int S, A, M, P, D, bpb;
+    int ring_off;            // element offset of this channel's y-history ring
+    int flags;               // CH_* below
+};
+enum { CH_RESET_NUMSYMS = 1, CH_RESET_PHASEAVG = 2, CH_SRI_CHANGED = 4 };
+
+// Carried phase-tracking state of one channel (cpp/psk_soft.h:70-85 minus the timing deques).
+struct ChanState {
+    FitState fit;
+    float  est;          // phaseEstimate
+    float  sampleRate;   // psk_soft_i::sampleRate
+    float2 last;         // psk_soft_i::last
+    unsigned long long wraps;
+};
+
+struct DevCounters {
+    unsigned long long wraps, spec_chunks, spec_misses, seq_channels;
+};
+
+// first call-local output symbol whose emission sample lies at or after input position x
+// (symbol k is emitted when virtual sample (k+A)*S-1 arrives, cpp/psk_soft.cpp:454-457)
+__host__ __device__ inline long long first_symbol_at(long long x, long long tail_len, int S, int A, long long K) {
+    long long v = x + tail_len + 1;
+    long long k = (v + S - 1) / S - A;
+    if (k < 0) k = 0;
+    if (k > K) k = K;
+    return k;
+}
+
+// ---- kernel launchers (pskd_kernels.cu) ----
+struct LaunchCtx {
+    cudaStream_t stream;
+    int n_channels;
+    long long Kmax;          // max K over channels
+    int Smax, Amax;
+    const ChanDesc* d_desc;
+    ChanState* d_state;
+    float* d_ring;
+    float2* d_sel;           // scratch: timing-selected sample per symbol
+    float* d_theta;          // scratch: M-th power angle per symbol
+    float* d_phase_tmp;      // scratch phase when the caller passes no phase buffer
+    float* out_soft; int16_t* out_bits; float* out_phase; int16_t* out_sidx;
+    double sri_xdelta;
+    DevCounters* d_counters;
+    unsigned long long* launches;   // host counter
+};
+
+cudaError_t launch_front(const LaunchCtx& c);
+cudaError_t launch_chain_seq(const LaunchCtx& c);
+cudaError_t launch_back(const LaunchCtx& c);
+cudaError_t launch_finish(const LaunchCtx& c);
+
+}  // namespace pskd

@@ -1,0 +1,41 @@
+"""Comparison helpers shared by the parity tests.
+
+Bar (BASELINE.json north_star): sampleIndex and bits BIT-EXACT; phase and soft within
+1e-4 * max(1, |ref|).  With differential decoding the first symbol is relative to the
+default-constructed `last` (inf/NaN, reference: cpp/psk_soft.cpp:488, cpp/psk_soft.h:70) and is
+skipped for the float comparison exactly as the reference's own test does
+(tests/test_psk_soft.py:199-202); its bits are still compared.
+"""
+import numpy as np
+
+FLOAT_RTOL = 1e-4
+
+
+def float_close(a, b, rtol=FLOAT_RTOL):
+    a = np.asarray(a); b = np.asarray(b)
+    if np.iscomplexobj(a):
+        mag = np.maximum(1.0, np.abs(b))
+        err = np.abs(a - b)
+    else:
+        mag = np.maximum(1.0, np.abs(b))
+        err = np.abs(a - b)
+    bad = ~(err <= rtol * mag)
+    return bad, (err / mag)
+
+
+def assert_parity(got, ref, differential=False, tag="", check_first_bits=True):
+    assert len(got["sidx"]) == len(ref["sidx"]), f"{tag}: symbol count {len(got['sidx'])} != {len(ref['sidx'])}"
+    assert len(got["bits"]) == len(ref["bits"]), f"{tag}: bit count {len(got['bits'])} != {len(ref['bits'])}"
+    assert np.array_equal(got["sidx"], ref["sidx"]), f"{tag}: sampleIndex differs at {np.nonzero(got['sidx'] != ref['sidx'])[0][:8]}"
+    gb, rb = got["bits"], ref["bits"]
+    if differential and not check_first_bits and len(ref["sidx"]):
+        bpb = len(rb) // len(ref["sidx"])
+        gb, rb = gb[bpb:], rb[bpb:]
+    assert np.array_equal(gb, rb), f"{tag}: bits differ at {np.nonzero(gb != rb)[0][:8]} of {len(rb)}"
+    bad, rel = float_close(got["phase"], ref["phase"])
+    assert not bad.any(), f"{tag}: phase differs at {np.nonzero(bad)[0][:8]} max rel {np.nanmax(rel):.3e}"
+    s0 = 1 if differential else 0
+    bad, rel = float_close(got["soft"][s0:], ref["soft"][s0:])
+    assert not bad.any(), f"{tag}: soft differs at {np.nonzero(bad)[0][:8] + s0} max rel {np.nanmax(rel):.3e}"
+    return dict(max_rel_phase=float(np.nanmax(float_close(got["phase"], ref["phase"])[1])) if len(ref["phase"]) else 0.0,
+                max_rel_soft=float(np.nanmax(rel)) if len(rel) else 0.0)

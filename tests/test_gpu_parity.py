@@ -1,0 +1,91 @@
+"""GPU parity: libpskd.so (through the C ABI, host-buffer entry) vs the CPU oracle on the same
+seeded inputs.  Everything here needs a B200: `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import siggen
+from parity import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # SURVEY 3.4 / 8d shapes, reduced to sizes the oracle finishes in a blink
+    dict(S=8, M=4, A=100, P=50, D=0, pkt=64000, xd=0.01, sig=0.02, f=1e-5, n=200000),
+    dict(S=10, M=2, A=100, P=50, D=0, pkt=6400, xd=0.01, sig=0.05, f=1e-4, pn=0.002, n=200000),
+    dict(S=8, M=8, A=100, P=50, D=1, pkt=8000, xd=0.01, sig=0.02, f=2e-5, n=200000),
+    dict(S=8, M=8, A=100, P=50, D=0, pkt=64000, xd=0.01, sig=0.02, f=2e-5, n=200000),
+    dict(S=8, M=8, A=37, P=20, D=0, pkt=1001, xd=1.0, sig=0.02, f=2e-5, n=100000),
+    dict(S=9, M=2, A=64, P=50, D=1, pkt=777, xd=0.01, sig=0.05, f=0.0, n=100000),
+    dict(S=8, M=4, A=100, P=50, D=0, pkt=64, xd=0.01, sig=0.02, f=1e-5, n=50000),
+    dict(S=8, M=3, A=10, P=5, D=0, pkt=500, xd=0.5, sig=0.02, f=1e-5, n=50000),
+    dict(S=2, M=2, A=1, P=1, D=0, pkt=333, xd=0.01, sig=0.05, f=0.0, n=20000),
+    dict(S=16, M=8, A=250, P=200, D=0, pkt=64000, xd=0.01, sig=0.02, f=1e-5, n=200000),
+]
+
+
+def _props(t):
+    return dict(samplesPerBaud=t["S"], constelationSize=t["M"], numAvg=t["A"], phaseAvg=t["P"], differentialDecoding=t["D"])
+
+
+@pytest.mark.parametrize("t", CASES, ids=lambda t: f"S{t['S']}M{t['M']}A{t['A']}P{t['P']}D{t['D']}pkt{t['pkt']}")
+def test_single_channel_vs_oracle(t, oracle_built):
+    import psk_soft_b200 as pk
+    iq = siggen.gen_shaped(t["n"], t["S"], t["M"], seed=5, sigma=t["sig"], freq=t["f"], pn_sigma=t.get("pn", 0), timing_shift=3)
+    ref = oracle_built.OracleComponent(**_props(t)).demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
+    got = pk.PskSoft(**_props(t)).demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
+    assert len(ref["sidx"]) > 0
+    assert_parity(got, ref, differential=bool(t["D"]), tag=str(t))
+
+
+@pytest.mark.parametrize("name", [c[0] for c in siggen.REFERENCE_CASE_ORDER])
+def test_reference_test_cases(name, oracle_built):
+    """The six cases of the reference's own test module (tests/test_psk_soft.py:160-176)."""
+    import psk_soft_b200 as pk
+    c = siggen.reference_cases()[name]
+    props = dict(samplesPerBaud=8, constelationSize=c["M"], numAvg=100, differentialDecoding=int(c["differential"]))
+    ref = oracle_built.OracleComponent(**props).demod(c["iq"], packet_len=64000, xdelta=0.01)
+    got = pk.PskSoft(**props).demod(c["iq"], packet_len=64000, xdelta=0.01)
+    assert len(got["sidx"]) == 901
+    assert_parity(got, ref, differential=c["differential"], tag=name)
+
+
+def test_streaming_calls_match_one_shot(oracle_built):
+    """State carried across pskd_process calls == the reference fed packet by packet."""
+    import psk_soft_b200 as pk
+    t = dict(S=8, M=8, A=100, P=50, D=0)
+    iq = siggen.gen_shaped(120000, 8, 8, seed=11, sigma=0.02, freq=3e-5, timing_shift=5)
+    orc = oracle_built.OracleComponent(**_props(t))
+    dev = pk.PskSoft(**_props(t))
+    cuts = [0, 1000, 1003, 9000, 9001, 50000, 120000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ref = orc.push(iq[a:b], xdelta=0.01)
+        got = dev.push(iq[a:b], xdelta=0.01)
+        assert_parity(got, ref, tag=f"packet {a}:{b}")
+
+
+def test_channel_bank_mixed(oracle_built):
+    """A small mixed bank: per-channel S/M/A/P/D and ragged lengths, one call."""
+    import psk_soft_b200 as pk
+    rs = np.random.RandomState(3)
+    nch, nmax = 12, 60000
+    props, lens, iqs = [], [], np.zeros((nch, nmax), np.complex64)
+    for c in range(nch):
+        S = int(rs.choice([8, 9, 10])); M = int(rs.choice([2, 4, 8])); A = int(rs.choice([50, 100, 200]))
+        P = int(rs.choice([25, 50, 100])); D = int(rs.randint(0, 2))
+        n = int(rs.randint(nmax // 2, nmax + 1))
+        props.append(dict(samplesPerBaud=S, constelationSize=M, numAvg=A, phaseAvg=P, differentialDecoding=D))
+        lens.append(n)
+        iqs[c, :n] = siggen.gen_shaped(n, S, M, seed=100 + c, sigma=0.02, freq=float(rs.uniform(-2e-5, 2e-5)),
+                                       phase0=float(rs.uniform(0, 6.28)), timing_shift=int(rs.randint(0, S)))
+    bank = pk.Bank(nch, props)
+    got = bank.process_host(iqs, n_complex=lens, xdelta=0.01, packet_len=16000)
+    for c in range(nch):
+        ref = oracle_built.OracleComponent(**props[c]).demod(iqs[c, :lens[c]], packet_len=16000, xdelta=0.01)
+        assert_parity(got[c], ref, differential=bool(props[c]["differentialDecoding"]), tag=f"ch{c} {props[c]}")
+
+
+def test_real_data_is_ignored():
+    import psk_soft_b200 as pk
+    dev = pk.PskSoft(samplesPerBaud=8)
+    out = dev.push(np.ones(4000, np.complex64), mode=0)
+    assert out["rc"] == 1 and len(out["soft"]) == 0
