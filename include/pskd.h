@@ -149,6 +149,17 @@ int pskd_get_stats(pskd_handle h, pskd_stats* st);
 /* number of kernel launches this bank has issued since create (bench.py's gpu_launches) */
 uint64_t pskd_launch_count(pskd_handle h);
 
+/* per-kernel device timing, measured with CUDA events on the bank's stream around every launch
+ * (bench.py's live roofline figure).  Off by default. */
+typedef struct pskd_kernel_time {
+    char     name[32];
+    double   ms_total;     /* summed event-to-event time of this kernel's launches */
+    uint64_t launches;
+} pskd_kernel_time;
+int pskd_profile_enable(pskd_handle h, int on);
+/* waits for the stream, then copies up to cap entries; *n = entries available; reset != 0 zeroes them */
+int pskd_profile_read(pskd_handle h, pskd_kernel_time* out, int cap, int* n, int reset);
+
 /* last CUDA / argument error text for this thread */
 const char* pskd_last_error(void);
 

@@ -103,6 +103,16 @@ class Bank:
         self._check(self.lib.pskd_get_stats(self._h, C.byref(s)))
         return {n: int(getattr(s, n)) for n, _ in B.Stats._fields_}
 
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.pskd_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{kernel name: (total ms, launches)} measured with CUDA events on the bank's stream."""
+        arr = (B.KernelTime * 16)()
+        n = C.c_int(0)
+        self._check(self.lib.pskd_profile_read(self._h, arr, 16, C.byref(n), int(reset)))
+        return {arr[i].name.decode(): (arr[i].ms_total, int(arr[i].launches)) for i in range(min(n.value, 16))}
+
     # -- the hot path ----------------------------------------------------------------------
     def process_raw(self, iq_ptr, iq_stride, n_complex, soft_ptr, bits_ptr, phase_ptr, sidx_ptr, sym_stride,
                     bits_stride, xdelta=0.01, packet_len=64000, flags=0, sri_mode=1, counts=True):

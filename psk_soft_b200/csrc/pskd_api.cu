@@ -85,6 +85,7 @@ struct pskd_bank {
     DevBuf<float> st_in; DevBuf<float> st_soft; DevBuf<float> st_phase; DevBuf<int16_t> st_bits; DevBuf<int16_t> st_sidx;
     unsigned long long launches = 0;
     pskd_stats stats{};
+    Profiler prof;
 };
 
 static void default_props(pskd_props* p) {
@@ -222,6 +223,7 @@ int pskd_destroy(pskd_handle b) {
     cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]);
     b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
     b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release();
+    b->prof.destroy();
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return PSKD_OK;
@@ -263,6 +265,32 @@ int pskd_sync(pskd_handle b) {
     if (!b) return fail(PSKD_ERR_ARG, "null handle");
     CUDA_TRY(cudaSetDevice(b->device));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return PSKD_OK;
+}
+
+int pskd_profile_enable(pskd_handle b, int on) {
+    if (!b) return fail(PSKD_ERR_ARG, "null handle");
+    b->prof.enabled = on != 0;
+    return PSKD_OK;
+}
+
+int pskd_profile_read(pskd_handle b, pskd_kernel_time* out, int cap, int* n, int reset) {
+    if (!b || !n) return fail(PSKD_ERR_ARG, "pskd_profile_read: bad arguments");
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    b->prof.drain();
+    int k = 0;
+    for (int i = 0; i < KID_COUNT; i++) {
+        if (!b->prof.launches[i]) continue;
+        if (out && k < cap) {
+            memset(&out[k], 0, sizeof(out[k]));
+            strncpy(out[k].name, kernel_name(i), sizeof(out[k].name) - 1);
+            out[k].ms_total = b->prof.ms[i]; out[k].launches = b->prof.launches[i];
+        }
+        k++;
+    }
+    *n = k;
+    if (reset) for (int i = 0; i < KID_COUNT; i++) { b->prof.ms[i] = 0; b->prof.launches[i] = 0; }
     return PSKD_OK;
 }
 
@@ -401,7 +429,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     L.d_desc = b->d_desc; L.d_state = b->d_state; L.d_ring = b->d_ring;
     L.d_sel = b->sel.p; L.d_theta = b->theta.p; L.d_phase_tmp = b->phase_tmp.p;
     L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;
-    L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches;
+    L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches; L.prof = &b->prof;
 
     CUDA_TRY(launch_front(L));
     CUDA_TRY(launch_chain_seq(L));

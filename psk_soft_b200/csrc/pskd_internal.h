@@ -51,6 +51,22 @@ __host__ __device__ inline long long first_symbol_at(long long x, long long tail
     return k;
 }
 
+// ---- optional per-kernel event timing --------------------------------------------------------
+enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_SPEC, KID_CHAIN_SCAN, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_COUNT };
+struct Profiler {
+    bool enabled = false;
+    struct Pair { cudaEvent_t a, b; int kid; };
+    Pair* pending = nullptr; int n_pending = 0, cap_pending = 0;
+    cudaEvent_t* pool = nullptr; int n_pool = 0, cap_pool = 0;
+    double ms[KID_COUNT] = {0}; unsigned long long launches[KID_COUNT] = {0};
+    cudaEvent_t get();
+    void begin(int kid, cudaStream_t s);
+    void end(cudaStream_t s);
+    void drain();          // caller has synchronised the stream
+    void destroy();
+};
+const char* kernel_name(int kid);
+
 // ---- kernel launchers (pskd_kernels.cu) ----
 struct LaunchCtx {
     cudaStream_t stream;
@@ -67,6 +83,7 @@ struct LaunchCtx {
     double sri_xdelta;
     DevCounters* d_counters;
     unsigned long long* launches;   // host counter
+    Profiler* prof;
 };
 
 cudaError_t launch_front(const LaunchCtx& c);

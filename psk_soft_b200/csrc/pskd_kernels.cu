@@ -12,6 +12,55 @@
 
 namespace pskd {
 
+const char* kernel_name(int kid) {
+    static const char* names[KID_COUNT] = {"k_front", "k_chain_seq", "k_chain_spec", "k_chain_scan", "k_chain_exact", "k_back", "k_finish"};
+    return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "?";
+}
+cudaEvent_t Profiler::get() {
+    if (n_pool > 0) return pool[--n_pool];
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+void Profiler::begin(int kid, cudaStream_t s) {
+    if (!enabled) return;
+    if (n_pending == cap_pending) {
+        int nc = cap_pending ? 2 * cap_pending : 64;
+        Pair* np = new Pair[nc];
+        for (int i = 0; i < n_pending; i++) np[i] = pending[i];
+        delete[] pending; pending = np; cap_pending = nc;
+    }
+    Pair& p = pending[n_pending];
+    p.a = get(); p.b = get(); p.kid = kid;
+    cudaEventRecord(p.a, s);
+}
+void Profiler::end(cudaStream_t s) {
+    if (!enabled) return;
+    cudaEventRecord(pending[n_pending].b, s);
+    n_pending++;
+}
+void Profiler::drain() {
+    for (int i = 0; i < n_pending; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, pending[i].a, pending[i].b) == cudaSuccess) { ms[pending[i].kid] += t; launches[pending[i].kid]++; }
+        for (cudaEvent_t e : {pending[i].a, pending[i].b}) {
+            if (n_pool == cap_pool) {
+                int nc = cap_pool ? 2 * cap_pool : 128;
+                cudaEvent_t* np = new cudaEvent_t[nc];
+                for (int j = 0; j < n_pool; j++) np[j] = pool[j];
+                delete[] pool; pool = np; cap_pool = nc;
+            }
+            pool[n_pool++] = e;
+        }
+    }
+    n_pending = 0;
+}
+void Profiler::destroy() {
+    drain();
+    for (int i = 0; i < n_pool; i++) cudaEventDestroy(pool[i]);
+    delete[] pool; delete[] pending; pool = nullptr; pending = nullptr; n_pool = cap_pool = cap_pending = 0;
+}
+
 // virtual stream = tail ++ in
 struct VStream {
     const float2* tail; const float2* in; long long tail_len;
@@ -119,7 +168,9 @@ cudaError_t launch_front(const LaunchCtx& c) {
         configured = smem;
     }
     dim3 grid((unsigned)((c.Kmax + FT - 1) / FT), (unsigned)c.n_channels);
+    c.prof->begin(KID_FRONT, c.stream);
     k_front<<<grid, FRONT_THREADS, smem, c.stream>>>(c.d_desc, c.out_sidx, c.d_sel, c.d_theta);
+    c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
 }
@@ -210,8 +261,10 @@ cudaError_t launch_chain_seq(const LaunchCtx& c) {
     int threads = 32;
     int blocks = (c.n_channels + threads - 1) / threads;
     float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
+    c.prof->begin(KID_CHAIN_SEQ, c.stream);
     k_chain_seq<<<blocks, threads, 0, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, phase,
                                                   c.sri_xdelta, c.n_channels, c.d_counters);
+    c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
 }
@@ -249,7 +302,9 @@ cudaError_t launch_back(const LaunchCtx& c) {
     if (!c.out_soft && !c.out_bits) return cudaSuccess;
     dim3 grid((unsigned)((c.Kmax + 255) / 256), (unsigned)c.n_channels);
     const float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
+    c.prof->begin(KID_BACK, c.stream);
     k_back<<<grid, 256, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
+    c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
 }
@@ -269,7 +324,9 @@ __global__ void k_finish(const ChanDesc* __restrict__ desc, ChanState* __restric
 }
 
 cudaError_t launch_finish(const LaunchCtx& c) {
+    c.prof->begin(KID_FINISH, c.stream);
     k_finish<<<c.n_channels, 128, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel);
+    c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
 }
