@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -60,6 +61,7 @@ struct ChanHost {
     bool resetNumSymbols = true, resetPhaseAvg = true, resetSamplesPerBaud = true;   // cpp/psk_soft.cpp:191-193
     size_t symbolEnergySize = 10;   // symbolEnergy.size() (cpp/psk_soft.cpp:189), for the listener at :640
     bool first_packet = true;
+    int fit_n = 0;             // LinearFit::n currently held in the device state
     long long tail_off = 0;    // element offset of this channel's tail region
     long long tail_cap = 0;
     pskd_sri_out sri{};
@@ -85,6 +87,7 @@ struct pskd_bank {
     DevBuf<float> st_in; DevBuf<float> st_soft; DevBuf<float> st_phase; DevBuf<int16_t> st_bits; DevBuf<int16_t> st_sidx;
     unsigned long long launches = 0;
     pskd_stats stats{};
+    int chain_mode = 0;        // 0 auto (scan-based where possible), 1 force the sequential chain (PSKD_CHAIN=seq)
     Profiler prof;
 };
 
@@ -180,7 +183,9 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
         int rc = check_props(b->ch[i].props);
         if (rc != PSKD_OK) { delete b; return rc; }
         b->ch[i].latched = b->ch[i].props;
+        b->ch[i].fit_n = b->ch[i].props.phaseAvg;
     }
+    if (const char* e = getenv("PSKD_CHAIN")) b->chain_mode = (strcmp(e, "seq") == 0) ? 1 : 0;
     cudaError_t e;
 #define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
     CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
@@ -344,7 +349,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     b->h_desc = b->h_desc_slot[b->desc_slot];
     CUDA_TRY(cudaEventSynchronize(b->desc_ev[b->desc_slot]));   // previous upload from this slot is done
     long long Kmax = 0, scr_total = 0, nmax = 0;
-    int Smax = 2, Amax = 1;
+    int Smax = 2, Amax = 1, Pmax_fast = 1, n_fast = 0, n_seq = 0;
     bool any_nobits = false;
     const int next_tail = b->tail_cur ^ 1;
     for (int i = 0; i < nch; i++) {
@@ -384,6 +389,9 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         d.S = S; d.A = A; d.M = M; d.P = P; d.D = c.props.differentialDecoding ? 1 : 0; d.bpb = bpb_of(M);
         d.ring_off = i * b->ring_cap;
         d.flags = (c.resetNumSymbols ? CH_RESET_NUMSYMS : 0) | (c.resetPhaseAvg ? CH_RESET_PHASEAVG : 0);
+        // the scan-based chain needs the history staged in shared memory and an unchanged window length
+        const bool fast = b->chain_mode == 0 && P <= CHAIN_PAR_PMAX && c.fit_n == P;
+        if (fast) { d.flags |= CH_FAST; n_fast++; Pmax_fast = std::max(Pmax_fast, P); } else n_seq++;
         if (d.bpb == 0) any_nobits = true;
         if ((size_t)K > out->sym_stride && (out->soft || out->phase || out->sample_index))
             return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld symbols > sym_stride %zu", i, K, out->sym_stride);
@@ -426,12 +434,14 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
 
     LaunchCtx L{};
     L.stream = b->stream; L.n_channels = nch; L.Kmax = Kmax; L.Smax = Smax; L.Amax = Amax;
+    L.Pmax_fast = Pmax_fast; L.n_fast_channels = n_fast; L.n_seq_channels = n_seq;
     L.d_desc = b->d_desc; L.d_state = b->d_state; L.d_ring = b->d_ring;
     L.d_sel = b->sel.p; L.d_theta = b->theta.p; L.d_phase_tmp = b->phase_tmp.p;
     L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;
     L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches; L.prof = &b->prof;
 
     CUDA_TRY(launch_front(L));
+    CUDA_TRY(launch_chain_par(L));
     CUDA_TRY(launch_chain_seq(L));
     CUDA_TRY(launch_back(L));
     CUDA_TRY(launch_finish(L));
@@ -444,6 +454,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         c.latched = c.props;
         if (d.n_pkts > 0) {
             c.resetNumSymbols = false; c.resetPhaseAvg = false;
+            c.fit_n = d.P;
             // out-port SRIs (cpp/psk_soft.cpp:399-404), pushed on every packet
             double xd = in->sri_xdelta * (double)d.S;
             c.sri.soft_xdelta = xd; c.sri.soft_mode = 1;

@@ -26,7 +26,9 @@ struct ChanDesc {
     int ring_off;            // element offset of this channel's y-history ring
     int flags;               // CH_* below
 };
-enum { CH_RESET_NUMSYMS = 1, CH_RESET_PHASEAVG = 2, CH_SRI_CHANGED = 4 };
+enum { CH_RESET_NUMSYMS = 1, CH_RESET_PHASEAVG = 2, CH_SRI_CHANGED = 4,
+       CH_FAST = 8 /* phase chain + back run in k_chain_par (scan-based), else k_chain_seq + k_back */ };
+constexpr int CHAIN_PAR_PMAX = 1024;   // largest phaseAvg the scan-based chain stages in shared memory
 
 // Carried phase-tracking state of one channel (cpp/psk_soft.h:70-85 minus the timing deques).
 struct ChanState {
@@ -52,7 +54,7 @@ __host__ __device__ inline long long first_symbol_at(long long x, long long tail
 }
 
 // ---- optional per-kernel event timing --------------------------------------------------------
-enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_SPEC, KID_CHAIN_SCAN, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_COUNT };
+enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_CHAIN_SCAN, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_COUNT };
 struct Profiler {
     bool enabled = false;
     struct Pair { cudaEvent_t a, b; int kid; };
@@ -72,7 +74,8 @@ struct LaunchCtx {
     cudaStream_t stream;
     int n_channels;
     long long Kmax;          // max K over channels
-    int Smax, Amax;
+    int Smax, Amax, Pmax_fast;
+    int n_seq_channels, n_fast_channels;
     const ChanDesc* d_desc;
     ChanState* d_state;
     float* d_ring;
@@ -88,6 +91,7 @@ struct LaunchCtx {
 
 cudaError_t launch_front(const LaunchCtx& c);
 cudaError_t launch_chain_seq(const LaunchCtx& c);
+cudaError_t launch_chain_par(const LaunchCtx& c);
 cudaError_t launch_back(const LaunchCtx& c);
 cudaError_t launch_finish(const LaunchCtx& c);
 

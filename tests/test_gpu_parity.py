@@ -23,12 +23,19 @@ CASES = [
 ]
 
 
+@pytest.fixture(params=["par", "seq"])
+def chain_mode(request, monkeypatch):
+    """run every case through the scan-based chain and through the literal sequential chain"""
+    monkeypatch.setenv("PSKD_CHAIN", request.param)
+    return request.param
+
+
 def _props(t):
     return dict(samplesPerBaud=t["S"], constelationSize=t["M"], numAvg=t["A"], phaseAvg=t["P"], differentialDecoding=t["D"])
 
 
 @pytest.mark.parametrize("t", CASES, ids=lambda t: f"S{t['S']}M{t['M']}A{t['A']}P{t['P']}D{t['D']}pkt{t['pkt']}")
-def test_single_channel_vs_oracle(t, oracle_built):
+def test_single_channel_vs_oracle(t, oracle_built, chain_mode):
     import psk_soft_b200 as pk
     iq = siggen.gen_shaped(t["n"], t["S"], t["M"], seed=5, sigma=t["sig"], freq=t["f"], pn_sigma=t.get("pn", 0), timing_shift=3)
     ref = oracle_built.OracleComponent(**_props(t)).demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
@@ -38,7 +45,7 @@ def test_single_channel_vs_oracle(t, oracle_built):
 
 
 @pytest.mark.parametrize("name", [c[0] for c in siggen.REFERENCE_CASE_ORDER])
-def test_reference_test_cases(name, oracle_built):
+def test_reference_test_cases(name, oracle_built, chain_mode):
     """The six cases of the reference's own test module (tests/test_psk_soft.py:160-176)."""
     import psk_soft_b200 as pk
     c = siggen.reference_cases()[name]
@@ -49,7 +56,7 @@ def test_reference_test_cases(name, oracle_built):
     assert_parity(got, ref, differential=c["differential"], tag=name)
 
 
-def test_streaming_calls_match_one_shot(oracle_built):
+def test_streaming_calls_match_one_shot(oracle_built, chain_mode):
     """State carried across pskd_process calls == the reference fed packet by packet."""
     import psk_soft_b200 as pk
     t = dict(S=8, M=8, A=100, P=50, D=0)
@@ -63,7 +70,7 @@ def test_streaming_calls_match_one_shot(oracle_built):
         assert_parity(got, ref, tag=f"packet {a}:{b}")
 
 
-def test_channel_bank_mixed(oracle_built):
+def test_channel_bank_mixed(oracle_built, chain_mode):
     """A small mixed bank: per-channel S/M/A/P/D and ragged lengths, one call."""
     import psk_soft_b200 as pk
     rs = np.random.RandomState(3)
@@ -89,3 +96,27 @@ def test_real_data_is_ignored():
     dev = pk.PskSoft(samplesPerBaud=8)
     out = dev.push(np.ones(4000, np.complex64), mode=0)
     assert out["rc"] == 1 and len(out["soft"]) == 0
+
+
+LOW_SNR = [
+    # per-sample SNRs where classic sample-to-sample unwrapping disagrees with the reference's
+    # unwrap-against-the-fit rule: the scan chain must repair its predictions
+    dict(S=8, M=2, A=100, P=50, D=0, pkt=64000, xd=0.01, sig=0.35, f=1e-4, n=400000),
+    dict(S=8, M=4, A=100, P=50, D=0, pkt=16000, xd=0.01, sig=0.25, f=5e-5, n=400000),
+    dict(S=8, M=8, A=100, P=50, D=0, pkt=64000, xd=0.01, sig=0.15, f=2e-5, n=400000),
+    dict(S=10, M=8, A=50, P=25, D=0, pkt=6400, xd=1.0, sig=0.2, f=2e-5, n=400000),
+]
+
+
+@pytest.mark.parametrize("t", LOW_SNR, ids=lambda t: f"M{t['M']}sig{t['sig']}")
+def test_low_snr_unwrap_repairs(t, oracle_built, monkeypatch):
+    import psk_soft_b200 as pk
+    monkeypatch.setenv("PSKD_CHAIN", "par")
+    iq = siggen.gen_shaped(t["n"], t["S"], t["M"], seed=21, sigma=t["sig"], freq=t["f"], timing_shift=1)
+    ref = oracle_built.OracleComponent(**_props(t)).demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
+    dev = pk.PskSoft(**_props(t))
+    got = dev.demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
+    st = dev.stats()
+    print("chain stats", st)
+    assert st["spec_chunks"] > 0
+    assert_parity(got, ref, tag=str(t))
