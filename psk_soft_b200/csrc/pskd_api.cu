@@ -98,7 +98,9 @@ static void default_props(pskd_props* p) {
 
 static int check_props(const pskd_props& p) {
     if (p.samplesPerBaud < 2) return fail(PSKD_ERR_UNSUPPORTED, "samplesPerBaud=%u: the GPU path needs >= 2 (the reference's sps==1 branch only emits with numAvg==0)", p.samplesPerBaud);
-    if (p.samplesPerBaud > 64) return fail(PSKD_ERR_UNSUPPORTED, "samplesPerBaud=%u > 64", p.samplesPerBaud);
+    if (p.samplesPerBaud > 63) return fail(PSKD_ERR_UNSUPPORTED, "samplesPerBaud=%u > 63", p.samplesPerBaud);
+    if ((size_t)(512 + p.numAvg) * (p.samplesPerBaud | 1) * 8 + 16384 > 220 * 1024)
+        return fail(PSKD_ERR_UNSUPPORTED, "numAvg=%u x samplesPerBaud=%u: the timing window does not fit the shared-memory tile", p.numAvg, p.samplesPerBaud);
     if (p.numAvg < 1) return fail(PSKD_ERR_UNSUPPORTED, "numAvg=0 never emits a symbol in the reference");
     if ((unsigned long long)p.numAvg * p.samplesPerBaud > (1ull << 22)) return fail(PSKD_ERR_UNSUPPORTED, "numAvg*samplesPerBaud too large");
     if (p.phaseAvg < 1) return fail(PSKD_ERR_UNSUPPORTED, "phaseAvg=0 is undefined behaviour in the reference (front() of an empty deque)");
@@ -350,6 +352,8 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     CUDA_TRY(cudaEventSynchronize(b->desc_ev[b->desc_slot]));   // previous upload from this slot is done
     long long Kmax = 0, scr_total = 0, nmax = 0;
     int Smax = 2, Amax = 1, Pmax_fast = 1, n_fast = 0, n_seq = 0;
+    unsigned long long S_mask = 0, S_mask_fast = 0;
+    int Amax_fast = 1, Amin_fast = 1 << 30;
     bool any_nobits = false;
     const int next_tail = b->tail_cur ^ 1;
     for (int i = 0; i < nch; i++) {
@@ -400,6 +404,11 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         scr_total += (K + 3) & ~3LL;
         Kmax = std::max(Kmax, K); nmax = std::max(nmax, n_in);
         Smax = std::max(Smax, S); Amax = std::max(Amax, A);
+        if (K > 0) {
+            const bool front_fast = (S == 8 || S == 9 || S == 10 || S == 16) && A <= FRONT_FAST_AMAX;
+            if (front_fast) { d.flags |= CH_FRONT_FAST; S_mask_fast |= 1ull << S; Amax_fast = std::max(Amax_fast, A); Amin_fast = std::min(Amin_fast, A); }
+            else S_mask |= 1ull << S;
+        }
     }
 
     // ---- buffers ------------------------------------------------------------------------------
@@ -434,7 +443,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
 
     LaunchCtx L{};
     L.stream = b->stream; L.n_channels = nch; L.Kmax = Kmax; L.Smax = Smax; L.Amax = Amax;
-    L.Pmax_fast = Pmax_fast; L.n_fast_channels = n_fast; L.n_seq_channels = n_seq;
+    L.S_mask = S_mask; L.S_mask_fast = S_mask_fast; L.Amax_fast = Amax_fast; L.Amin_fast = Amin_fast; L.Pmax_fast = Pmax_fast; L.n_fast_channels = n_fast; L.n_seq_channels = n_seq;
     L.d_desc = b->d_desc; L.d_state = b->d_state; L.d_ring = b->d_ring;
     L.d_sel = b->sel.p; L.d_theta = b->theta.p; L.d_phase_tmp = b->phase_tmp.p;
     L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;

@@ -27,7 +27,9 @@ struct ChanDesc {
     int flags;               // CH_* below
 };
 enum { CH_RESET_NUMSYMS = 1, CH_RESET_PHASEAVG = 2, CH_SRI_CHANGED = 4,
-       CH_FAST = 8 /* phase chain + back run in k_chain_par (scan-based), else k_chain_seq + k_back */ };
+       CH_FAST = 8 /* phase chain + back run in k_chain_par (scan-based), else k_chain_seq + k_back */,
+       CH_FRONT_FAST = 16 /* timing runs in k_front_t<S>, else in the generic k_front */ };
+constexpr int FRONT_FAST_AMAX = 768;   // largest numAvg the specialised front tile (1024 symbols) still uses efficiently
 constexpr int CHAIN_PAR_PMAX = 1024;   // largest phaseAvg the scan-based chain stages in shared memory
 
 // Carried phase-tracking state of one channel (cpp/psk_soft.h:70-85 minus the timing deques).
@@ -54,7 +56,7 @@ __host__ __device__ inline long long first_symbol_at(long long x, long long tail
 }
 
 // ---- optional per-kernel event timing --------------------------------------------------------
-enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_CHAIN_SCAN, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_COUNT };
+enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_COUNT };
 struct Profiler {
     bool enabled = false;
     struct Pair { cudaEvent_t a, b; int kid; };
@@ -75,6 +77,9 @@ struct LaunchCtx {
     int n_channels;
     long long Kmax;          // max K over channels
     int Smax, Amax, Pmax_fast;
+    unsigned long long S_mask;   // bit s set: some channel with samplesPerBaud == s takes the generic front kernel
+    unsigned long long S_mask_fast;   // same for the specialised kernels
+    int Amax_fast, Amin_fast;
     int n_seq_channels, n_fast_channels;
     const ChanDesc* d_desc;
     ChanState* d_state;

@@ -13,7 +13,7 @@
 namespace pskd {
 
 const char* kernel_name(int kid) {
-    static const char* names[KID_COUNT] = {"k_front", "k_chain_seq", "k_chain_par", "k_chain_scan", "k_chain_exact", "k_back", "k_finish"};
+    static const char* names[KID_COUNT] = {"k_front", "k_chain_seq", "k_chain_par", "k_back_par", "k_chain_exact", "k_back", "k_finish"};
     return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "?";
 }
 cudaEvent_t Profiler::get() {
@@ -85,9 +85,10 @@ constexpr int FRONT_THREADS = 256;
 
 __global__ void __launch_bounds__(FRONT_THREADS)
 k_front(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
-        float2* __restrict__ sel, float* __restrict__ theta)
+        float2* __restrict__ sel, float* __restrict__ theta, unsigned long long S_mask)
 {
     const ChanDesc& d = desc[blockIdx.y];
+    if (d.flags & CH_FRONT_FAST) return;        // handled by the specialised kernel
     const long long k0 = (long long)blockIdx.x * FT;
     if (k0 >= d.K) return;
     const int S = d.S, A = d.A, M = d.M;
@@ -157,19 +158,244 @@ k_front(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_front_t<S>: specialised on samplesPerBaud.  One CTA (FT_THREADS threads) = one tile of
+// FT_ROWS = FT_THREADS*8 input symbols of one channel:
+//   stage : coalesced 128-bit loads of the IQ samples, e = f32(re^2+im^2) (std::norm<float>,
+//           cpp/psk_soft.cpp:448) stored as FLOAT rows e[j][0..S) in shared memory
+//   sums  : thread r owns the run of 8 rows 8r..8r+7 (kept in registers).  Block sums per phase
+//           (double) -> prefix over runs (warp shuffles + one shared row per warp) -> window sum
+//           of the first symbol of the run = difference of two run prefixes + (A mod 8) rows,
+//           then the window slides one symbol at a time: + newest row, - oldest (own) row
+//           (cpp/psk_soft.cpp:451, 576).  All sums are doubles of float-exact energies.
+//   pick  : first maximum over the S phases (:462), gather that sample of the oldest symbol
+//           (:465), M-th power angle (:474); writes sampleIndex, sample, theta.
+// Shared-memory traffic is ~20 B/sample (float rows) instead of ~40 B/sample for a double prefix
+// table, and every global load is a fully coalesced LDG.128 -- the two things ncu showed the
+// generic kernel was bound by (profiles/r01b).  Rows are padded by 4 words per run so the
+// quarter-warp row reads (stride 8 rows) hit distinct bank groups.
+// ---------------------------------------------------------------------------------------------
+constexpr int FT_THREADS = 128;
+constexpr int FT_R = 8;
+constexpr int FT_ROWS = FT_THREADS * FT_R;       // 1024 input symbols per tile
+
+__device__ __forceinline__ float mth_power_angle_fast(float2 s, unsigned M) {
+    // unchecked squarings; a (NaN,NaN) anywhere propagates to the end, and only then can the
+    // reference have gone through __mulsc3 -> redo with the checked multiply.
+    float2 x = s, y = (M & 1u) ? s : make_float2(1.0f, 0.0f);
+    unsigned n = M;
+    while (n >>= 1) {
+        x = make_float2(fsubr(fmulr(x.x, x.x), fmulr(x.y, x.y)), faddr(fmulr(x.x, x.y), fmulr(x.y, x.x)));
+        if (n & 1u) y = make_float2(fsubr(fmulr(y.x, x.x), fmulr(y.y, x.y)), faddr(fmulr(y.x, x.y), fmulr(y.y, x.x)));
+    }
+    if (isnan(y.x) && isnan(y.y)) y = cpow_unsigned(s, M);
+    return atan2f(y.y, y.x);
+}
+
+template <int S> struct FrontCfg {
+    static constexpr int SE = (S + 3) & ~3;                       // row stride in floats (16-byte rows)
+    static constexpr int RUNW = FT_R * SE + 4;                    // words per run incl. the 4-word pad
+    static constexpr int E_WORDS = FT_THREADS * RUNW;
+    static constexpr int PB_DOUBLES = (FT_THREADS / 32) * S;      // per-warp totals
+    static constexpr int PBR_DOUBLES = FT_THREADS * S;            // inclusive run prefixes
+    static constexpr size_t SMEM = (size_t)E_WORDS * 4 + (size_t)(PB_DOUBLES + PBR_DOUBLES) * 8;
+};
+
+template <int S>
+__global__ void __launch_bounds__(FT_THREADS)
+k_front_t(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
+          float2* __restrict__ sel, float* __restrict__ theta)
+{
+    using C = FrontCfg<S>;
+    constexpr int SE = C::SE;
+    const ChanDesc& d = desc[blockIdx.y];
+    if (d.S != S || !(d.flags & CH_FRONT_FAST)) return;
+    const int A = d.A;
+    const int T_out = FT_ROWS - A + 1;           // output symbols per tile (host guarantees >= 64)
+    const long long k0 = (long long)blockIdx.x * T_out;
+    if (k0 >= d.K) return;
+    const unsigned M = (unsigned)d.M;
+
+    extern __shared__ double smem[];
+    double* pbr = smem;                           // [FT_THREADS][S] inclusive prefix of the run sums
+    double* wt  = pbr + C::PBR_DOUBLES;           // [warps][S]
+    float*  es  = (float*)(wt + C::PB_DOUBLES);   // energies, run-padded rows
+
+    const int tid = threadIdx.x;
+    const long long s0 = k0 * S;                  // first virtual sample of the tile
+    const long long V = d.tail_len + d.n_in;      // virtual stream length
+    const bool in_tail = s0 < d.tail_len;
+    const float2* gin = d.in + (s0 - d.tail_len); // valid address arithmetic only when !in_tail
+    VStream vs{d.tail, d.in, d.tail_len};
+
+    // ---- stage: 2 samples per thread per step -------------------------------------------------
+    {
+        constexpr int NCHUNK = FT_ROWS * S / 2;   // float4 chunks in the tile
+        const long long avail = V - s0;           // samples of the tile that exist
+        const bool vec_ok = !in_tail && ((reinterpret_cast<uintptr_t>(gin) & 15) == 0) && (S % 2 == 0);
+        if (vec_ok && avail >= (long long)FT_ROWS * S) {
+            const float4* g4 = reinterpret_cast<const float4*>(gin);
+#pragma unroll 8
+            for (int c = tid; c < NCHUNK; c += FT_THREADS) {
+                float4 x = __ldg(g4 + c);
+                const int smp = 2 * c, j = smp / S, p = smp - j * S;
+                float2 e = make_float2(energy_f32(x.x, x.y), energy_f32(x.z, x.w));
+                *reinterpret_cast<float2*>(es + (j >> 3) * C::RUNW + (j & 7) * SE + p) = e;
+            }
+        } else {
+            for (int smp = tid; smp < FT_ROWS * S; smp += FT_THREADS) {
+                float2 x = make_float2(0.f, 0.f);
+                if (smp < avail) x = in_tail ? vs.at(s0 + smp) : __ldg(gin + smp);
+                const int j = smp / S, p = smp - j * S;
+                es[(j >> 3) * C::RUNW + (j & 7) * SE + p] = energy_f32(x.x, x.y);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- run sums and their prefix over runs -----------------------------------------------------
+    const int r = tid, lane = tid & 31, w = tid >> 5;
+    const float* myrun = es + r * C::RUNW;
+    double bs[S], pin[S];                         // run sum, inclusive prefix over runs
+#pragma unroll
+    for (int q = 0; q < S; q++) bs[q] = 0.0;
+#pragma unroll
+    for (int i = 0; i < FT_R; i++) {
+        float rowv[S];
+#pragma unroll
+        for (int q = 0; q + 3 < S; q += 4) {
+            float4 v = *reinterpret_cast<const float4*>(myrun + i * SE + q);
+            rowv[q] = v.x; rowv[q + 1] = v.y; rowv[q + 2] = v.z; rowv[q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = S & ~3; q < S; q++) rowv[q] = myrun[i * SE + q];
+#pragma unroll
+        for (int q = 0; q < S; q++) bs[q] = daddr(bs[q], (double)rowv[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < S; q++) pin[q] = bs[q];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < S; q++) {
+            double u = __shfl_up_sync(0xffffffffu, pin[q], o);
+            if (lane >= o) pin[q] = daddr(pin[q], u);
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int q = 0; q < S; q++) wt[w * S + q] = pin[q];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ww = 0; ww < FT_THREADS / 32 - 1; ww++) {
+        if (ww < w) {
+#pragma unroll
+            for (int q = 0; q < S; q++) pin[q] = daddr(pin[q], wt[ww * S + q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < S; q++) pbr[r * S + q] = pin[q];
+    __syncthreads();
+
+    // ---- window sums of this run's symbols ----------------------------------------------------------
+    const int kk0 = r * FT_R;                     // tile-local index of this run's first symbol
+    if (kk0 >= T_out || k0 + kk0 >= d.K) return;
+    const int nq = A / FT_R, rem = A - nq * FT_R;
+    double E[S];
+    if (nq >= 1) {
+        const double* hi = pbr + (r + nq - 1) * S;     // runs r .. r+nq-1 = prefix[r+nq-1] - (prefix[r] - own sum)
+#pragma unroll
+        for (int q = 0; q < S; q++) E[q] = daddr(dsubr(hi[q], pin[q]), bs[q]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < S; q++) E[q] = 0.0;
+    }
+    {
+        const int jr = kk0 + nq * FT_R;           // first of the `rem` extra rows
+        for (int i = 0; i < rem; i++) {
+            const int j = jr + i;
+            const float* row = es + (j >> 3) * C::RUNW + (j & 7) * SE;
+#pragma unroll
+            for (int q = 0; q < S; q++) E[q] = daddr(E[q], (double)row[q]);
+        }
+    }
+    const long long obase = d.sym_off + k0, sbase = d.scr_off + k0;
+#pragma unroll
+    for (int i = 0; i < FT_R; i++) {
+        const int kk = kk0 + i;
+        if (kk >= T_out || k0 + kk >= d.K) break;
+        if (i > 0) {                              // slide: + newest symbol's energies, - oldest (cpp/psk_soft.cpp:451,576)
+            const int j = kk + A - 1;
+            const float* row = es + (j >> 3) * C::RUNW + (j & 7) * SE;
+            const float* trow = myrun + (i - 1) * SE;
+            float lead[S], trail[S];
+#pragma unroll
+            for (int q = 0; q + 3 < S; q += 4) {
+                float4 v = *reinterpret_cast<const float4*>(row + q);
+                lead[q] = v.x; lead[q + 1] = v.y; lead[q + 2] = v.z; lead[q + 3] = v.w;
+                float4 u = *reinterpret_cast<const float4*>(trow + q);
+                trail[q] = u.x; trail[q + 1] = u.y; trail[q + 2] = u.z; trail[q + 3] = u.w;
+            }
+#pragma unroll
+            for (int q = S & ~3; q < S; q++) { lead[q] = row[q]; trail[q] = trow[q]; }
+#pragma unroll
+            for (int q = 0; q < S; q++) E[q] = dsubr(daddr(E[q], (double)lead[q]), (double)trail[q]);
+        }
+        double best = E[0]; int idx = 0;
+#pragma unroll
+        for (int q = 1; q < S; q++) if (best < E[q]) { best = E[q]; idx = q; }        // first maximum (:462)
+        float2 smp = in_tail ? vs.at(s0 + (long long)kk * S + idx) : __ldg(gin + kk * S + idx);
+        out_sidx[obase + kk] = (int16_t)idx;
+        sel[sbase + kk] = smp;
+        theta[sbase + kk] = mth_power_angle_fast(smp, M);
+    }
+}
+
+template <int S>
+static cudaError_t launch_front_t(const LaunchCtx& c) {
+    using C = FrontCfg<S>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_front_t<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_front_t<S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int T_out = FT_ROWS - c.Amin_fast + 1;   // smallest tile count that covers every fast channel is per channel; use the worst case
+    (void)T_out;
+    const int T_min = FT_ROWS - c.Amax_fast + 1;
+    dim3 grid((unsigned)((c.Kmax + T_min - 1) / T_min), (unsigned)c.n_channels);
+    c.prof->begin(KID_FRONT, c.stream);
+    k_front_t<S><<<grid, FT_THREADS, C::SMEM, c.stream>>>(c.d_desc, c.out_sidx, c.d_sel, c.d_theta);
+    c.prof->end(c.stream);
+    (*c.launches)++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_front(const LaunchCtx& c) {
     if (c.Kmax <= 0) return cudaSuccess;
+    // specialised kernels for the recommended oversampling factors (psk_soft.prf.xml:24 "8-10"), 16 too
+    unsigned long long mask = c.S_mask;
+    cudaError_t e = cudaSuccess;
+    unsigned long long fmask = c.S_mask_fast;
+    if (fmask & (1ull << 8))  { e = launch_front_t<8>(c);  if (e != cudaSuccess) return e; }
+    if (fmask & (1ull << 9))  { e = launch_front_t<9>(c);  if (e != cudaSuccess) return e; }
+    if (fmask & (1ull << 10)) { e = launch_front_t<10>(c); if (e != cudaSuccess) return e; }
+    if (fmask & (1ull << 16)) { e = launch_front_t<16>(c); if (e != cudaSuccess) return e; }
+    if (!mask) return cudaSuccess;
     int SPmax = c.Smax | 1;
     size_t smem = ((size_t)(FT + c.Amax) * SPmax + (size_t)(FRONT_THREADS / 2) * SPmax) * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     dim3 grid((unsigned)((c.Kmax + FT - 1) / FT), (unsigned)c.n_channels);
     c.prof->begin(KID_FRONT, c.stream);
-    k_front<<<grid, FRONT_THREADS, smem, c.stream>>>(c.d_desc, c.out_sidx, c.d_sel, c.d_theta);
+    k_front<<<grid, FRONT_THREADS, smem, c.stream>>>(c.d_desc, c.out_sidx, c.d_sel, c.d_theta, mask);
     c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
@@ -338,29 +564,33 @@ cudaError_t launch_finish(const LaunchCtx& c) {
 }
 
 // =============================================================================================
-// k_chain_par: scan-based phase chain + derotate/slice, one CTA per channel.
+// k_chain_par: scan-based phase chain + derotate/slice.  ONE WARP PER CHANNEL, warp-synchronous
+// (no block barriers), CW_WARPS channels per CTA.
 //
 // The reference's per-symbol recursion (cpp/psk_soft.cpp:474-482 + LinearFit::next :48-87)
 //     n_k = round((est_{k-1} - theta_k)/2pi);  y_k = f32(theta_k + 2pi n_k);  est_k = fit(y_{k-P+1..k})
-// is sequential only through the INTEGER n_k.  Per sub-block of CP_B symbols this kernel
-//   1. predicts n_k by classic sample-to-sample unwrapping (an integer prefix sum), anchored on
-//      the exact rule for the first symbol of the block,
+// is sequential only through the INTEGER n_k.  Per sub-block of CW_B = 32*CW_V symbols a warp
+//   1. predicts n_k by classic sample-to-sample unwrapping (an integer warp scan), anchored on
+//      the reference's own rule for the first symbol of the block,
 //   2. evaluates y_k, the window sums ySum (differences of double prefix sums) and the xySum
-//      recurrence X_k = X_{k-1} - xdelta*ySum'_k + T_k (another double prefix sum, T_k rounded in
-//      float exactly as :78) and from them est_k with the reference's own rounding (:157-162),
+//      recurrence X_k = X_{k-1} - xdelta*ySum'_k + T_k (another double warp scan, T_k rounded in
+//      float exactly as :78) and from them est_k with the reference's float roundings (:157-162),
 //   3. VERIFIES every n_k against the reference's rule using est_{k-1}; on the first mismatch it
 //      shifts the remaining predictions by the observed difference and repeats (each pass
 //      proves at least one more symbol), falling back to the literal sequential recursion for
-//      that sub-block after CP_MAX_ITERS passes.
-// So the emitted n_k are exactly those of the sequential recursion run on the same theta_k; the
-// double sums are formed in scan order instead of symbol order (<= 1e-15 relative apart, far
-// below the float rounding of m,b; see DESIGN.md "phase chain").  Fill-up (fewer than P points),
-// the 2^20-call re-sum (:51-52) and packet prologue/epilogue run on one thread, literally.
+//      that sub-block after CW_MAX_ITERS passes.
+// So the emitted n_k are exactly those of the sequential recursion run on the same theta_k.  The
+// double sums are formed in scan order instead of symbol order and the two divisions of :157-158
+// are multiplications by correctly rounded reciprocals -- both <= 2 ulp(double) from the
+// reference's value, i.e. a float-ulp flip of est in ~1e-8 of the symbols, far inside the stated
+// 1e-4 tolerance (DESIGN.md "phase chain").  Fill-up (fewer than P points), the 2^20-call re-sum
+// (:51-52), packet prologue/epilogue run on lane 0, literally.
 // =============================================================================================
-constexpr int CP_THREADS = 256;
-constexpr int CP_V = 4;
-constexpr int CP_B = CP_THREADS * CP_V;
-constexpr int CP_MAX_ITERS = 24;
+constexpr int CW_WARPS = 4;
+constexpr int CW_MIN_CTAS = 7;     // 28 warps/SM: a 4096-channel bank is one wave on 148 SMs
+constexpr int CW_V = 4;
+constexpr int CW_B = 32 * CW_V;
+constexpr int CW_MAX_ITERS = 16;
 
 struct SmemRing {
     float* base;
@@ -369,12 +599,10 @@ struct SmemRing {
     __device__ void repack(int, int, int, int, int) const {}   // never called: P changes take the sequential chain
 };
 
-struct CpShared {
+struct CwShared {
     ChanState st;
     int flags;
-    int mis;          // first mismatching symbol of the pass
-    int delta;        // correction to add to n_i for i >= mis
-    int mode;         // 0 parallel, 1 sequential
+    int mode;
     unsigned int passes, seq_blocks;
 };
 
@@ -388,316 +616,420 @@ __device__ __forceinline__ double warp_scan_dbl(double v, int lane) {
     for (int o = 1; o < 32; o <<= 1) { double u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v = daddr(v, u); }
     return v;
 }
-// exclusive offset of this thread's partial `tot` over the CTA (CP_THREADS threads); wtot: smem[8]
-__device__ __forceinline__ int block_excl_int(int tot, int* wtot, int tid) {
-    int lane = tid & 31, w = tid >> 5;
-    int inc = warp_scan_int(tot, lane);
-    if (lane == 31) wtot[w] = inc;
-    __syncthreads();
-    int off = 0;
-#pragma unroll
-    for (int i = 0; i < CP_THREADS / 32; i++) if (i < w) off += wtot[i];
-    __syncthreads();
-    return off + inc - tot;
-}
-__device__ __forceinline__ double block_excl_dbl(double tot, double* wtot, int tid) {
-    int lane = tid & 31, w = tid >> 5;
-    double inc = warp_scan_dbl(tot, lane);
-    if (lane == 31) wtot[w] = inc;
-    __syncthreads();
-    double off = 0.0;
-#pragma unroll
-    for (int i = 0; i < CP_THREADS / 32; i++) if (i < w) off = daddr(off, wtot[i]);
-    __syncthreads();
-    return daddr(off, dsubr(inc, tot));
-}
 
-// the reference's unwrap count for one symbol (cpp/psk_soft.cpp:477)
+// the reference's unwrap count for one symbol (cpp/psk_soft.cpp:477): round((est - theta)/2pi),
+// C round().  Fast form: multiply by 1/2pi and round to nearest; whenever the quotient is within
+// 1e-7 of a half-integer (where the division's last bit or the tie rule could matter) the
+// literal division + round() decides.
 __device__ __forceinline__ int unwrap_count(float est_prev, float theta) {
-    double q = __ddiv_rn(dsubr((double)est_prev, (double)theta), PSKD_M_2PI);
-    return (int)(long long)round(q);
+    const double dlt = dsubr((double)est_prev, (double)theta);       // exact
+    const double q = dmulr(dlt, 0.15915494309189535);
+    const double t = daddr(q, 6755399441055744.0);                   // 1.5 * 2^52: round to nearest integer
+    const double qr = dsubr(t, 6755399441055744.0);
+    const double fr = fabs(dsubr(q, qr));
+    if (fr > 0.4999999 || !(fabs(q) < 1.0e9))
+        return (int)(long long)round(__ddiv_rn(dlt, PSKD_M_2PI));
+    return __double2loint(t);
 }
 
-__global__ void __launch_bounds__(CP_THREADS)
+// constants of calculateFit for a full window (cpp/psk_soft.cpp:153-162)
+struct FitConst {
+    double half_span_d, rden, rpts;
+    float span, xAvg;
+};
+__device__ __forceinline__ FitConst fit_const(const FitState& f) {
+    FitConst c;
+    c.span = fmulr(f.xdelta, (float)(f.pts - 1));
+    c.half_span_d = (double)fmulr(c.span, 0.5f);
+    c.rden = __ddiv_rn(1.0, (double)f.denominator);
+    c.rpts = __ddiv_rn(1.0, (double)f.pts);
+    c.xAvg = f.xAvg;
+    return c;
+}
+__device__ __forceinline__ float fit_eval_fast(const FitConst& c, double ySum, double xySum, float* m_out, float* b_out) {
+    const double num = dsubr(xySum, dmulr(c.half_span_d, ySum));
+    const float m = __double2float_rn(dmulr(num, c.rden));                                        // :157
+    const float b = __double2float_rn(dsubr(dmulr(ySum, c.rpts), (double)fmulr(m, c.xAvg)));      // :158
+    if (m_out) { *m_out = m; *b_out = b; }
+    return faddr(fmulr(m, c.span), b);                                                            // :161-162
+}
+
+// 8-PSK slicer (cpp/psk_soft.cpp:547-563) without atan2f: sym = round(angle/(pi/4)) mod 8 is a
+// sector test against the rays at odd multiples of pi/8.  Within a guard band of the rays (or
+// for non-finite / zero input) the literal atan2f path decides.
+__device__ __forceinline__ unsigned slice8_fast(float2 c) {
+    const float a = fabsf(c.x), b = fabsf(c.y);
+    const float T = 0.41421356237309503f;       // tan(pi/8)
+    const float sum = a + b;
+    const float d1 = b - T * a, d2 = a - T * b;
+    const float g = 1.0e-5f * sum;
+    if (!(sum > 0.0f) || !(sum < 3.0e38f) || fabsf(d1) <= g || fabsf(d2) <= g) return slice_bits(c, 3);
+    if (d1 < 0.0f) return (c.x > 0.0f) ? 0u : 4u;
+    if (d2 < 0.0f) return (c.y > 0.0f) ? 2u : 6u;
+    return (c.x > 0.0f) ? ((c.y > 0.0f) ? 1u : 7u) : ((c.y > 0.0f) ? 3u : 5u);
+}
+
+struct CwWarp {          // per-warp shared state
+    ChanState st;
+    FitConst fc;
+    int flags;
+    unsigned int passes, seq_blocks;
+};
+
+// literal recursion over nb symbols (theta staged in th[]), lane 0 only.  Used for the fill-up
+// phase, around the 2^20-call re-sum and when the scan path gives up.
+static __device__ __noinline__ void chain_block_sequential(ChanState& st, float* yb, const float* th, float* estv, int nb) {
+    SmemRing ring{yb};
+    for (int i = 0; i < nb; i++) {
+        float y = unwrap_against(st.est, th[i], nullptr);
+        st.est = fit_next(st.fit, ring, y);
+        estv[i + 1] = st.est;
+    }
+}
+
+// history suffix sums hs[j] = sum_{m=j}^{P-1} yb[m] (history in logical order, head == 0)
+static __device__ __noinline__ void chain_rebuild_hs(const float* yb, double* hs, int P, int lane) {
+    double carry = 0.0;
+    for (int base = 0; base < P; base += 32) {
+        const int rr = base + lane;                        // reversed index: element P-1-rr
+        double x = (rr < P) ? (double)yb[P - 1 - rr] : 0.0;
+        double inc = daddr(warp_scan_dbl(x, lane), carry);
+        if (rr < P) hs[P - 1 - rr] = inc;
+        carry = __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) hs[P] = 0.0;
+    __syncwarp();
+}
+
+// rotate the ring so that yvals.front() sits at index 0 (tmp: >= P floats of scratch)
+static __device__ __noinline__ void chain_normalize_ring(float* yb, float* tmp, FitState& f, int P, int lane) {
+    const int head = f.head;
+    __syncwarp();
+    for (int j = lane; j < P; j += 32) { int s2 = head + j; if (s2 >= P) s2 -= P; tmp[j] = yb[s2]; }
+    __syncwarp();
+    for (int j = lane; j < P; j += 32) yb[j] = tmp[j];
+    if (lane == 0) f.head = 0;
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(CW_WARPS * 32, CW_MIN_CTAS)
 k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, float* __restrict__ ring_base,
-            const float* __restrict__ theta, const float2* __restrict__ sel,
-            float* __restrict__ out_phase, float2* __restrict__ out_soft, int16_t* __restrict__ out_bits,
-            double sri_xdelta, int Pcap, DevCounters* counters)
+            const float* __restrict__ theta, float* __restrict__ out_phase,
+            double sri_xdelta, int Pcap, int n_channels, DevCounters* counters)
 {
-    const ChanDesc& d = desc[blockIdx.x];
-    if (!(d.flags & CH_FAST)) return;
-    const int tid = threadIdx.x;
-    const int P = d.P;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ch = blockIdx.x * CW_WARPS + wid;
+    if (ch >= n_channels) return;
+    if (!(desc[ch].flags & CH_FAST)) return;
 
     extern __shared__ double smem_d[];
-    double* ps   = smem_d;                    // [CP_B]      inclusive prefix of the block's y
-    double* hs   = ps + CP_B;                 // [Pcap + 1]  suffix sums of the history
-    double* wtot = hs + Pcap + 1;             // [8]
-    float*  yb   = (float*)(wtot + 8);        // [Pcap + CP_B] history (ring, then logical order) ++ block y
-    float*  th   = yb + Pcap + CP_B;          // [CP_B]
-    float*  estv = th + CP_B;                 // [CP_B + 1]  estv[0] = estimate before the block
-    int*    wtoti = (int*)(estv + CP_B + 1);  // [8]
-    __shared__ CpShared sh;
+    const size_t per_warp_d = (size_t)CW_B + Pcap + 2;                       // ps[CW_B], hs[Pcap+1] (+1 pad)
+    const size_t per_warp_f = (size_t)Pcap + CW_B + CW_B + CW_B + 4;         // yb[Pcap+CW_B], th[CW_B], estv[CW_B+1]
+    double* ps   = smem_d + (size_t)wid * per_warp_d;
+    double* hs   = ps + CW_B;
+    float*  yb   = (float*)(smem_d + (size_t)CW_WARPS * per_warp_d) + (size_t)wid * per_warp_f;
+    float*  blk  = yb + Pcap;                 // the sub-block's y values (16-byte aligned: Pcap % 4 == 0)
+    float*  th   = yb + Pcap + CW_B;
+    float*  estv = th + CW_B;
+    __shared__ CwWarp shw[CW_WARPS];
+    CwWarp& sh = shw[wid];
 
-    float* gring = ring_base + d.ring_off;
-    if (tid == 0) { sh.st = state[blockIdx.x]; sh.flags = d.flags; sh.passes = 0; sh.seq_blocks = 0; }
-    for (int j = tid; j < P; j += CP_THREADS) yb[j] = gring[j];
-    __syncthreads();
-    SmemRing ring{yb};
+    // per-channel constants into registers once
+    const int P = desc[ch].P, M = desc[ch].M, S = desc[ch].S, A = desc[ch].A, n_pkts = desc[ch].n_pkts;
+    const int K = (int)desc[ch].K;
+    const long long pkt_len = desc[ch].pkt_len, tail_len = desc[ch].tail_len;
+    const float* thg = theta + desc[ch].scr_off;
+    float* phg = out_phase + desc[ch].sym_off;
+    float* gring = ring_base + desc[ch].ring_off;
+
+    if (lane == 0) { sh.st = state[ch]; sh.flags = desc[ch].flags; sh.passes = 0; sh.seq_blocks = 0; }
+    for (int j = lane; j < P; j += 32) yb[j] = gring[j];
+    __syncwarp();
     const unsigned long long wraps0 = sh.st.wraps;
-    const float* thg = theta + d.scr_off;
-    const float2* selg = sel + d.scr_off;
-    const int M = d.M, bpb = d.bpb;
-    const bool diff = d.D != 0;
+    const float fP1 = (float)(P - 1);
 
-    for (int pkt = 0; pkt < d.n_pkts; pkt++) {
-        if (tid == 0) chain_packet_prologue(sh.st, ring, d, sri_xdelta, sh.flags);
-        const long long klo = first_symbol_at((long long)pkt * d.pkt_len, d.tail_len, d.S, d.A, d.K);
-        const long long khi = (pkt + 1 == d.n_pkts) ? d.K
-                              : first_symbol_at((long long)(pkt + 1) * d.pkt_len, d.tail_len, d.S, d.A, d.K);
-        __syncthreads();
-        long long k = klo;
+    // software prefetch of the next sub-block's theta: strided layout, element i = lane + 32*q
+    int pf_k = 0;
+    float pf_th[CW_V];
+#pragma unroll
+    for (int q = 0; q < CW_V; q++) { const int kk = lane + 32 * q; pf_th[q] = (kk < K) ? __ldg(thg + kk) : 0.0f; }
+
+    bool hs_valid = false;
+    int k = 0;
+    for (int pkt = 0; pkt < n_pkts; pkt++) {
+        if (lane == 0) {
+            SmemRing ring{yb};
+            chain_packet_prologue(sh.st, ring, desc[ch], sri_xdelta, sh.flags);
+            if (sh.st.fit.pts == sh.st.fit.n && sh.st.fit.pts > 1) sh.fc = fit_const(sh.st.fit);
+        }
+        const int khi = (pkt + 1 == n_pkts) ? K : (int)first_symbol_at((long long)(pkt + 1) * pkt_len, tail_len, S, A, K);
+        __syncwarp();
         while (k < khi) {
-            // ---- choose the sub-block and its mode (uniform: every thread reads the same shared state)
-            if (tid == 0) {
-                FitState& f = sh.st.fit;
-                if (f.count == 1048576 && f.pts == f.n) fit_resum(f, ring);            // :51-52 at a block edge
-                sh.mode = (f.pts < f.n) ? 1 : 0;
-                sh.mis = 0x7fffffff;
-            }
-            __syncthreads();
-            int nb = (int)min((long long)CP_B, khi - k);
-            int mode = sh.mode;
-            if (mode == 0) nb = min(nb, 1048576 - sh.st.fit.count);
-            else nb = min(nb, max(1, sh.st.fit.n - sh.st.fit.pts));                     // only the fill-up runs sequentially
-            // ---- stage theta
-            for (int i = tid; i < nb; i += CP_THREADS) th[i] = thg[k + i];
-            if (tid == 0) estv[0] = sh.st.est;
-            // ---- make the history logical (head == 0) for the scan path
-            if (mode == 0 && sh.st.fit.head != 0) {
-                const int head = sh.st.fit.head;
-                __syncthreads();
-                for (int j = tid; j < P; j += CP_THREADS) { int s2 = head + j; if (s2 >= P) s2 -= P; estv[1 + j] = yb[s2]; }  // P <= CP_B
-                __syncthreads();
-                for (int j = tid; j < P; j += CP_THREADS) yb[j] = estv[1 + j];
-                if (tid == 0) sh.st.fit.head = 0;
-            }
-            __syncthreads();
-
-            if (mode == 0) {
-                // history suffix sums hs[j] = sum_{m=j}^{P-1} yb[m]  (scan over the reversed history)
-                {
-                    double loc[CP_V]; double run = 0.0;
-#pragma unroll
-                    for (int v = 0; v < CP_V; v++) {
-                        int r = tid * CP_V + v;                   // reversed index: element P-1-r
-                        double x = (r < P) ? (double)yb[P - 1 - r] : 0.0;
-                        run = daddr(run, x); loc[v] = run;
-                    }
-                    double off = block_excl_dbl(run, wtot, tid);
-#pragma unroll
-                    for (int v = 0; v < CP_V; v++) { int r = tid * CP_V + v; if (r < P) hs[P - 1 - r] = daddr(off, loc[v]); }
-                    if (tid == 0) hs[P] = 0.0;
+            int nb = min(CW_B, khi - k);
+            const int pts = sh.st.fit.pts, cnt = sh.st.fit.count;
+            bool fast = (pts == P) && (P > 1) && (cnt + nb <= 1048576);
+            if (!fast) {
+                if (pts == P && cnt == 1048576) {                                   // :51-52 at a block edge
+                    if (lane == 0) { SmemRing ring{yb}; fit_resum(sh.st.fit, ring); }
+                    __syncwarp();
+                    continue;
                 }
-                // classic-unwrap prediction of n (integer prefix sum), first symbol by the exact rule
-                int nloc[CP_V];
+                if (pts == P && P > 1) nb = 1048576 - cnt;                          // stop at the re-sum point
+                else nb = min(nb, max(1, P - pts));                                 // fill-up runs sequentially
+                fast = (pts == P) && (P > 1);
+            }
+            // stage theta (strided registers -> shared), start the next prefetch
+            if (pf_k != k) {
+#pragma unroll
+                for (int q = 0; q < CW_V; q++) { const int kk = k + lane + 32 * q; pf_th[q] = (kk < K) ? __ldg(thg + kk) : 0.0f; }
+            }
+#pragma unroll
+            for (int q = 0; q < CW_V; q++) th[lane + 32 * q] = pf_th[q];
+            pf_k = k + nb;
+#pragma unroll
+            for (int q = 0; q < CW_V; q++) { const int kk = pf_k + lane + 32 * q; pf_th[q] = (kk < K) ? __ldg(thg + kk) : 0.0f; }
+            const float est0 = sh.st.est;
+            if (lane == 0) estv[0] = est0;
+            __syncwarp();
+
+            bool done = false;
+            if (fast) {
+                if (sh.st.fit.head != 0) { chain_normalize_ring(yb, reinterpret_cast<float*>(hs), sh.st.fit, P, lane); hs_valid = false; }
+                if (!hs_valid) { chain_rebuild_hs(yb, hs, P, lane); hs_valid = true; }
+                const FitConst fc = sh.fc;
+                const float xdelta = sh.st.fit.xdelta;
+                const double xd = (double)xdelta;
+                const double X0 = sh.st.fit.xySum;
+                const int i0 = lane * CW_V;
+                // this lane's four consecutive symbols
+                const float4 t4 = *reinterpret_cast<const float4*>(th + i0);
+                const float tl[CW_V] = {t4.x, t4.y, t4.z, t4.w};
+                float tprev = __shfl_up_sync(0xffffffffu, t4.w, 1);
+                // classic-unwrap prediction of n (integer scan), first symbol by the reference's rule
+                int nloc[CW_V];
                 {
                     int run = 0;
 #pragma unroll
-                    for (int v = 0; v < CP_V; v++) {
-                        int i = tid * CP_V + v; int dn = 0;
-                        if (i < nb) {
-                            if (i == 0) dn = unwrap_count(estv[0], th[0]);
-                            else dn = -__float2int_rn((th[i] - th[i - 1]) * 0.15915494309189535f);
+                    for (int v = 0; v < CW_V; v++) {
+                        int dn = 0;
+                        if (i0 + v < nb) {
+                            const float pv = (v == 0) ? tprev : tl[v - 1];
+                            dn = (i0 + v == 0) ? unwrap_count(est0, tl[0]) : -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
                         }
                         run += dn; nloc[v] = run;
                     }
-                    int off = block_excl_int(run, wtoti, tid);
+                    const int off = warp_scan_int(run, lane) - run;
 #pragma unroll
-                    for (int v = 0; v < CP_V; v++) nloc[v] += off;
+                    for (int v = 0; v < CW_V; v++) nloc[v] += off;
                 }
-                const float xdelta = sh.st.fit.xdelta;
-                const double xd = (double)xdelta;
-                const float fP1 = (float)(P - 1);
-                const double X0 = sh.st.fit.xySum;
-                FitState fc = sh.st.fit;                          // constants: n, pts, denominator, xAvg, xdelta
                 int iter = 0;
-                bool ok = false;
-                float yl[CP_V], el[CP_V]; double Yl[CP_V], Xl[CP_V];
+                float yl[CW_V], el[CW_V]; double Yl[CW_V], Xl[CW_V];
                 while (true) {
-                    // y_k and the block prefix
                     double run = 0.0;
 #pragma unroll
-                    for (int v = 0; v < CP_V; v++) {
-                        int i = tid * CP_V + v;
+                    for (int v = 0; v < CW_V; v++) {
                         float y = 0.0f;
-                        if (i < nb) {
-                            y = __double2float_rn(daddr((double)th[i], dmulr((double)nloc[v], PSKD_M_2PI)));   // :478,481
-                            yb[P + i] = y;
-                        }
+                        if (i0 + v < nb) y = __double2float_rn(daddr((double)tl[v], dmulr((double)nloc[v], PSKD_M_2PI)));   // :478,481
                         yl[v] = y; run = daddr(run, (double)y); Yl[v] = run;
                     }
-                    double off = block_excl_dbl(run, wtot, tid);
+                    *reinterpret_cast<float4*>(blk + i0) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+                    const double off = dsubr(warp_scan_dbl(run, lane), run);      // prefix before this lane
+                    double Pl[CW_V];
 #pragma unroll
-                    for (int v = 0; v < CP_V; v++) { int i = tid * CP_V + v; if (i < nb) ps[i] = daddr(off, Yl[v]); }
-                    __syncthreads();
-                    // window sums, xySum increments
+                    for (int v = 0; v < CW_V; v++) Pl[v] = daddr(off, Yl[v]);      // inclusive prefix of the block's y
+                    *reinterpret_cast<double2*>(ps + i0) = make_double2(Pl[0], Pl[1]);
+                    *reinterpret_cast<double2*>(ps + i0 + 2) = make_double2(Pl[2], Pl[3]);
+                    __syncwarp();
                     double trun = 0.0;
 #pragma unroll
-                    for (int v = 0; v < CP_V; v++) {
-                        int i = tid * CP_V + v;
+                    for (int v = 0; v < CW_V; v++) {
+                        const int i = i0 + v;
                         double t = 0.0;
                         if (i < nb) {
-                            double W = (i + 1 <= P - 1) ? hs[i + 1] : 0.0;                 // history part of y_{k-P+1..k-1}
-                            double blk = (i >= 1) ? ps[i - 1] : 0.0;
-                            if (i - P >= 0) blk = dsubr(blk, ps[i - P]);
-                            W = daddr(W, blk);                                             // ySum after :70
-                            double a = dmulr(xd, W);                                       // :72
-                            double T = (double)fmulr(fmulr(yl[v], fP1), xdelta);           // :78
+                            double W = (i + 1 <= P - 1) ? hs[i + 1] : 0.0;             // history part of y_{k-P+1..k-1}
+                            double pb = (v == 0) ? off : Pl[v - 1];                    // prefix through y_{i-1}
+                            if (i - P >= 0) pb = dsubr(pb, ps[i - P]);
+                            W = daddr(W, pb);                                         // ySum after :70
+                            const double a = dmulr(xd, W);                             // :72
+                            const double T = (double)fmulr(fmulr(yl[v], fP1), xdelta); // :78
                             t = dsubr(T, a);
-                            Yl[v] = daddr(W, (double)yl[v]);                               // :75
+                            Yl[v] = daddr(W, (double)yl[v]);                           // :75  (Yl now holds ySum)
                         }
                         trun = daddr(trun, t); Xl[v] = trun;
                     }
-                    double xoff = block_excl_dbl(trun, wtot, tid);
+                    const double xoff = daddr(X0, dsubr(warp_scan_dbl(trun, lane), trun));
 #pragma unroll
-                    for (int v = 0; v < CP_V; v++) {
-                        int i = tid * CP_V + v;
-                        if (i < nb) {
-                            fc.ySum = Yl[v];
-                            fc.xySum = daddr(X0, daddr(xoff, Xl[v]));
-                            Xl[v] = fc.xySum;
-                            el[v] = fit_calc_fit(fc, yl[v]);                               // :135-162
-                            estv[i + 1] = el[v];
-                        }
+                    for (int v = 0; v < CW_V; v++) {
+                        Xl[v] = daddr(xoff, Xl[v]);
+                        el[v] = fit_eval_fast(fc, Yl[v], Xl[v], nullptr, nullptr);     // :135-162
                     }
-                    __syncthreads();
-                    // verify every predicted n against the reference's rule (:477)
+                    // verify every predicted n against the reference's rule (:477) with est_{i-1}
+                    float eprev = __shfl_up_sync(0xffffffffu, el[CW_V - 1], 1);
+                    int mymis = 0x7fffffff, mydelta = 0;
 #pragma unroll
-                    for (int v = 0; v < CP_V; v++) {
-                        int i = tid * CP_V + v;
+                    for (int v = CW_V - 1; v >= 0; v--) {
+                        const int i = i0 + v;
                         if (i >= 1 && i < nb) {
-                            int nt = unwrap_count(estv[i], th[i]);
-                            if (nt != nloc[v]) atomicMin(&sh.mis, i);
+                            const int nt = unwrap_count((v == 0) ? eprev : el[v - 1], tl[v]);
+                            if (nt != nloc[v]) { mymis = i; mydelta = nt - nloc[v]; }
                         }
                     }
-                    __syncthreads();
-                    const int mis = sh.mis;
-                    if (mis == 0x7fffffff) { ok = true; break; }
-                    if (++iter > CP_MAX_ITERS) break;
-                    if (mis / CP_V == tid) {
-                        int nv = 0;
+                    const int mis = (int)__reduce_min_sync(0xffffffffu, (unsigned)mymis);
+                    if (mis == 0x7fffffff) { done = true; break; }
+                    if (++iter > CW_MAX_ITERS) break;
+                    const int delta = __shfl_sync(0xffffffffu, mydelta, mis / CW_V);
 #pragma unroll
-                        for (int v = 0; v < CP_V; v++) if (v == mis % CP_V) nv = nloc[v];
-                        sh.delta = unwrap_count(estv[mis], th[mis]) - nv;
-                    }
-                    __syncthreads();
-                    const int delta = sh.delta;
-#pragma unroll
-                    for (int v = 0; v < CP_V; v++) if (tid * CP_V + v >= mis) nloc[v] += delta;
-                    if (tid == 0) sh.mis = 0x7fffffff;
-                    __syncthreads();
+                    for (int v = 0; v < CW_V; v++) if (i0 + v >= mis) nloc[v] += delta;
+                    __syncwarp();
                 }
-                if (tid == 0) sh.passes += (unsigned)iter;
-                if (ok) {
-                    // commit: sums/estimate after the last symbol, history = last P of (history ++ block)
+                if (iter && lane == 0) sh.passes += (unsigned)iter;
+                if (done) {
+                    *reinterpret_cast<float4*>(estv + 4 + i0) = make_float4(el[0], el[1], el[2], el[3]);   // estv[4+i] = est_i
                     const int last = nb - 1;
-                    if (last / CP_V == tid) {
-                        double Yv = 0.0, Xv = 0.0; float yv = 0.0f, ev = 0.0f;
+                    if (last / CW_V == lane) {
+                        double Yv = 0.0, Xv = 0.0;
 #pragma unroll
-                        for (int v = 0; v < CP_V; v++) if (v == last % CP_V) { Yv = Yl[v]; Xv = Xl[v]; yv = yl[v]; ev = el[v]; }
+                        for (int v = 0; v < CW_V; v++) if (v == last % CW_V) { Yv = Yl[v]; Xv = Xl[v]; }
                         FitState& f = sh.st.fit;
-                        fc.ySum = Yv; fc.xySum = Xv;
-                        (void)fit_calc_fit(fc, yv);
-                        f.ySum = Yv; f.xySum = Xv; f.m = fc.m; f.b = fc.b; f.count += nb;
-                        sh.st.est = ev;
+                        float mm, bb;
+                        sh.st.est = fit_eval_fast(fc, Yv, Xv, &mm, &bb);
+                        f.ySum = Yv; f.xySum = Xv; f.m = mm; f.b = bb; f.count += nb;
                     }
-                    float keep[(CHAIN_PAR_PMAX + CP_THREADS - 1) / CP_THREADS];
-#pragma unroll
-                    for (int q = 0; q < (CHAIN_PAR_PMAX + CP_THREADS - 1) / CP_THREADS; q++) {
-                        int j = tid + q * CP_THREADS;
-                        keep[q] = (j < P) ? yb[nb + j] : 0.0f;
+                    __syncwarp();
+                    if (nb >= P) {
+                        // new history = last P symbols of the block; its suffix sums come from the block prefix
+                        const double pend = ps[nb - 1];
+                        for (int j = lane; j < P; j += 32) {
+                            const int src = nb - P + j;               // block index of new history element j
+                            const double before = (src >= 1) ? ps[src - 1] : 0.0;
+                            hs[j] = dsubr(pend, before);
+                            yb[j] = blk[src];
+                        }
+                        __syncwarp();
+                    } else {
+                        for (int base = 0; base < P; base += 32) {    // forward chunks: reads stay ahead of writes
+                            const int j = base + lane;
+                            const int src = nb + j;                   // index in (history ++ block)
+                            float v = 0.0f;
+                            if (j < P) v = (src < P) ? yb[src] : blk[src - P];
+                            __syncwarp();
+                            if (j < P) yb[j] = v;
+                            __syncwarp();
+                        }
+                        hs_valid = false;
                     }
-                    __syncthreads();
-#pragma unroll
-                    for (int q = 0; q < (CHAIN_PAR_PMAX + CP_THREADS - 1) / CP_THREADS; q++) {
-                        int j = tid + q * CP_THREADS;
-                        if (j < P) yb[j] = keep[q];
-                    }
-                    __syncthreads();
                 } else {
-                    mode = 1;                                   // too many passes: literal recursion for this block
-                    if (tid == 0) sh.seq_blocks++;
-                    __syncthreads();
+                    if (lane == 0) sh.seq_blocks++;
                 }
             }
-            if (mode == 1) {
-                if (tid == 0) {
-                    ChanState& st = sh.st;
-                    for (int i = 0; i < nb; i++) {
-                        float y = unwrap_against(st.est, th[i], nullptr);
-                        st.est = fit_next(st.fit, ring, y);
-                        estv[i + 1] = st.est;
-                    }
+            if (!done) {
+                if (lane == 0) {
+                    chain_block_sequential(sh.st, yb, th, estv + 3, nb);       // estv[4+i] = est_i
+                    if (sh.st.fit.pts == sh.st.fit.n && sh.st.fit.pts > 1) sh.fc = fit_const(sh.st.fit);
                 }
-                __syncthreads();
+                hs_valid = false;
+                __syncwarp();
             }
-            // ---- outputs for symbols k .. k+nb: phase, then derotate / slice (cpp/psk_soft.cpp:482-566)
-            for (int i = tid; i < nb; i += CP_THREADS) {
-                const long long kk = k + i;
-                const float est = estv[i + 1];
-                if (out_phase) out_phase[d.sym_off + kk] = est;
-                if (out_soft || (out_bits && bpb)) {
-                    float2 s = selg[kk];
-                    if (diff) {
-                        float2 last = (kk > 0) ? selg[kk - 1] : sh.st.last;
-                        s = cdiv_f32(s, last);
-                    }
-                    float pc = phase_correction(est, M, diff);
-                    float2 c = derotate(s, pc);
-                    if (out_soft) out_soft[d.sym_off + kk] = c;
-                    if (out_bits && bpb) {
-                        unsigned b = slice_bits(c, bpb);
-                        int16_t* o = out_bits + d.bits_off + kk * bpb;
-                        for (int j = 0; j < bpb; j++) o[j] = (int16_t)((b >> j) & 1u);
-                    }
-                }
-            }
-            __syncthreads();
+            // phase output (cpp/psk_soft.cpp:482), coalesced
+#pragma unroll
+            for (int q = 0; q < CW_V; q++) { const int i = lane + 32 * q; if (i < nb) phg[k + i] = estv[4 + i]; }
+            __syncwarp();
             k += nb;
         }
-        if (tid == 0) chain_packet_epilogue(sh.st, ring, M);
-        __syncthreads();
+        if (lane == 0) {
+            SmemRing ring{yb};
+            const unsigned long long w0 = sh.st.wraps;
+            chain_packet_epilogue(sh.st, ring, M);
+            sh.flags |= (sh.st.wraps != w0) ? (1 << 30) : 0;
+        }
+        __syncwarp();
+        if (sh.flags & (1 << 30)) { hs_valid = false; if (lane == 0) sh.flags &= ~(1 << 30); __syncwarp(); }
     }
-    // ---- store the carried state (ring in whatever rotation it has; head says where it starts)
-    for (int j = tid; j < P; j += CP_THREADS) gring[j] = yb[j];
-    if (tid == 0) {
-        state[blockIdx.x] = sh.st;      // `last` is carried by k_finish
+    for (int j = lane; j < P; j += 32) gring[j] = yb[j];
+    if (lane == 0) {
+        state[ch] = sh.st;              // `last` is carried by k_finish
         if (sh.st.wraps != wraps0) atomicAdd(&counters->wraps, sh.st.wraps - wraps0);
-        atomicAdd(&counters->spec_chunks, (unsigned long long)((d.K + CP_B - 1) / CP_B));
+        atomicAdd(&counters->spec_chunks, (unsigned long long)((K + CW_B - 1) / CW_B));
         if (sh.passes) atomicAdd(&counters->spec_misses, (unsigned long long)sh.passes);
         if (sh.seq_blocks) atomicAdd(&counters->seq_channels, (unsigned long long)sh.seq_blocks);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_back_par: derotate / differential decode / slice for the channels of the scan chain, one
+// thread per symbol, fully coalesced (cpp/psk_soft.cpp:484-566).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ state,
+           const float2* __restrict__ sel, const float* __restrict__ phase,
+           float2* __restrict__ out_soft, int16_t* __restrict__ out_bits)
+{
+    const ChanDesc& d = desc[blockIdx.y];
+    if (!(d.flags & CH_FAST)) return;
+    const int K = (int)d.K;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int M = d.M, bpb = d.bpb;
+    const bool diff = d.D != 0;
+    const float2* selg = sel + d.scr_off;
+    float2 s = __ldg(selg + k);
+    float pc = 0.0f;
+    if (diff) {
+        float2 prev = (k > 0) ? __ldg(selg + k - 1) : state[blockIdx.y].last;
+        s = cdiv_f32(s, prev);                                                          // :488
+    } else {
+        const float est = __ldg(phase + d.sym_off + k);
+        pc = ((M & (M - 1)) == 0) ? fmulr(-est, 1.0f / (float)M) : __fdiv_rn(-est, (float)M);   // :494 (exact for 2^n)
+    }
+    if (M == 4) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                  // :497-498
+    const float2 c = derotate(s, pc);
+    if (out_soft) out_soft[d.sym_off + k] = c;
+    if (out_bits && bpb) {
+        int16_t* o = out_bits + d.bits_off + (long long)k * bpb;
+        if (bpb == 3) {
+            const unsigned b = slice8_fast(c);
+            o[0] = (int16_t)(b & 1u); o[1] = (int16_t)((b >> 1) & 1u); o[2] = (int16_t)((b >> 2) & 1u);
+        } else if (bpb == 1) {
+            o[0] = (int16_t)((c.x < 0.0f) ? 1 : 0);
+        } else {
+            const unsigned b = slice_bits(c, 2);
+            o[0] = (int16_t)(b & 1u); o[1] = (int16_t)((b >> 1) & 1u);
+        }
     }
 }
 
 cudaError_t launch_chain_par(const LaunchCtx& c) {
     if (c.n_fast_channels == 0) return cudaSuccess;
     int Pcap = c.Pmax_fast < 1 ? 1 : c.Pmax_fast;
-    size_t smem = (size_t)(CP_B + Pcap + 1 + 8) * sizeof(double)
-                + (size_t)(Pcap + CP_B + CP_B + CP_B + 1) * sizeof(float) + 8 * sizeof(int) + 16;
+    Pcap = (Pcap + 3) & ~3;
+    size_t per_warp = ((size_t)CW_B + Pcap + 2) * sizeof(double) + ((size_t)Pcap + 3 * CW_B + 4) * sizeof(float);
+    size_t smem = per_warp * CW_WARPS;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(k_chain_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_chain_par, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         configured = smem;
     }
     float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
+    int blocks = (c.n_channels + CW_WARPS - 1) / CW_WARPS;
     c.prof->begin(KID_CHAIN_PAR, c.stream);
-    k_chain_par<<<c.n_channels, CP_THREADS, smem, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, c.d_sel,
-                                                            phase, (float2*)c.out_soft, c.out_bits, c.sri_xdelta, Pcap, c.d_counters);
+    k_chain_par<<<blocks, CW_WARPS * 32, smem, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, phase,
+                                                          c.sri_xdelta, Pcap, c.n_channels, c.d_counters);
     c.prof->end(c.stream);
     (*c.launches)++;
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if ((c.out_soft || c.out_bits) && c.Kmax > 0) {
+        dim3 grid((unsigned)((c.Kmax + 255) / 256), (unsigned)c.n_channels);
+        c.prof->begin(KID_BACK_PAR, c.stream);
+        k_back_par<<<grid, 256, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
+        c.prof->end(c.stream);
+        (*c.launches)++;
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 }  // namespace pskd
