@@ -235,12 +235,33 @@ k_front_t(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
         const bool vec_ok = !in_tail && ((reinterpret_cast<uintptr_t>(gin) & 15) == 0) && (S % 2 == 0);
         if (vec_ok && avail >= (long long)FT_ROWS * S) {
             const float4* g4 = reinterpret_cast<const float4*>(gin);
+            if constexpr ((2 * FT_THREADS) % (8 * S) == 0) {
+                // every step of FT_THREADS chunks covers a whole number of 8-row runs: the shared
+                // address advances by a constant, no per-chunk division
+                constexpr int ROWS_PER_STEP = 2 * FT_THREADS / S;
+                constexpr int STEP_WORDS = (ROWS_PER_STEP / 8) * C::RUNW;
+                const int j0 = (2 * tid) / S, p0 = 2 * tid - j0 * S;
+                float* dst = es + (j0 >> 3) * C::RUNW + (j0 & 7) * SE + p0;
+                const float4* src = g4 + tid;
+                constexpr int NIT = NCHUNK / FT_THREADS, UN = 16;
+                static_assert(NIT % UN == 0, "staging unroll");
+                for (int it0 = 0; it0 < NIT; it0 += UN) {
+                    float4 x[UN];
+#pragma unroll
+                    for (int u = 0; u < UN; u++) x[u] = __ldg(src + (it0 + u) * FT_THREADS);   // UN x 16 B in flight per thread
+#pragma unroll
+                    for (int u = 0; u < UN; u++)
+                        *reinterpret_cast<float2*>(dst + (it0 + u) * STEP_WORDS) =
+                            make_float2(energy_f32(x[u].x, x[u].y), energy_f32(x[u].z, x[u].w));
+                }
+            } else {
 #pragma unroll 8
-            for (int c = tid; c < NCHUNK; c += FT_THREADS) {
-                float4 x = __ldg(g4 + c);
-                const int smp = 2 * c, j = smp / S, p = smp - j * S;
-                float2 e = make_float2(energy_f32(x.x, x.y), energy_f32(x.z, x.w));
-                *reinterpret_cast<float2*>(es + (j >> 3) * C::RUNW + (j & 7) * SE + p) = e;
+                for (int c = tid; c < NCHUNK; c += FT_THREADS) {
+                    float4 x = __ldg(g4 + c);
+                    const int smp = 2 * c, j = smp / S, p = smp - j * S;
+                    float2 e = make_float2(energy_f32(x.x, x.y), energy_f32(x.z, x.w));
+                    *reinterpret_cast<float2*>(es + (j >> 3) * C::RUNW + (j & 7) * SE + p) = e;
+                }
             }
         } else {
             for (int smp = tid; smp < FT_ROWS * S; smp += FT_THREADS) {
@@ -295,60 +316,96 @@ k_front_t(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
         }
     }
 #pragma unroll
-    for (int q = 0; q < S; q++) pbr[r * S + q] = pin[q];
+    for (int q = 0; q < S; q++) pbr[q * FT_THREADS + r] = pin[q];        // phase-major: lanes hit consecutive banks
     __syncthreads();
 
     // ---- window sums of this run's symbols ----------------------------------------------------------
     const int kk0 = r * FT_R;                     // tile-local index of this run's first symbol
-    if (kk0 >= T_out || k0 + kk0 >= d.K) return;
+    const int n_tile = (int)min((long long)T_out, d.K - k0);      // symbols this tile emits
+    const int nvalid = min(FT_R, n_tile - kk0);   // symbols of this run that are emitted (<= 0: none)
     const int nq = A / FT_R, rem = A - nq * FT_R;
-    double E[S];
-    if (nq >= 1) {
-        const double* hi = pbr + (r + nq - 1) * S;     // runs r .. r+nq-1 = prefix[r+nq-1] - (prefix[r] - own sum)
+    int   oi[FT_R]; float2 os[FT_R]; float ot[FT_R];
+    if (nvalid > 0) {
+        double E[S];
+        if (nq >= 1) {
+            const double* hi = pbr + (r + nq - 1);         // runs r .. r+nq-1 = prefix[r+nq-1] - (prefix[r] - own sum)
 #pragma unroll
-        for (int q = 0; q < S; q++) E[q] = daddr(dsubr(hi[q], pin[q]), bs[q]);
-    } else {
+            for (int q = 0; q < S; q++) E[q] = daddr(dsubr(hi[q * FT_THREADS], pin[q]), bs[q]);
+        } else {
 #pragma unroll
-        for (int q = 0; q < S; q++) E[q] = 0.0;
-    }
-    {
-        const int jr = kk0 + nq * FT_R;           // first of the `rem` extra rows
-        for (int i = 0; i < rem; i++) {
-            const int j = jr + i;
-            const float* row = es + (j >> 3) * C::RUNW + (j & 7) * SE;
-#pragma unroll
-            for (int q = 0; q < S; q++) E[q] = daddr(E[q], (double)row[q]);
+            for (int q = 0; q < S; q++) E[q] = 0.0;
         }
-    }
-    const long long obase = d.sym_off + k0, sbase = d.scr_off + k0;
+        {
+            const int jr = kk0 + nq * FT_R;           // first of the `rem` extra rows
+            for (int i = 0; i < rem; i++) {
+                const int j = jr + i;
+                const float* row = es + (j >> 3) * C::RUNW + (j & 7) * SE;
 #pragma unroll
-    for (int i = 0; i < FT_R; i++) {
-        const int kk = kk0 + i;
-        if (kk >= T_out || k0 + kk >= d.K) break;
-        if (i > 0) {                              // slide: + newest symbol's energies, - oldest (cpp/psk_soft.cpp:451,576)
-            const int j = kk + A - 1;
-            const float* row = es + (j >> 3) * C::RUNW + (j & 7) * SE;
-            const float* trow = myrun + (i - 1) * SE;
-            float lead[S], trail[S];
-#pragma unroll
-            for (int q = 0; q + 3 < S; q += 4) {
-                float4 v = *reinterpret_cast<const float4*>(row + q);
-                lead[q] = v.x; lead[q + 1] = v.y; lead[q + 2] = v.z; lead[q + 3] = v.w;
-                float4 u = *reinterpret_cast<const float4*>(trow + q);
-                trail[q] = u.x; trail[q + 1] = u.y; trail[q + 2] = u.z; trail[q + 3] = u.w;
+                for (int q = 0; q < S; q++) E[q] = daddr(E[q], (double)row[q]);
             }
-#pragma unroll
-            for (int q = S & ~3; q < S; q++) { lead[q] = row[q]; trail[q] = trow[q]; }
-#pragma unroll
-            for (int q = 0; q < S; q++) E[q] = dsubr(daddr(E[q], (double)lead[q]), (double)trail[q]);
         }
-        double best = E[0]; int idx = 0;
 #pragma unroll
-        for (int q = 1; q < S; q++) if (best < E[q]) { best = E[q]; idx = q; }        // first maximum (:462)
-        float2 smp = in_tail ? vs.at(s0 + (long long)kk * S + idx) : __ldg(gin + kk * S + idx);
-        out_sidx[obase + kk] = (int16_t)idx;
-        sel[sbase + kk] = smp;
-        theta[sbase + kk] = mth_power_angle_fast(smp, M);
+        for (int i = 0; i < FT_R; i++) {
+            if (i < nvalid) {
+                const int kk = kk0 + i;
+                if (i > 0) {                              // slide: + newest symbol's energies, - oldest (cpp/psk_soft.cpp:451,576)
+                    const int j = kk + A - 1;
+                    const float* row = es + (j >> 3) * C::RUNW + (j & 7) * SE;
+                    const float* trow = myrun + (i - 1) * SE;
+                    float lead[S], trail[S];
+#pragma unroll
+                    for (int q = 0; q + 3 < S; q += 4) {
+                        float4 v = *reinterpret_cast<const float4*>(row + q);
+                        lead[q] = v.x; lead[q + 1] = v.y; lead[q + 2] = v.z; lead[q + 3] = v.w;
+                        float4 u = *reinterpret_cast<const float4*>(trow + q);
+                        trail[q] = u.x; trail[q + 1] = u.y; trail[q + 2] = u.z; trail[q + 3] = u.w;
+                    }
+#pragma unroll
+                    for (int q = S & ~3; q < S; q++) { lead[q] = row[q]; trail[q] = trow[q]; }
+#pragma unroll
+                    for (int q = 0; q < S; q++) E[q] = dsubr(daddr(E[q], (double)lead[q]), (double)trail[q]);
+                }
+                double best = E[0]; int idx = 0;
+#pragma unroll
+                for (int q = 1; q < S; q++) if (best < E[q]) { best = E[q]; idx = q; }        // first maximum (:462)
+                oi[i] = idx;
+            }
+        }
+        // gather the chosen sample of every symbol of the run (:465): all loads in flight together
+#pragma unroll
+        for (int i = 0; i < FT_R; i++) {
+            if (i < nvalid) {
+                const int kk = kk0 + i;
+                os[i] = in_tail ? vs.at(s0 + (long long)kk * S + oi[i]) : __ldg(gin + kk * S + oi[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < FT_R; i++) if (i < nvalid) ot[i] = mth_power_angle_fast(os[i], M);   // :474
+    }
+    // ---- stage the outputs in shared memory (the energy rows are dead now) and write them coalesced
+    __syncthreads();
+    // element kk lives at kk + (kk >> 3): one pad per run so the per-run (stride-8) writes spread over the banks
+    constexpr int OPAD = FT_ROWS + FT_ROWS / 8;
+    float2* s_sel = reinterpret_cast<float2*>(es);            // [OPAD]
+    float*  s_th  = es + 2 * OPAD;                            // [OPAD]
+    short*  s_idx = reinterpret_cast<short*>(es + 3 * OPAD);  // [OPAD]
+    if (nvalid > 0) {
+#pragma unroll
+        for (int i = 0; i < FT_R; i++) {
+            if (i < nvalid) { const int pos = kk0 + i + r; s_sel[pos] = os[i]; s_th[pos] = ot[i]; s_idx[pos] = (short)oi[i]; }
+        }
+    }
+    __syncthreads();
+    {
+        int16_t* g_idx = out_sidx + d.sym_off + k0;
+        float2* g_sel = sel + d.scr_off + k0;
+        float* g_th = theta + d.scr_off + k0;
+        for (int t = tid; t < n_tile; t += FT_THREADS) {
+            const int pos = t + (t >> 3);
+            g_sel[t] = s_sel[pos];
+            g_th[t] = s_th[pos];
+            g_idx[t] = s_idx[pos];
+        }
     }
 }
 
@@ -959,7 +1016,11 @@ k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, fl
 // k_back_par: derotate / differential decode / slice for the channels of the scan chain, one
 // thread per symbol, fully coalesced (cpp/psk_soft.cpp:484-566).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int BP_THREADS = 256;
+constexpr int BP_V = 4;                       // symbols per thread: 4 x 12 B of loads in flight
+constexpr int BP_TILE = BP_THREADS * BP_V;
+
+__global__ void __launch_bounds__(BP_THREADS)
 k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ state,
            const float2* __restrict__ sel, const float* __restrict__ phase,
            float2* __restrict__ out_soft, int16_t* __restrict__ out_bits)
@@ -967,34 +1028,60 @@ k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ stat
     const ChanDesc& d = desc[blockIdx.y];
     if (!(d.flags & CH_FAST)) return;
     const int K = (int)d.K;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
+    const int k0 = blockIdx.x * BP_TILE;
+    if (k0 >= K) return;
+    __shared__ short sb[BP_TILE * 3];
     const int M = d.M, bpb = d.bpb;
     const bool diff = d.D != 0;
     const float2* selg = sel + d.scr_off;
-    float2 s = __ldg(selg + k);
-    float pc = 0.0f;
-    if (diff) {
-        float2 prev = (k > 0) ? __ldg(selg + k - 1) : state[blockIdx.y].last;
-        s = cdiv_f32(s, prev);                                                          // :488
-    } else {
-        const float est = __ldg(phase + d.sym_off + k);
-        pc = ((M & (M - 1)) == 0) ? fmulr(-est, 1.0f / (float)M) : __fdiv_rn(-est, (float)M);   // :494 (exact for 2^n)
-    }
-    if (M == 4) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                  // :497-498
-    const float2 c = derotate(s, pc);
-    if (out_soft) out_soft[d.sym_off + k] = c;
-    if (out_bits && bpb) {
-        int16_t* o = out_bits + d.bits_off + (long long)k * bpb;
-        if (bpb == 3) {
-            const unsigned b = slice8_fast(c);
-            o[0] = (int16_t)(b & 1u); o[1] = (int16_t)((b >> 1) & 1u); o[2] = (int16_t)((b >> 2) & 1u);
-        } else if (bpb == 1) {
-            o[0] = (int16_t)((c.x < 0.0f) ? 1 : 0);
-        } else {
-            const unsigned b = slice_bits(c, 2);
-            o[0] = (int16_t)(b & 1u); o[1] = (int16_t)((b >> 1) & 1u);
+    const float* phg = phase + d.sym_off;
+    float2* softg = out_soft ? out_soft + d.sym_off : nullptr;
+    const float inv_m = 1.0f / (float)M;
+    const bool m_pow2 = (M & (M - 1)) == 0;
+
+    float2 sv[BP_V], pv[BP_V]; float ev[BP_V];
+#pragma unroll
+    for (int v = 0; v < BP_V; v++) {              // all loads first
+        const int k = k0 + threadIdx.x + v * BP_THREADS;
+        sv[v] = make_float2(0.f, 0.f); pv[v] = sv[v]; ev[v] = 0.f;
+        if (k < K) {
+            sv[v] = __ldg(selg + k);
+            if (diff) pv[v] = (k > 0) ? __ldg(selg + k - 1) : state[blockIdx.y].last;
+            else ev[v] = __ldg(phg + k);
         }
+    }
+#pragma unroll
+    for (int v = 0; v < BP_V; v++) {
+        const int kl = threadIdx.x + v * BP_THREADS, k = k0 + kl;
+        if (k < K) {
+            float2 s = sv[v];
+            float pc = 0.0f;
+            if (diff) s = cdiv_f32(s, pv[v]);                                                   // :488
+            else pc = m_pow2 ? fmulr(-ev[v], inv_m) : __fdiv_rn(-ev[v], (float)M);               // :494 (exact for 2^n)
+            if (M == 4) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                  // :497-498
+            const float2 c = derotate(s, pc);
+            if (softg) softg[k] = c;
+            unsigned b = 0;
+            if (bpb == 3) b = slice8_fast(c);
+            else if (bpb == 1) b = (c.x < 0.0f) ? 1u : 0u;
+            else if (bpb == 2) b = slice_bits(c, 2);
+            short* o = sb + kl * bpb;
+            for (int j = 0; j < bpb; j++) o[j] = (short)((b >> j) & 1u);
+        }
+    }
+    if (!out_bits || !bpb) return;
+    __syncthreads();
+    // bits_dataShort_out: one short per bit, LSB first (cpp/psk_soft.cpp:512,525-526,559-563), written coalesced
+    const int nsh = min(BP_TILE, K - k0) * bpb;
+    int16_t* o = out_bits + d.bits_off + (long long)k0 * bpb;
+    if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+        const int n2 = nsh >> 1;
+        const int* s2 = reinterpret_cast<const int*>(sb);
+        int* o2 = reinterpret_cast<int*>(o);
+        for (int t = threadIdx.x; t < n2; t += BP_THREADS) o2[t] = s2[t];
+        if ((nsh & 1) && threadIdx.x == 0) o[nsh - 1] = sb[nsh - 1];
+    } else {
+        for (int t = threadIdx.x; t < nsh; t += BP_THREADS) o[t] = sb[t];
     }
 }
 
@@ -1022,9 +1109,9 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if ((c.out_soft || c.out_bits) && c.Kmax > 0) {
-        dim3 grid((unsigned)((c.Kmax + 255) / 256), (unsigned)c.n_channels);
+        dim3 grid((unsigned)((c.Kmax + BP_TILE - 1) / BP_TILE), (unsigned)c.n_channels);
         c.prof->begin(KID_BACK_PAR, c.stream);
-        k_back_par<<<grid, 256, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
+        k_back_par<<<grid, BP_THREADS, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
         c.prof->end(c.stream);
         (*c.launches)++;
         e = cudaGetLastError();
