@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpskd.so")
 SOURCES = ["pskd_api.cu", "pskd_kernels.cu", "pskd_synth.cu"]
-HEADERS = ["pskd_exact.cuh", "pskd_internal.h", os.path.join("..", "..", "include", "pskd.h")]
+HEADERS = ["pskd_exact.cuh", "pskd_internal.h", os.path.join("..", "..", "include", "pskd.h"),
+           os.path.join("..", "host", "psk_soft_gpu.hpp"), os.path.join("..", "host", "demo_component.cpp")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
 
@@ -47,7 +48,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    build_host_demo()
     return LIB_PATH
+
+
+def build_host_demo() -> str:
+    """Compile the C++ host mirror's demo against libpskd.so (checks psk_soft_gpu.hpp builds as plain C++11)."""
+    host = os.path.join(HERE, "host")
+    exe = os.path.join(LIB_DIR, "demo_component")
+    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-pthread", "-o", exe, os.path.join(host, "demo_component.cpp"),
+           "-L" + LIB_DIR, "-lpskd", "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed on the host mirror:\n" + res.stdout + res.stderr)
+    return exe
 
 
 if __name__ == "__main__":
