@@ -170,7 +170,7 @@ def run_reference(args, w):
         device_ok = torch.cuda.is_available()
     except Exception:
         device_ok = False
-    ch = min(w["channels"], max(cores * 4, 16))
+    ch = min(w["channels"], 512)
     n = min(w["samples"], 1_000_000) if w["channels"] > 1 else min(w["samples"], 8_000_000)
     iq = host_sample(w, ch, n, seed=1234, device_ok=device_ok)
     for _ in range(args.warmup):
@@ -295,7 +295,8 @@ def main():
     if kern:
         K = n // S
         own = {"k_front": nch * (8 * n + 2 * K), "k_fused": algorithmic_bytes(w, nch, n),
-               "k_back": nch * K * (8 + 2 * bpb)}            # each kernel's own share of the algorithmic bytes
+               "k_chain_par": nch * K * 4, "k_chain_seq": nch * K * 4,
+               "k_back_par": nch * K * (8 + 2 * bpb), "k_back": nch * K * (8 + 2 * bpb)}   # each kernel's own share of the algorithmic bytes
         dom = max(kern, key=lambda k: kern[k][0])
         ms_launch = kern[dom][0] / max(kern[dom][1], 1)
         launches_per_step = kern[dom][1] / args.steps
@@ -356,7 +357,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        cch = min(nch, max(16, cores * 4))
+        cch = min(nch, 512)                      # ~20-30 core-seconds of reference CPU work
         cn = n if nch > 1 else min(n, 16_000_000)
         iq_h = iq[:cch, :cn].contiguous().cpu().numpy().view(np.complex64).reshape(cch, cn)
         rate, kind, secs = cpu_demod_rate(w, iq_h, cores)

@@ -76,7 +76,7 @@ def load(build_if_missing: bool = True):
     if not os.path.isfile(_build.LIB_PATH):
         raise ImportError(f"{_build.LIB_PATH} is missing: the CUDA extension was not built "
                           "(run `python -m psk_soft_b200._build`); there is no CPU fallback")
-    lib = C.CDLL(_build.LIB_PATH)
+    lib = C.CDLL(os.environ.get("PSKD_LIB") or _build.LIB_PATH)   # PSKD_LIB: tuning builds only
     H = C.c_void_p
     lib.pskd_default_props.argtypes = [C.POINTER(Props)]; lib.pskd_default_props.restype = None
     lib.pskd_create.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.POINTER(Props)]; lib.pskd_create.restype = C.c_int

@@ -87,6 +87,8 @@ struct pskd_bank {
     DevBuf<float> st_in; DevBuf<float> st_soft; DevBuf<float> st_phase; DevBuf<int16_t> st_bits; DevBuf<int16_t> st_sidx;
     unsigned long long launches = 0;
     pskd_stats stats{};
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host-buffer mode: H2D / D2H overlap the kernels slab by slab
+    cudaEvent_t slab_in[16] = {nullptr}, slab_done[16] = {nullptr};
     int chain_mode = 0;        // 0 auto (scan-based where possible), 1 force the sequential chain (PSKD_CHAIN=seq)
     Profiler prof;
 };
@@ -191,6 +193,12 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     cudaError_t e;
 #define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
     CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CT(cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
+    CT(cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; i++) {
+        CT(cudaEventCreateWithFlags(&b->slab_in[i], cudaEventDisableTiming));
+        CT(cudaEventCreateWithFlags(&b->slab_done[i], cudaEventDisableTiming));
+    }
     CT(cudaMalloc((void**)&b->d_desc, sizeof(ChanDesc) * n_channels));
     for (int i = 0; i < 2; i++) {
         CT(cudaMallocHost((void**)&b->h_desc_slot[i], sizeof(ChanDesc) * n_channels));
@@ -231,6 +239,9 @@ int pskd_destroy(pskd_handle b) {
     b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
     b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release();
     b->prof.destroy();
+    for (int i = 0; i < 16; i++) { if (b->slab_in[i]) cudaEventDestroy(b->slab_in[i]); if (b->slab_done[i]) cudaEventDestroy(b->slab_done[i]); }
+    if (b->copy_in) cudaStreamDestroy(b->copy_in);
+    if (b->copy_out) cudaStreamDestroy(b->copy_out);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
     return PSKD_OK;
@@ -415,15 +426,12 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     CUDA_TRY(b->sel.reserve((size_t)scr_total + 4));
     CUDA_TRY(b->theta.reserve((size_t)scr_total + 4));
     float* dev_soft = out->soft; float* dev_phase = out->phase; int16_t* dev_bits = out->bits; int16_t* dev_sidx = out->sample_index;
-    size_t sym_stride = out->sym_stride, bits_stride = out->bits_stride;
+    size_t sym_stride = out->sym_stride, bits_stride = out->bits_stride, in_stride = 0;
     if (host_bufs) {
         // stage through device buffers with the caller's strides squeezed to what this call needs
         sym_stride = (size_t)((Kmax + 7) & ~7LL); bits_stride = sym_stride * 3;
-        const size_t in_stride = (size_t)((nmax + 1) & ~1LL);
+        in_stride = (size_t)((nmax + 1) & ~1LL);
         CUDA_TRY(b->st_in.reserve(2 * in_stride * nch + 4));
-        if (nmax > 0)
-            CUDA_TRY(cudaMemcpy2DAsync(b->st_in.p, in_stride * 8, in->iq, in->iq_stride * 8, (size_t)nmax * 8, nch,
-                                       cudaMemcpyHostToDevice, b->stream));
         if (out->soft) { CUDA_TRY(b->st_soft.reserve(2 * sym_stride * nch + 4)); dev_soft = b->st_soft.p; }
         if (out->phase) { CUDA_TRY(b->st_phase.reserve(sym_stride * nch + 4)); dev_phase = b->st_phase.p; }
         if (out->bits) { CUDA_TRY(b->st_bits.reserve(bits_stride * nch + 4)); dev_bits = b->st_bits.p; }
@@ -449,11 +457,47 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;
     L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches; L.prof = &b->prof;
 
-    CUDA_TRY(launch_front(L));
-    CUDA_TRY(launch_chain_par(L));
-    CUDA_TRY(launch_chain_seq(L));
-    CUDA_TRY(launch_back(L));
-    CUDA_TRY(launch_finish(L));
+    if (!host_bufs) {
+        CUDA_TRY(launch_front(L));
+        CUDA_TRY(launch_chain_par(L));
+        CUDA_TRY(launch_chain_seq(L));
+        CUDA_TRY(launch_back(L));
+        CUDA_TRY(launch_finish(L));
+    } else {
+        // host buffers: channel slabs flow H2D (copy_in) -> kernels (stream) -> D2H (copy_out), so the
+        // PCIe transfers of neighbouring slabs overlap the kernels (channels are independent)
+        const int n_slabs = std::min(nch, nmax * (long long)nch >= (1 << 22) ? 8 : 1);
+        for (int s = 0; s < n_slabs; s++) {
+            const int lo = (int)((long long)s * nch / n_slabs), hi = (int)((long long)(s + 1) * nch / n_slabs);
+            if (nmax > 0)
+                CUDA_TRY(cudaMemcpy2DAsync(b->st_in.p + 2 * in_stride * lo, in_stride * 8, in->iq + 2 * in->iq_stride * lo,
+                                           in->iq_stride * 8, (size_t)nmax * 8, hi - lo, cudaMemcpyHostToDevice, b->copy_in));
+            CUDA_TRY(cudaEventRecord(b->slab_in[s], b->copy_in));
+        }
+        for (int s = 0; s < n_slabs; s++) {
+            const int lo = (int)((long long)s * nch / n_slabs), hi = (int)((long long)(s + 1) * nch / n_slabs);
+            LaunchCtx Ls = L;
+            Ls.d_desc = b->d_desc + lo; Ls.d_state = b->d_state + lo; Ls.n_channels = hi - lo;
+            CUDA_TRY(cudaStreamWaitEvent(b->stream, b->slab_in[s], 0));
+            CUDA_TRY(launch_front(Ls));
+            CUDA_TRY(launch_chain_par(Ls));
+            CUDA_TRY(launch_chain_seq(Ls));
+            CUDA_TRY(launch_back(Ls));
+            CUDA_TRY(launch_finish(Ls));
+            CUDA_TRY(cudaEventRecord(b->slab_done[s], b->stream));
+            CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->slab_done[s], 0));
+            if (Kmax > 0) {
+                const size_t rows = (size_t)(hi - lo);
+                if (out->soft) CUDA_TRY(cudaMemcpy2DAsync(out->soft + 2 * out->sym_stride * lo, out->sym_stride * 8, dev_soft + 2 * sym_stride * lo, sym_stride * 8, (size_t)Kmax * 8, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                if (out->phase) CUDA_TRY(cudaMemcpy2DAsync(out->phase + out->sym_stride * lo, out->sym_stride * 4, dev_phase + sym_stride * lo, sym_stride * 4, (size_t)Kmax * 4, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                if (out->sample_index) CUDA_TRY(cudaMemcpy2DAsync(out->sample_index + out->sym_stride * lo, out->sym_stride * 2, dev_sidx + sym_stride * lo, sym_stride * 2, (size_t)Kmax * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                if (out->bits) {
+                    size_t w = std::min((size_t)Kmax * 3, out->bits_stride);
+                    CUDA_TRY(cudaMemcpy2DAsync(out->bits + out->bits_stride * lo, out->bits_stride * 2, dev_bits + bits_stride * lo, bits_stride * 2, w * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                }
+            }
+        }
+    }
 
     // ---- host-side bookkeeping (what the reference's members hold after the packets) ------------
     for (int i = 0; i < nch; i++) {
@@ -480,15 +524,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     b->tail_cur = next_tail;
 
     if (host_bufs) {
-        if (Kmax > 0) {
-            if (out->soft) CUDA_TRY(cudaMemcpy2DAsync(out->soft, out->sym_stride * 8, dev_soft, sym_stride * 8, (size_t)Kmax * 8, nch, cudaMemcpyDeviceToHost, b->stream));
-            if (out->phase) CUDA_TRY(cudaMemcpy2DAsync(out->phase, out->sym_stride * 4, dev_phase, sym_stride * 4, (size_t)Kmax * 4, nch, cudaMemcpyDeviceToHost, b->stream));
-            if (out->sample_index) CUDA_TRY(cudaMemcpy2DAsync(out->sample_index, out->sym_stride * 2, dev_sidx, sym_stride * 2, (size_t)Kmax * 2, nch, cudaMemcpyDeviceToHost, b->stream));
-            if (out->bits) {
-                size_t w = std::min((size_t)Kmax * 3, out->bits_stride);
-                CUDA_TRY(cudaMemcpy2DAsync(out->bits, out->bits_stride * 2, dev_bits, bits_stride * 2, w * 2, nch, cudaMemcpyDeviceToHost, b->stream));
-            }
-        }
+        CUDA_TRY(cudaStreamSynchronize(b->copy_out));
         CUDA_TRY(cudaStreamSynchronize(b->stream));
     } else if (!(in->flags & PSKD_FLAG_NO_SYNC)) {
         CUDA_TRY(cudaStreamSynchronize(b->stream));

@@ -201,8 +201,11 @@ template <int S> struct FrontCfg {
     static constexpr size_t SMEM = (size_t)E_WORDS * 4 + (size_t)(PB_DOUBLES + PBR_DOUBLES) * 8;
 };
 
+#ifndef PSKD_FT_MIN_CTAS
+#define PSKD_FT_MIN_CTAS 5
+#endif
 template <int S>
-__global__ void __launch_bounds__(FT_THREADS)
+__global__ void __launch_bounds__(FT_THREADS, PSKD_FT_MIN_CTAS)
 k_front_t(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
           float2* __restrict__ sel, float* __restrict__ theta)
 {
@@ -644,7 +647,10 @@ cudaError_t launch_finish(const LaunchCtx& c) {
 // (:51-52), packet prologue/epilogue run on lane 0, literally.
 // =============================================================================================
 constexpr int CW_WARPS = 4;
-constexpr int CW_MIN_CTAS = 7;     // 28 warps/SM: a 4096-channel bank is one wave on 148 SMs
+#ifndef PSKD_CW_MIN_CTAS
+#define PSKD_CW_MIN_CTAS 7
+#endif
+constexpr int CW_MIN_CTAS = PSKD_CW_MIN_CTAS;     // 28 warps/SM: a 4096-channel bank is one wave on 148 SMs
 constexpr int CW_V = 4;
 constexpr int CW_B = 32 * CW_V;
 constexpr int CW_MAX_ITERS = 16;
@@ -1017,7 +1023,10 @@ k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, fl
 // thread per symbol, fully coalesced (cpp/psk_soft.cpp:484-566).
 // ---------------------------------------------------------------------------------------------
 constexpr int BP_THREADS = 256;
-constexpr int BP_V = 4;                       // symbols per thread: 4 x 12 B of loads in flight
+#ifndef PSKD_BP_V
+#define PSKD_BP_V 4
+#endif
+constexpr int BP_V = PSKD_BP_V;               // symbols per thread: BP_V x 12 B of loads in flight
 constexpr int BP_TILE = BP_THREADS * BP_V;
 
 __global__ void __launch_bounds__(BP_THREADS)
