@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpskd.so")
-SOURCES = ["pskd_api.cu", "pskd_kernels.cu", "pskd_synth.cu"]
-HEADERS = ["pskd_exact.cuh", "pskd_internal.h", os.path.join("..", "..", "include", "pskd.h"),
+SOURCES = ["pskd_api.cu", "pskd_kernels.cu", "pskd_fused.cu", "pskd_synth.cu"]
+HEADERS = ["pskd_exact.cuh", "pskd_internal.h", "pskd_device.cuh", os.path.join("..", "..", "include", "pskd.h"),
            os.path.join("..", "host", "psk_soft_gpu.hpp"), os.path.join("..", "host", "demo_component.cpp")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]

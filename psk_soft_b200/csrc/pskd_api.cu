@@ -90,6 +90,12 @@ struct pskd_bank {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host-buffer mode: H2D / D2H overlap the kernels slab by slab
     cudaEvent_t slab_in[16] = {nullptr}, slab_done[16] = {nullptr};
     int chain_mode = 0;        // 0 auto (scan-based where possible), 1 force the sequential chain (PSKD_CHAIN=seq)
+    int fused_mode = -1;       // -1 auto (large banks), 0 never, 1 whenever a channel qualifies (PSKD_FUSED)
+    int fused_min_channels = 1024;   // auto: channels per launch from which the fused kernel fills the GPU (PSKD_FUSED_MIN)
+    int* d_list = nullptr;     // fused launch lists (channel indices), one segment per (slab, samplesPerBaud)
+    int* h_list_slot[2] = {nullptr, nullptr};
+    int* d_done = nullptr;     // [n_channels] units completed per channel in the current call
+    int* d_ticket = nullptr;   // [16 slabs x 4 samplesPerBaud values] unit ticket counters
     Profiler prof;
 };
 
@@ -190,6 +196,8 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
         b->ch[i].fit_n = b->ch[i].props.phaseAvg;
     }
     if (const char* e = getenv("PSKD_CHAIN")) b->chain_mode = (strcmp(e, "seq") == 0) ? 1 : 0;
+    if (const char* e = getenv("PSKD_FUSED")) b->fused_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
+    if (const char* e = getenv("PSKD_FUSED_MIN")) b->fused_min_channels = std::max(1, atoi(e));
     cudaError_t e;
 #define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
     CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
@@ -202,8 +210,12 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     CT(cudaMalloc((void**)&b->d_desc, sizeof(ChanDesc) * n_channels));
     for (int i = 0; i < 2; i++) {
         CT(cudaMallocHost((void**)&b->h_desc_slot[i], sizeof(ChanDesc) * n_channels));
+        CT(cudaMallocHost((void**)&b->h_list_slot[i], sizeof(int) * n_channels));
         CT(cudaEventCreateWithFlags(&b->desc_ev[i], cudaEventDisableTiming));
     }
+    CT(cudaMalloc((void**)&b->d_list, sizeof(int) * n_channels));
+    CT(cudaMalloc((void**)&b->d_done, sizeof(int) * n_channels));
+    CT(cudaMalloc((void**)&b->d_ticket, sizeof(int) * 64));
     b->h_desc = b->h_desc_slot[0];
     CT(cudaMalloc((void**)&b->d_state, sizeof(ChanState) * n_channels));
     CT(cudaMalloc((void**)&b->d_counters, sizeof(DevCounters)));
@@ -233,7 +245,8 @@ int pskd_destroy(pskd_handle b) {
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_desc);
-    for (int i = 0; i < 2; i++) { if (b->h_desc_slot[i]) cudaFreeHost(b->h_desc_slot[i]); if (b->desc_ev[i]) cudaEventDestroy(b->desc_ev[i]); }
+    for (int i = 0; i < 2; i++) { if (b->h_desc_slot[i]) cudaFreeHost(b->h_desc_slot[i]); if (b->h_list_slot[i]) cudaFreeHost(b->h_list_slot[i]); if (b->desc_ev[i]) cudaEventDestroy(b->desc_ev[i]); }
+    cudaFree(b->d_list); cudaFree(b->d_done); cudaFree(b->d_ticket);
     cudaFree(b->d_state); cudaFree(b->d_counters); cudaFree(b->d_ring);
     cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]);
     b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
@@ -367,6 +380,15 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     int Amax_fast = 1, Amin_fast = 1 << 30;
     bool any_nobits = false;
     const int next_tail = b->tail_cur ^ 1;
+    // host-buffer mode works through slabs of channels (H2D / kernels / D2H overlap); the fused
+    // kernel is chosen per launch, i.e. per slab
+    int n_slabs = 1;
+    if (host_bufs) {
+        long long nm = 0;
+        for (int i = 0; i < nch; i++) nm = std::max(nm, (long long)(in->n_complex ? in->n_complex[i] : in->n_complex_all));
+        n_slabs = std::min(nch, nm * (long long)nch >= (1 << 22) ? 8 : 1);
+    }
+    std::vector<unsigned char> fusable(nch, 0);
     for (int i = 0; i < nch; i++) {
         ChanHost& c = b->ch[i];
         const long long n_in = (long long)(in->n_complex ? in->n_complex[i] : in->n_complex_all);
@@ -399,28 +421,61 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         if (d.next_tail_len > c.tail_cap) return fail(PSKD_ERR_UNSUPPORTED, "channel %d: carried window exceeds its capacity", i);
         d.sym_off = (long long)i * (long long)out->sym_stride;
         d.bits_off = (long long)i * (long long)out->bits_stride;
-        d.scr_off = scr_total;
         d.pkt_len = pkt; d.n_pkts = (int)npk;
         d.S = S; d.A = A; d.M = M; d.P = P; d.D = c.props.differentialDecoding ? 1 : 0; d.bpb = bpb_of(M);
         d.ring_off = i * b->ring_cap;
         d.flags = (c.resetNumSymbols ? CH_RESET_NUMSYMS : 0) | (c.resetPhaseAvg ? CH_RESET_PHASEAVG : 0);
         // the scan-based chain needs the history staged in shared memory and an unchanged window length
         const bool fast = b->chain_mode == 0 && P <= CHAIN_PAR_PMAX && c.fit_n == P;
-        if (fast) { d.flags |= CH_FAST; n_fast++; Pmax_fast = std::max(Pmax_fast, P); } else n_seq++;
+        if (fast) d.flags |= CH_FAST;
+        fusable[i] = fast && b->fused_mode != 0 && fused_supports(S, A, P) && K < (1LL << 30);
         if (d.bpb == 0) any_nobits = true;
         if ((size_t)K > out->sym_stride && (out->soft || out->phase || out->sample_index))
             return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld symbols > sym_stride %zu", i, K, out->sym_stride);
         if (out->bits && (size_t)(K * d.bpb) > out->bits_stride)
             return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld bits > bits_stride %zu", i, K * d.bpb, out->bits_stride);
-        scr_total += (K + 3) & ~3LL;
         Kmax = std::max(Kmax, K); nmax = std::max(nmax, n_in);
-        Smax = std::max(Smax, S); Amax = std::max(Amax, A);
-        if (K > 0) {
-            const bool front_fast = (S == 8 || S == 9 || S == 10 || S == 16) && A <= FRONT_FAST_AMAX;
-            if (front_fast) { d.flags |= CH_FRONT_FAST; S_mask_fast |= 1ull << S; Amax_fast = std::max(Amax_fast, A); Amin_fast = std::min(Amin_fast, A); }
-            else S_mask |= 1ull << S;
+    }
+    // ---- which channels take the fused kernel (per slab), which the staged kernels --------------
+    struct FusedSeg { int slab, S, first, count, Amax, Pmax, max_pkts; long long pkt_len_min; };
+    std::vector<FusedSeg> segs;
+    int* h_list = b->h_list_slot[b->desc_slot];
+    int n_listed = 0;
+    static const int fusedS[4] = {8, 9, 10, 16};
+    for (int s = 0; s < n_slabs; s++) {
+        const int lo = (int)((long long)s * nch / n_slabs), hi = (int)((long long)(s + 1) * nch / n_slabs);
+        int nf = 0;
+        for (int i = lo; i < hi; i++) nf += fusable[i];
+        const bool use = nf > 0 && (b->fused_mode == 1 || nf >= b->fused_min_channels);
+        if (!use) continue;
+        for (int si = 0; si < 4; si++) {
+            FusedSeg g{s, fusedS[si], n_listed, 0, 1, 1, 0, 1LL << 62};
+            for (int i = lo; i < hi; i++) {
+                ChanDesc& d = b->h_desc[i];
+                if (!fusable[i] || d.S != g.S) continue;
+                d.flags |= CH_FUSED;
+                h_list[n_listed++] = i - lo;
+                g.count++; g.Amax = std::max(g.Amax, d.A); g.Pmax = std::max(g.Pmax, d.P);
+                g.max_pkts = std::max(g.max_pkts, d.n_pkts);
+                if (d.n_pkts > 0) g.pkt_len_min = std::min(g.pkt_len_min, d.pkt_len);
+            }
+            if (g.count) segs.push_back(g);
         }
     }
+    for (int i = 0; i < nch; i++) {
+        ChanDesc& d = b->h_desc[i];
+        if (d.flags & CH_FUSED) { d.scr_off = 0; continue; }
+        if (d.flags & CH_FAST) { n_fast++; Pmax_fast = std::max(Pmax_fast, d.P); } else n_seq++;
+        d.scr_off = scr_total;
+        scr_total += (d.K + 3) & ~3LL;
+        Smax = std::max(Smax, d.S); Amax = std::max(Amax, d.A);
+        if (d.K > 0) {
+            const bool front_fast = (d.S == 8 || d.S == 9 || d.S == 10 || d.S == 16) && d.A <= FRONT_FAST_AMAX;
+            if (front_fast) { d.flags |= CH_FRONT_FAST; S_mask_fast |= 1ull << d.S; Amax_fast = std::max(Amax_fast, d.A); Amin_fast = std::min(Amin_fast, d.A); }
+            else S_mask |= 1ull << d.S;
+        }
+    }
+    const bool any_staged = (n_fast + n_seq) > 0;
 
     // ---- buffers ------------------------------------------------------------------------------
     CUDA_TRY(b->sel.reserve((size_t)scr_total + 4));
@@ -443,10 +498,15 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             d.bits_off = (long long)i * (long long)bits_stride;
         }
     }
-    if (!dev_phase) { CUDA_TRY(b->phase_tmp.reserve(sym_stride * nch + 4)); }
+    if (!dev_phase && any_staged) { CUDA_TRY(b->phase_tmp.reserve(sym_stride * nch + 4)); }
     if (!dev_sidx) { CUDA_TRY(b->sidx_tmp.reserve(sym_stride * nch + 4)); dev_sidx = b->sidx_tmp.p; }
 
     CUDA_TRY(cudaMemcpyAsync(b->d_desc, b->h_desc, sizeof(ChanDesc) * nch, cudaMemcpyHostToDevice, b->stream));
+    if (n_listed > 0) {
+        CUDA_TRY(cudaMemcpyAsync(b->d_list, h_list, sizeof(int) * n_listed, cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int) * nch, b->stream));
+        CUDA_TRY(cudaMemsetAsync(b->d_ticket, 0, sizeof(int) * 64, b->stream));
+    }
     CUDA_TRY(cudaEventRecord(b->desc_ev[b->desc_slot], b->stream));
 
     LaunchCtx L{};
@@ -457,16 +517,37 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;
     L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches; L.prof = &b->prof;
 
+    // the kernels of one slab of channels [lo, hi)
+    auto run_slab = [&](const LaunchCtx& Ls, int slab, int lo) -> int {
+        for (const FusedSeg& g : segs) {
+            if (g.slab != slab) continue;
+            FusedLaunch f{};
+            f.S = g.S; f.d_list = b->d_list + g.first; f.n_list = g.count;
+            // a unit = enough consecutive packets for >= ~4096 symbols
+            const long long ppu = std::max<long long>(1, (4096LL * g.S + g.pkt_len_min - 1) / g.pkt_len_min);
+            f.pkts_per_unit = (int)std::min<long long>(ppu, 1 << 20);
+            f.units_per_channel = (g.max_pkts + f.pkts_per_unit - 1) / f.pkts_per_unit;
+            if ((long long)f.units_per_channel * g.count > 0x7fffffffLL) return fail(PSKD_ERR_ARG, "too many packets");
+            f.Amax = g.Amax; f.Pmax = g.Pmax;
+            f.d_ticket = b->d_ticket + (slab * 4 + (g.S == 8 ? 0 : g.S == 9 ? 1 : g.S == 10 ? 2 : 3));
+            f.d_done = b->d_done + lo;
+            CUDA_TRY(launch_fused(Ls, f));
+        }
+        if (any_staged) {
+            CUDA_TRY(launch_front(Ls));
+            CUDA_TRY(launch_chain_par(Ls));
+            CUDA_TRY(launch_chain_seq(Ls));
+            CUDA_TRY(launch_back(Ls));
+        }
+        CUDA_TRY(launch_finish(Ls));
+        return PSKD_OK;
+    };
     if (!host_bufs) {
-        CUDA_TRY(launch_front(L));
-        CUDA_TRY(launch_chain_par(L));
-        CUDA_TRY(launch_chain_seq(L));
-        CUDA_TRY(launch_back(L));
-        CUDA_TRY(launch_finish(L));
+        rc = run_slab(L, 0, 0);
+        if (rc != PSKD_OK) return rc;
     } else {
         // host buffers: channel slabs flow H2D (copy_in) -> kernels (stream) -> D2H (copy_out), so the
         // PCIe transfers of neighbouring slabs overlap the kernels (channels are independent)
-        const int n_slabs = std::min(nch, nmax * (long long)nch >= (1 << 22) ? 8 : 1);
         for (int s = 0; s < n_slabs; s++) {
             const int lo = (int)((long long)s * nch / n_slabs), hi = (int)((long long)(s + 1) * nch / n_slabs);
             if (nmax > 0)
@@ -479,11 +560,8 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             LaunchCtx Ls = L;
             Ls.d_desc = b->d_desc + lo; Ls.d_state = b->d_state + lo; Ls.n_channels = hi - lo;
             CUDA_TRY(cudaStreamWaitEvent(b->stream, b->slab_in[s], 0));
-            CUDA_TRY(launch_front(Ls));
-            CUDA_TRY(launch_chain_par(Ls));
-            CUDA_TRY(launch_chain_seq(Ls));
-            CUDA_TRY(launch_back(Ls));
-            CUDA_TRY(launch_finish(Ls));
+            rc = run_slab(Ls, s, lo);
+            if (rc != PSKD_OK) return rc;
             CUDA_TRY(cudaEventRecord(b->slab_done[s], b->stream));
             CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->slab_done[s], 0));
             if (Kmax > 0) {

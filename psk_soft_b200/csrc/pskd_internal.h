@@ -28,9 +28,12 @@ struct ChanDesc {
 };
 enum { CH_RESET_NUMSYMS = 1, CH_RESET_PHASEAVG = 2, CH_SRI_CHANGED = 4,
        CH_FAST = 8 /* phase chain + back run in k_chain_par (scan-based), else k_chain_seq + k_back */,
-       CH_FRONT_FAST = 16 /* timing runs in k_front_t<S>, else in the generic k_front */ };
+       CH_FRONT_FAST = 16 /* timing runs in k_front_t<S>, else in the generic k_front */,
+       CH_FUSED = 32 /* the whole path of this channel runs in k_fused<S> (pskd_fused.cu); the staged kernels skip it */ };
 constexpr int FRONT_FAST_AMAX = 768;   // largest numAvg the specialised front tile (1024 symbols) still uses efficiently
-constexpr int CHAIN_PAR_PMAX = 1024;   // largest phaseAvg the scan-based chain stages in shared memory
+constexpr int CHAIN_PAR_PMAX = 1024;
+constexpr int FUSED_AMAX = 256;        // largest numAvg whose energy ring the fused kernel keeps in shared memory
+constexpr int FUSED_PMAX = 128;        // largest phaseAvg of the fused kernel's chain blocks   // largest phaseAvg the scan-based chain stages in shared memory
 
 // Carried phase-tracking state of one channel (cpp/psk_soft.h:70-85 minus the timing deques).
 struct ChanState {
@@ -56,7 +59,7 @@ __host__ __device__ inline long long first_symbol_at(long long x, long long tail
 }
 
 // ---- optional per-kernel event timing --------------------------------------------------------
-enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_COUNT };
+enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_FUSED, KID_COUNT };
 struct Profiler {
     bool enabled = false;
     struct Pair { cudaEvent_t a, b; int kid; };
@@ -93,6 +96,19 @@ struct LaunchCtx {
     unsigned long long* launches;   // host counter
     Profiler* prof;
 };
+
+// one launch of the fused kernel: the CH_FUSED channels of one samplesPerBaud value
+struct FusedLaunch {
+    int S;
+    const int* d_list; int n_list;     // channel indices (relative to LaunchCtx::d_desc)
+    int units_per_channel;             // ceil(max n_pkts / pkts_per_unit)
+    int pkts_per_unit;
+    int Amax, Pmax;                    // over the listed channels (sizes the shared-memory regions)
+    int* d_ticket;                     // one int, zero before the launch
+    int* d_done;                       // [n_channels] zero before the launch (indexed like d_desc)
+};
+bool fused_supports(int S, int A, int P);
+cudaError_t launch_fused(const LaunchCtx& c, const FusedLaunch& f);
 
 cudaError_t launch_front(const LaunchCtx& c);
 cudaError_t launch_chain_seq(const LaunchCtx& c);

@@ -9,6 +9,13 @@ from parity import assert_parity
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["1", "0"], ids=["fused", "staged"], autouse=True)
+def fused_mode(request, monkeypatch):
+    """every bank test runs through the fused kernel and through the staged kernels"""
+    monkeypatch.setenv("PSKD_FUSED", request.param)
+    return request.param
+
+
 def _run_bank(pk, torch, props, nch, n, cuts, seed, packet_len=16000):
     from psk_soft_b200 import binding as B
     S = props["samplesPerBaud"]

@@ -14,6 +14,13 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.n
 PROP_NAMES = ("samplesPerBaud", "numAvg", "constelationSize", "phaseAvg", "differentialDecoding")
 
 
+@pytest.fixture(params=["1", "0"], ids=["fused", "staged"], autouse=True)
+def fused_mode(request, monkeypatch):
+    """every test of this module runs through the fused kernel and through the staged kernels"""
+    monkeypatch.setenv("PSKD_FUSED", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
 def test_gpu_matches_golden(path):
     import psk_soft_b200 as pk

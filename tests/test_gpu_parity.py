@@ -23,10 +23,12 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["par", "seq"])
+@pytest.fixture(params=["fused", "par", "seq"])
 def chain_mode(request, monkeypatch):
-    """run every case through the scan-based chain and through the literal sequential chain"""
-    monkeypatch.setenv("PSKD_CHAIN", request.param)
+    """run every case through the fused kernel (where the configuration qualifies), the staged
+    kernels with the scan-based chain, and the staged kernels with the literal sequential chain"""
+    monkeypatch.setenv("PSKD_CHAIN", "par" if request.param == "fused" else request.param)
+    monkeypatch.setenv("PSKD_FUSED", "1" if request.param == "fused" else "0")
     return request.param
 
 
@@ -108,10 +110,12 @@ LOW_SNR = [
 ]
 
 
+@pytest.mark.parametrize("fused", ["1", "0"], ids=["fused", "staged"])
 @pytest.mark.parametrize("t", LOW_SNR, ids=lambda t: f"M{t['M']}sig{t['sig']}")
-def test_low_snr_unwrap_repairs(t, oracle_built, monkeypatch):
+def test_low_snr_unwrap_repairs(t, fused, oracle_built, monkeypatch):
     import psk_soft_b200 as pk
     monkeypatch.setenv("PSKD_CHAIN", "par")
+    monkeypatch.setenv("PSKD_FUSED", fused)
     iq = siggen.gen_shaped(t["n"], t["S"], t["M"], seed=21, sigma=t["sig"], freq=t["f"], timing_shift=1)
     ref = oracle_built.OracleComponent(**_props(t)).demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
     dev = pk.PskSoft(**_props(t))
