@@ -1,6 +1,6 @@
 // pskd_fused.cu -- the whole demod path of one channel in ONE kernel pass (sm_100a).
 //
-//   k_fused<S>   ingest + symbol timing + M-th power angle + unwrap/LinearFit chain + derotate /
+//   k_fused<S,..> ingest + symbol timing + M-th power angle + unwrap/LinearFit chain + derotate /
 //                differential decode / slice, per channel, with every intermediate (energies,
 //                window sums, selected samples, angles, unwrapped phases) living in shared memory
 //                or registers.  HBM sees only the algorithmic bytes: each IQ sample read once,
@@ -20,13 +20,16 @@
 //            (:451, :576), an exclusive scan over the row groups adds the carried window sum; the
 //            sums are transposed through shared memory so that lane = row takes the FIRST maximum
 //            over the phases (:462), gathers that sample of the window's oldest symbol (:465,
-//            an L2 hit: the row was streamed numAvg-1 rows ago) and forms atan2f(s^M) (:474)
+//            an L2 hit: the row was streamed numAvg-1 rows ago; consumed one chunk later so the
+//            latency is hidden) and forms atan2f(s^M) (:474)
 //   chain  : every 128 symbols (or at a packet end): classic-unwrap prediction of the integer
 //            unwrap counts, double prefix sums for LinearFit's ySum / xySum, point-wise verification
 //            of every count against the reference's rule round((est_{k-1}-theta_k)/2pi) (:477) and
 //            repair -- the emitted integers are exactly those of the sequential recursion
 //   back   : derotate by -est/M (+pi/4) or divide by the previous sample (:484-501), slice
 //            (:503-566); phase, soft and bits are staged in shared memory and written coalesced.
+// The chain + back stage is one non-inlined function (fz_drain) so that it gets its own register
+// allocation; everything it shares with the chunk loop lives in the warp's FzCtx in shared memory.
 #include "pskd_internal.h"
 #include "pskd_device.cuh"
 
@@ -41,6 +44,28 @@ constexpr int FZ_MAX_ITERS = 16;
 #define PSKD_FZ_MIN_CTAS 5
 #endif
 
+struct FzCtx {                         // one per warp, shared memory
+    ChanState st;
+    FitConst fc;
+    const float2* in_mt;               // in - tail_len: virtual sample v >= tail_len lives at in_mt[v]
+    const float2* tail;
+    const ChanDesc* desc;
+    float2* o_soft; float* o_phase; int16_t* o_bits;       // this channel's output rows (or null)
+    double sri_xdelta;
+    long long tail_len, pkt_len;
+    int n_pkts, pk1, K, A, M, P, bpb, diff;
+    int pkt, pk_hi, kchain, nbuf, cz_valid, unit_done, flags;
+    unsigned int passes, seq_blocks, blocks;
+    float fP1;
+    // chunk-loop constants of the unit (parked here to keep the loop's register set small)
+    int kA, kB, lag, RR, NS, tc, c_lo, c_hi, nchunks, gather_in, ch, ug;
+    long long V;
+    int16_t* o_sidx;
+    unsigned long long wraps0;
+};
+
+constexpr int fz_align16(int x) { return (x + 15) & ~15; }
+
 template <int S> struct FzCfg {
     static constexpr int G = 32 / S;                         // row groups (lane = g*S + p)
     static constexpr int R = (32 + G - 1) / G;               // rows per group
@@ -51,18 +76,22 @@ template <int S> struct FzCfg {
     static_assert(!PADDED || (32 % R) == 0, "padded groups must tile a chunk");
     __host__ __device__ static constexpr int fpos(int pos) { return pos * S + (PADDED ? (pos / R) * PAD : 0); }
     __host__ __device__ static constexpr int ring_rows(int A) { return ((A - 1 + 32 + 31) / 32) * 32; }
-    __host__ __device__ static constexpr int ring_floats(int A) { return (fpos(ring_rows(A) + R) + 3) & ~3; }
 };
 
-struct FzLayout {          // byte offsets inside one warp's shared-memory region
-    int off_th, off_sel, off_yh, off_st, off_cz, off_alias, bytes;
-};
-
-struct FzWarp {
-    ChanState st;
-    FitConst fc;
-    int flags;
-    unsigned int passes, seq_blocks, blocks;
+// compile-time layout of one warp's shared-memory region.  RRC = ring capacity in rows (covers
+// numAvg <= RRC - 31), PC = phaseAvg capacity.
+template <int S, int RRC, int PC> struct FzL {
+    using C = FzCfg<S>;
+    static constexpr int RING_F = (C::fpos(RRC + C::R) + 3) & ~3;
+    static constexpr int OFF_TH = RING_F * 4;                              // float  th[FZ_BUF]
+    static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                    // float2 selb[FZ_BUF + 2]; [1] = previous sample
+    static constexpr int OFF_YH = fz_align16(OFF_SEL + (FZ_BUF + 2) * 8);  // float  yh[PC]   y history, logical order
+    static constexpr int OFF_CTX = fz_align16(OFF_YH + PC * 4);
+    static constexpr int OFF_CZ = fz_align16(OFF_CTX + (int)sizeof(FzCtx));// double cz[PC + 1], ends where ALIAS starts
+    static constexpr int OFF_ALIAS = OFF_CZ + fz_align16((PC + 1) * 8);
+    static constexpr int E_BYTES = 32 * C::ES * 8;                         // ingest phase: window sums [32][ES]
+    static constexpr int C_BYTES = FZ_B * 8 + FZ_B * 4 + (FZ_B + 4) * 4;   // chain phase: prefix block, y block, est block
+    static constexpr int BYTES = OFF_ALIAS + fz_align16(E_BYTES > C_BYTES ? E_BYTES : C_BYTES);
 };
 
 struct FusedParams {
@@ -74,30 +103,10 @@ struct FusedParams {
     int* done;                         // [n_channels] units completed per channel (zeroed before the launch)
     float2* out_soft; int16_t* out_bits; float* out_phase; int16_t* out_sidx;
     double sri_xdelta;
-    int Pcap;
-    FzLayout lay;
     DevCounters* counters;
 };
 
-template <int S>
-static FzLayout fz_layout(int Amax, int Pcap) {
-    using C = FzCfg<S>;
-    FzLayout L;
-    int o = C::ring_floats(Amax) * 4;
-    L.off_th = o;                      o += FZ_BUF * 4;
-    L.off_sel = o;                     o += (FZ_BUF + 2) * 8;
-    o = (o + 15) & ~15;
-    L.off_yh = o;                      o += Pcap * 4;
-    o = (o + 15) & ~15;
-    L.off_st = o;                      o += (int)((sizeof(FzWarp) + 15) & ~15);
-    L.off_cz = o;                      o += ((Pcap + 1) * 8 + 15) & ~15;
-    L.off_alias = o;
-    int e = 32 * C::ES * 8;                          // window-sum transposition buffer
-    int c = FZ_B * 8 + FZ_B * 4 + (FZ_B + 4) * 4;    // chain: prefix block, y block, est block
-    o += ((e > c ? e : c) + 15) & ~15;
-    L.bytes = o;
-    return L;
-}
+extern __shared__ __align__(16) unsigned char fz_smem[];
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -133,538 +142,806 @@ static __device__ __noinline__ void fz_normalize_ring(float* yh, float* tmp, Fit
     __syncwarp();
 }
 
-static __device__ __noinline__ void fz_block_sequential(ChanState& st, float* yh, const float* th, float* estv, int nb) {
+// literal recursion (lane 0): fill-up, around the 2^20-call re-sum, and when the scan path gives up
+static __device__ __noinline__ void fz_block_sequential(FzCtx& cx, float* yh, const float* th, float* estv, int nb) {
     SmemRing ring{yh};
+    ChanState st = cx.st;
     for (int i = 0; i < nb; i++) {
         float y = unwrap_against(st.est, th[i], nullptr);
         st.est = fit_next(st.fit, ring, y);
         estv[i] = st.est;
     }
+    cx.st = st;
+    if (st.fit.pts == st.fit.n && st.fit.pts > 1) cx.fc = fit_const(st.fit);
 }
 
+// packet prologue of the phase estimator (cpp/psk_soft.cpp:393-426), lane 0
+static __device__ __noinline__ void fz_prologue(FzCtx& cx, float* yh) {
+    SmemRing r{yh};
+    ChanState st = cx.st;
+    int flags = cx.flags;
+    chain_packet_prologue(st, r, *cx.desc, cx.sri_xdelta, flags);
+    cx.st = st; cx.flags = flags;
+    if (st.fit.pts == st.fit.n && st.fit.pts > 1) cx.fc = fit_const(st.fit);
+}
+
+// packet epilogue (cpp/psk_soft.cpp:592-603), lane 0; returns through cx.cz_valid whether the history moved
+static __device__ __noinline__ void fz_epilogue(FzCtx& cx, float* yh) {
+    SmemRing r{yh};
+    ChanState st = cx.st;
+    const unsigned long long w0 = st.wraps;
+    chain_packet_epilogue(st, r, cx.M);
+    if (st.wraps != w0) { cx.st = st; cx.cz_valid = 0; }
+}
+
+static __device__ __noinline__ int fz_unwrap_count_slow(float est_prev, float theta) {
+    const double dlt = dsubr((double)est_prev, (double)theta);
+    return (int)(long long)round(__ddiv_rn(dlt, PSKD_M_2PI));
+}
+// the reference's unwrap count (cpp/psk_soft.cpp:477), fast form with a guard band (see unwrap_count)
+__device__ __forceinline__ int fz_unwrap_count(float est_prev, float theta) {
+    const double dlt = dsubr((double)est_prev, (double)theta);       // exact
+    const double q = dmulr(dlt, 0.15915494309189535);
+    const double t = daddr(q, 6755399441055744.0);                   // 1.5 * 2^52: round to nearest integer
+    const double qr = dsubr(t, 6755399441055744.0);
+    const double fr = fabs(dsubr(q, qr));
+    if (fr > 0.4999999 || !(fabs(q) < 1.0e9)) return fz_unwrap_count_slow(est_prev, theta);
+    return __double2loint(t);
+}
+
+static __device__ __noinline__ unsigned fz_slice8_slow(float cx_, float cy_) { return slice_bits(make_float2(cx_, cy_), 3); }
+__device__ __forceinline__ unsigned fz_slice8(float2 c) {
+    const float a = fabsf(c.x), b = fabsf(c.y);
+    const float T = 0.41421356237309503f;       // tan(pi/8)
+    const float sum = a + b;
+    const float d1 = b - T * a, d2 = a - T * b;
+    const float g = 1.0e-5f * sum;
+    if (!(sum > 0.0f) || !(sum < 3.0e38f) || fabsf(d1) <= g || fabsf(d2) <= g) return fz_slice8_slow(c.x, c.y);
+    if (d1 < 0.0f) return (c.x > 0.0f) ? 0u : 4u;
+    if (d2 < 0.0f) return (c.y > 0.0f) ? 2u : 6u;
+    return (c.x > 0.0f) ? ((c.y > 0.0f) ? 1u : 7u) : ((c.y > 0.0f) ? 3u : 5u);
+}
+
+static __device__ __noinline__ float2 fz_cdiv(float2 n, float2 d) { return cdiv_f32(n, d); }
+
+// four symbols' bits as shorts (LSB first, cpp/psk_soft.cpp:512,525-526,559-563) packed into words
+template <int BPB>
+__device__ __forceinline__ void fz_store_bits(unsigned* dst, const unsigned b[4]) {
+    if (BPB == 1) {
+        *reinterpret_cast<uint2*>(dst) = make_uint2(b[0] | (b[1] << 16), b[2] | (b[3] << 16));
+    } else if (BPB == 2) {
+        uint4 w;
+        w.x = (b[0] & 1u) | ((b[0] >> 1) << 16); w.y = (b[1] & 1u) | ((b[1] >> 1) << 16);
+        w.z = (b[2] & 1u) | ((b[2] >> 1) << 16); w.w = (b[3] & 1u) | ((b[3] >> 1) << 16);
+        *reinterpret_cast<uint4*>(dst) = w;
+    } else {
+        // shorts: b0.0 b0.1 | b0.2 b1.0 | b1.1 b1.2 | b2.0 b2.1 | b2.2 b3.0 | b3.1 b3.2
+        uint2 w0, w1, w2;
+        w0.x = (b[0] & 1u) | (((b[0] >> 1) & 1u) << 16);
+        w0.y = ((b[0] >> 2) & 1u) | ((b[1] & 1u) << 16);
+        w1.x = ((b[1] >> 1) & 1u) | (((b[1] >> 2) & 1u) << 16);
+        w1.y = (b[2] & 1u) | (((b[2] >> 1) & 1u) << 16);
+        w2.x = ((b[2] >> 2) & 1u) | ((b[3] & 1u) << 16);
+        w2.y = ((b[3] >> 1) & 1u) | (((b[3] >> 2) & 1u) << 16);
+        reinterpret_cast<uint2*>(dst)[0] = w0; reinterpret_cast<uint2*>(dst)[1] = w1; reinterpret_cast<uint2*>(dst)[2] = w2;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fz_drain: consume buffered symbols: chain blocks of FZ_B (shorter at a packet end) followed by
+// the output stage; runs the packet epilogue / next prologue whenever a packet is exhausted.
+// ---------------------------------------------------------------------------------------------
+template <int S, int RRC, int PC>
+static __device__ __noinline__ void fz_drain(const unsigned wofs)
+{
+    using L = FzL<S, RRC, PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    double* czblk = reinterpret_cast<double*>(wb + L::OFF_ALIAS);                    // cz[P+1 ...]
+    float*  yblk = reinterpret_cast<float*>(wb + L::OFF_ALIAS + FZ_B * 8);
+    float*  estv = yblk + FZ_B;
+    const int lane = threadIdx.x & 31;
+    const int P = cx.P, M = cx.M, bpb = cx.bpb;
+    double* cz = czblk - (P + 1);
+
+    while (!cx.unit_done) {
+        const int kchain = cx.kchain;
+        const int rem = cx.pk_hi - kchain;
+        if (rem == 0) {
+            if (lane == 0) fz_epilogue(cx, yh);                                     // :592-603
+            __syncwarp();
+            const int pkt = cx.pkt + 1;
+            if (pkt == cx.pk1) { if (lane == 0) cx.unit_done = 1; __syncwarp(); break; }
+            if (lane == 0) {
+                cx.pkt = pkt;
+                fz_prologue(cx, yh);                                                // :393-426
+                cx.pk_hi = (pkt + 1 == cx.n_pkts) ? cx.K
+                           : (int)first_symbol_at((long long)(pkt + 1) * cx.pkt_len, cx.tail_len, S, cx.A, cx.K);
+            }
+            __syncwarp();
+            continue;
+        }
+        const int nbuf = cx.nbuf;
+        const int want = min(FZ_B, rem);
+        if (nbuf < want) break;
+
+        // ---- one sub-block of m symbols at buffer offset 0 ----------------------------------------
+        int m = want;
+        const int pts = cx.st.fit.pts, cnt = cx.st.fit.count;
+        bool fast = (pts == P) && (P > 1);
+        if (fast && cnt + m > 1048576) {
+            if (cnt == 1048576) {                                                   // :51-52 at a block edge
+                if (lane == 0) { SmemRing r{yh}; fit_resum(cx.st.fit, r); }
+                __syncwarp();
+                continue;
+            }
+            m = 1048576 - cnt;                                                      // stop at the re-sum point
+        }
+        if (!fast) m = min(m, max(1, P - pts));                                     // fill-up runs sequentially
+        const int i0 = lane * 4;
+        const float4 t4 = *reinterpret_cast<const float4*>(th + i0);
+        const float tl[4] = {t4.x, t4.y, t4.z, t4.w};
+        float el[4];
+        bool done = false;
+        if (fast) {
+            if (cx.st.fit.head != 0) { fz_normalize_ring(yh, estv, cx.st.fit, P, lane); cx.cz_valid = 0; __syncwarp(); }
+            if (!cx.cz_valid) { fz_rebuild_cz(yh, cz, P, lane); if (lane == 0) cx.cz_valid = 1; __syncwarp(); }
+            const FitConst fc = cx.fc;
+            const float xdelta = cx.st.fit.xdelta;
+            const float fP1 = cx.fP1;
+            const double xd = (double)xdelta;
+            const double X0 = cx.st.fit.xySum;
+            const double HPP = cz[P];
+            const float est0 = cx.st.est;
+            // classic-unwrap prediction of n (integer scan), first symbol by the reference's rule
+            int nloc[4];
+            {
+                const float tprev = __shfl_up_sync(0xffffffffu, t4.w, 1);
+                int run = 0;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const float pv = (v == 0) ? tprev : tl[v - 1];
+                    int dn = -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
+                    if (v == 0 && lane == 0) dn = fz_unwrap_count(est0, tl[0]);
+                    run += dn; nloc[v] = run;
+                }
+                const int off = warp_scan_int(run, lane) - run;
+#pragma unroll
+                for (int v = 0; v < 4; v++) nloc[v] += off;
+            }
+            int iter = 0;
+            float yl[4]; double Ys[4], Xl[4];
+            while (true) {
+                double Cl[4], hi0;
+                {
+                    double run = 0.0;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const float y = __double2float_rn(daddr((double)tl[v], dmulr((double)nloc[v], PSKD_M_2PI)));   // :478,481
+                        yl[v] = y; run = daddr(run, (double)y); Cl[v] = run;
+                    }
+                    hi0 = daddr(HPP, dsubr(warp_scan_dbl(run, lane), run));          // cz[P+i0]
+#pragma unroll
+                    for (int v = 0; v < 4; v++) Cl[v] = daddr(hi0, Cl[v]);           // cz[P+1+i0+v]
+                }
+                *reinterpret_cast<float4*>(yblk + i0) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+                *reinterpret_cast<double2*>(czblk + i0) = make_double2(Cl[0], Cl[1]);
+                *reinterpret_cast<double2*>(czblk + i0 + 2) = make_double2(Cl[2], Cl[3]);
+                __syncwarp();
+                double trun = 0.0;
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const double hi = (v == 0) ? hi0 : Cl[v - 1];                    // cz[P+i]
+                    const double W = dsubr(hi, cz[i0 + v + 1]);                      // ySum after :70
+                    const double a = dmulr(xd, W);                                   // :72
+                    const double T = (double)fmulr(fmulr(yl[v], fP1), xdelta);       // :78
+                    trun = daddr(trun, dsubr(T, a)); Xl[v] = trun;
+                    Ys[v] = daddr(W, (double)yl[v]);                                 // :75
+                }
+                const double xoff = daddr(X0, dsubr(warp_scan_dbl(trun, lane), trun));
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    Xl[v] = daddr(xoff, Xl[v]);
+                    el[v] = fit_eval_fast(fc, Ys[v], Xl[v], nullptr, nullptr);       // :135-162
+                }
+                // verify every predicted n against the reference's rule (:477) with est_{i-1}
+                const float eprev = __shfl_up_sync(0xffffffffu, el[3], 1);
+                int mymis = 0x7fffffff, mydelta = 0;
+#pragma unroll
+                for (int v = 3; v >= 0; v--) {
+                    const int i = i0 + v;
+                    if (i >= 1 && i < m) {
+                        const int nt = fz_unwrap_count((v == 0) ? eprev : el[v - 1], tl[v]);
+                        if (nt != nloc[v]) { mymis = i; mydelta = nt - nloc[v]; }
+                    }
+                }
+                const int mis = (int)__reduce_min_sync(0xffffffffu, (unsigned)mymis);
+                if (mis == 0x7fffffff) { done = true; break; }
+                if (++iter > FZ_MAX_ITERS) break;
+                const int delta = __shfl_sync(0xffffffffu, mydelta, mis >> 2);
+#pragma unroll
+                for (int v = 0; v < 4; v++) if (i0 + v >= mis) nloc[v] += delta;
+                __syncwarp();
+            }
+            if (iter && lane == 0) cx.passes += (unsigned)iter;
+            if (done) {
+                const int last = m - 1;
+                if ((last >> 2) == lane) {
+                    double Yv = Ys[0], Xv = Xl[0];
+#pragma unroll
+                    for (int v = 1; v < 4; v++) if (v == (last & 3)) { Yv = Ys[v]; Xv = Xl[v]; }
+                    FitState& f = cx.st.fit;
+                    float mm, bb;
+                    cx.st.est = fit_eval_fast(fc, Yv, Xv, &mm, &bb);
+                    f.ySum = Yv; f.xySum = Xv; f.m = mm; f.b = bb; f.count += m;
+                }
+                __syncwarp();
+                // new history = last P of (history ++ block): shift the prefix and the values by m
+                const double czm = cz[m];
+                for (int base = 0; base <= P; base += 32) {
+                    const int j = base + lane;
+                    double pv = 0.0; float yv = 0.0f;
+                    if (j <= P) pv = dsubr(cz[m + j], czm);
+                    if (j < P) yv = (m + j < P) ? yh[m + j] : yblk[m + j - P];
+                    __syncwarp();
+                    if (j <= P) cz[j] = pv;
+                    if (j < P) yh[j] = yv;
+                    __syncwarp();
+                }
+            } else {
+                if (lane == 0) { cx.seq_blocks++; cx.cz_valid = 0; }
+            }
+        }
+        if (!done) {
+            __syncwarp();
+            if (lane == 0) { fz_block_sequential(cx, yh, th, estv, m); cx.cz_valid = 0; }
+            __syncwarp();
+#pragma unroll
+            for (int v = 0; v < 4; v++) el[v] = (i0 + v < m) ? estv[i0 + v] : 0.0f;
+            __syncwarp();
+        }
+        if (lane == 0) cx.blocks++;
+
+        // ---- back: derotate / differential decode / slice (cpp/psk_soft.cpp:484-566) -----------------
+        const bool diff = cx.diff != 0;
+        const float2 prev_new = selb[2 + m - 1];
+        float2 sv[4];
+        {
+            const float4 a = *reinterpret_cast<const float4*>(selb + 2 + i0);
+            const float4 b = *reinterpret_cast<const float4*>(selb + 4 + i0);
+            sv[0] = make_float2(a.x, a.y); sv[1] = make_float2(a.z, a.w);
+            sv[2] = make_float2(b.x, b.y); sv[3] = make_float2(b.z, b.w);
+        }
+        const float2 sprev = selb[1 + i0];
+        __syncwarp();
+        // phase_dataFloat_out (:482): staged in th[0..m), i.e. over consumed entries only
+        if (i0 + 3 < m) *reinterpret_cast<float4*>(th + i0) = make_float4(el[0], el[1], el[2], el[3]);
+        else if (i0 < m) {
+#pragma unroll
+            for (int v = 0; v < 3; v++) if (i0 + v < m) th[i0 + v] = el[v];
+        }
+        unsigned bsym[4];
+        {
+            const float inv_m = 1.0f / (float)M;
+            const bool m_pow2 = (M & (M - 1)) == 0;
+            float2 cv[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                float2 s = sv[v];
+                float pc = 0.0f;
+                if (diff) s = fz_cdiv(s, (v == 0) ? sprev : sv[v - 1]);                                 // :488
+                else pc = m_pow2 ? fmulr(-el[v], inv_m) : __fdiv_rn(-el[v], (float)M);                   // :494 (exact for 2^n)
+                if (M == 4) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                      // :497-498
+                cv[v] = derotate(s, pc);                                                                // :499-501
+                unsigned b = 0;
+                if (bpb == 3) b = fz_slice8(cv[v]);
+                else if (bpb == 1) b = (cv[v].x < 0.0f) ? 1u : 0u;
+                else if (bpb == 2) b = slice_bits(cv[v], 2);
+                bsym[v] = b;
+            }
+            if (i0 + 3 < m) {
+                *reinterpret_cast<float4*>(selb + 2 + i0) = make_float4(cv[0].x, cv[0].y, cv[1].x, cv[1].y);
+                *reinterpret_cast<float4*>(selb + 4 + i0) = make_float4(cv[2].x, cv[2].y, cv[3].x, cv[3].y);
+            } else if (i0 < m) {
+#pragma unroll
+                for (int v = 0; v < 3; v++) if (i0 + v < m) selb[2 + i0 + v] = cv[v];
+            }
+        }
+        short* bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS);           // chain buffers are dead now
+        int16_t* o_bits = cx.o_bits;
+        if (bpb > 0 && o_bits) {
+            unsigned* dst = reinterpret_cast<unsigned*>(bstage) + lane * 2 * bpb;
+            if (bpb == 3) fz_store_bits<3>(dst, bsym);
+            else if (bpb == 2) fz_store_bits<2>(dst, bsym);
+            else fz_store_bits<1>(dst, bsym);
+        }
+        __syncwarp();
+        {
+            float* o_phase = cx.o_phase;
+            if (o_phase) {
+                float* o = o_phase + kchain;
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, th[i]); }
+            }
+            float2* o_soft = cx.o_soft;
+            if (o_soft) {
+                float2* o = o_soft + kchain;
+#pragma unroll
+                for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, selb[2 + i]); }
+            }
+            if (bpb > 0 && o_bits) {
+                int16_t* o = o_bits + (long long)kchain * bpb;
+                const int nsh = m * bpb;
+                if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+                    const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage);
+                    unsigned* o32 = reinterpret_cast<unsigned*>(o);
+                    for (int t = lane; t < (nsh >> 1); t += 32) __stcs(o32 + t, s32[t]);
+                    if ((nsh & 1) && lane == 0) o[nsh - 1] = bstage[nsh - 1];
+                } else {
+                    for (int t = lane; t < nsh; t += 32) o[t] = bstage[t];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- drop the consumed symbols from the buffer ------------------------------------------------
+        const int left = nbuf - m;
+        for (int base = 0; base < left; base += 32) {
+            const int i = base + lane;
+            float tv = 0.f; float2 sv2 = make_float2(0.f, 0.f);
+            if (i < left) { tv = th[m + i]; sv2 = selb[2 + m + i]; }
+            __syncwarp();
+            if (i < left) { th[i] = tv; selb[2 + i] = sv2; }
+            __syncwarp();
+        }
+        if (lane == 0) { selb[1] = prev_new; cx.nbuf = left; cx.kchain = kchain + m; }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// atan2f for the M-th power angle (cpp/psk_soft.cpp:474).  glibc's atan2f (the reference) and
+// CUDA's are both "a few ulp" functions; this one is too (|error| <= 3e-7 rad: 2-ulp quotient,
+// degree-8 minimax polynomial in r^2, pi split in two floats), in ~25 instructions instead of ~60.
+// The angle only feeds the unwrap count (an integer; every count is verified) and the fitted
+// phase (tolerance 1e-4).  Zero, non-finite and extreme-magnitude inputs take the library call.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fz_atan2(float y, float x, bool& bad) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    bad = !(mx > 1.0e-18f && mx < 1.0e18f);
+    const float r = __fdividef(mn, mx);
+    const float t = r * r;
+    float q = 0.0029035548213869333f;
+    q = fmaf(q, t, -0.01628301665186882f);
+    q = fmaf(q, t, 0.04303938150405884f);
+    q = fmaf(q, t, -0.0753367692232132f);
+    q = fmaf(q, t, 0.1065467819571495f);
+    q = fmaf(q, t, -0.14207133650779724f);
+    q = fmaf(q, t, 0.19993054866790771f);
+    q = fmaf(q, t, -0.3333309292793274f);
+    float a = fmaf(r * t, q, r);
+    if (ay > ax) a = (1.57079637050628662109375f - a) + -4.37113900018624283e-8f;
+    if (x < 0.0f) a = (3.1415927410125732421875f - a) + -8.74227800037248566e-8f;
+    return copysignf(a, y);
+}
+
+// atan2f(Im s^M, Re s^M) with s^M by repeated squaring, unfused (libstdc++ __complex_pow_unsigned,
+// cpp/psk_soft.cpp:474); straight-line for M = 2, 4, 8.  `bad` asks for the literal path
+// (fz_theta_fixup): other M, zero / non-finite / extreme powers (a (NaN, NaN) product can also
+// mean the reference's __mulsc3 recovery ran).
+__device__ __forceinline__ float2 fz_csq(float2 x) {
+    return make_float2(fsubr(fmulr(x.x, x.x), fmulr(x.y, x.y)), faddr(fmulr(x.x, x.y), fmulr(x.y, x.x)));
+}
+__device__ __forceinline__ float fz_theta(float2 s, int M, bool& bad) {
+    float2 y = s;
+    if (M == 8) y = fz_csq(fz_csq(fz_csq(s)));
+    else if (M == 4) y = fz_csq(fz_csq(s));
+    else if (M == 2) y = fz_csq(s);
+    const float th = fz_atan2(y.y, y.x, bad);
+    bad = bad || !(M == 2 || M == 4 || M == 8);
+    return th;
+}
+// literal path for the lanes that asked for it: th[i] = atan2f(pow(sel[i], M)) with the library call
+static __device__ __noinline__ void fz_theta_fixup(float* th, const float2* sel, int i, unsigned M) {
+    const float2 z = cpow_unsigned(sel[i], M);
+    th[i] = atan2f(z.y, z.x);
+}
+
+// timing, part 1: exact sliding window sums of one chunk, lane = (phase wp, row group wg):
+// Eloc_i = sum of this group's rows' leading energies through row i minus the trailing energies
+// before row i (cpp/psk_soft.cpp:451, 576).  TC (padded layouts): rows i >= TC of the trailing
+// run sit behind one more pad.
+template <int S, int TC>
+__device__ __forceinline__ double fz_window_rows(const float* __restrict__ addp, const float* __restrict__ subp,
+                                                 int wg, double (&Eloc)[FzCfg<S>::R]) {
+    using C = FzCfg<S>;
+    constexpr int G = C::G, R = C::R;
+    double x = 0.0;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        if (G * R == 32 || R * wg + i < 32) {
+            const float a = addp[i * S];
+            const float sb = subp[i * S + ((C::PADDED && i >= TC) ? C::PAD : 0)];
+            x = daddr(x, (double)a);
+            Eloc[i] = x;
+            x = dsubr(x, (double)sb);
+        } else Eloc[i] = 0.0;
+    }
+    return x;
+}
 template <int S>
+__device__ __forceinline__ double fz_window(const float* addp, const float* subp, int wg, int tc, double (&Eloc)[FzCfg<S>::R]) {
+    using C = FzCfg<S>;
+    if (!C::PADDED) return fz_window_rows<S, C::R>(addp, subp, wg, Eloc);
+    if (S == 8) {
+        switch (tc) {
+            case 1: return fz_window_rows<S, 1>(addp, subp, wg, Eloc);
+            case 2: return fz_window_rows<S, 2>(addp, subp, wg, Eloc);
+            case 3: return fz_window_rows<S, 3>(addp, subp, wg, Eloc);
+            case 4: return fz_window_rows<S, 4>(addp, subp, wg, Eloc);
+            case 5: return fz_window_rows<S, 5>(addp, subp, wg, Eloc);
+            case 6: return fz_window_rows<S, 6>(addp, subp, wg, Eloc);
+            case 7: return fz_window_rows<S, 7>(addp, subp, wg, Eloc);
+            default: return fz_window_rows<S, 8>(addp, subp, wg, Eloc);
+        }
+    }
+    // other padded layouts (S = 16): run-time carry
+    constexpr int G = C::G, R = C::R;
+    double x = 0.0;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        if (G * R == 32 || R * wg + i < 32) {
+            const float a = addp[i * S];
+            const float sb = subp[i * S + ((i >= tc) ? C::PAD : 0)];
+            x = daddr(x, (double)a);
+            Eloc[i] = x;
+            x = dsubr(x, (double)sb);
+        } else Eloc[i] = 0.0;
+    }
+    return x;
+}
+
+__device__ __forceinline__ void fz_prefetch_l2(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// fz_unit_begin: claim-independent set-up of one unit: geometry, wait for the predecessor unit,
+// carried state into shared memory, first packet prologue, ring priming.  Returns the number of
+// chunks (< 0: nothing to do for this ticket); the lane's carried window sum goes through ebuf[lane].
+// ---------------------------------------------------------------------------------------------
+template <int S, int RRC, int PC>
+static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const unsigned wofs, const int u)
+{
+    using C = FzCfg<S>;
+    using L = FzL<S, RRC, PC>;
+    constexpr int G = C::G, R = C::R, ES = C::ES;
+    constexpr int CHS = FZ_CH * S;
+    unsigned char* wb = fz_smem + wofs;
+    float*  ring = reinterpret_cast<float*>(wb);
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);
+    const int lane = threadIdx.x & 31;
+    const bool wact = lane < G * S;
+    const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
+
+    const int ug = u / prm.n_list;
+    const int ch = __ldg(prm.list + (u - ug * prm.n_list));
+    const ChanDesc* dgp = prm.desc + ch;
+    const int n_pkts = dgp->n_pkts;
+    const int pk0 = ug * prm.pkts_per_unit;
+    if (pk0 >= n_pkts) return -1;
+    const int pk1 = min(pk0 + prm.pkts_per_unit, n_pkts);
+    const int A = dgp->A, P = dgp->P;
+    const long long tail_len = dgp->tail_len, pkt_len = dgp->pkt_len;
+    const int K = (int)dgp->K;
+    const long long V = tail_len + dgp->n_in;
+    const int lag = A - 1, RR = C::ring_rows(A);
+    const int kA = (int)first_symbol_at((long long)pk0 * pkt_len, tail_len, S, A, K);
+    const int kB = (pk1 == n_pkts) ? K : (int)first_symbol_at((long long)pk1 * pkt_len, tail_len, S, A, K);
+    const int nchunks = (kB - kA + FZ_CH - 1) / FZ_CH;
+    const float2* in_mt = dgp->in - tail_len;
+    const float2* tailp = dgp->tail;
+    // chunks [c_lo, c_hi) lie wholly inside `in` at a 16-byte aligned address: 128-bit loads
+    int c_lo = 0, c_hi = 0;
+    {
+        const long long sA0 = (long long)(kA + lag) * S;
+        if ((reinterpret_cast<uintptr_t>(in_mt + sA0) & 15) == 0) {
+            long long lo = (tail_len - sA0 + CHS - 1) / CHS;
+            if (lo < 0) lo = 0;
+            long long hi = (V - sA0) / CHS;                               // chunks fully below V
+            if (hi > nchunks) hi = nchunks;
+            if (lo < hi) { c_lo = (int)lo; c_hi = (int)hi; }
+        }
+        // start the stream: chunks 0 and 1 towards L2
+        if (lane == 0 && c_lo == 0 && c_hi > 0) fz_prefetch_l2(in_mt + sA0, (unsigned)min(2, c_hi) * CHS * 8);
+    }
+    // ---- wait for the previous unit of this channel, then load its carried state ------------------
+    if (ug > 0) {
+        if (lane == 0) { while (ld_acquire(prm.done + ch) < ug) __nanosleep(200); }
+        __syncwarp();
+    }
+    const float* gring = prm.ring_base + dgp->ring_off;
+    if (lane == 0) {
+        const int4* src = reinterpret_cast<const int4*>(prm.state + ch);
+        int4* dst = reinterpret_cast<int4*>(&cx.st);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(ChanState) / 16); i++) dst[i] = __ldcg(src + i);
+        const long long sym_off = dgp->sym_off;
+        cx.flags = (ug == 0) ? dgp->flags : (dgp->flags & ~(CH_RESET_NUMSYMS | CH_RESET_PHASEAVG));
+        cx.passes = 0; cx.seq_blocks = 0; cx.blocks = 0;
+        cx.in_mt = in_mt; cx.tail = tailp; cx.desc = dgp;
+        cx.o_soft = prm.out_soft ? prm.out_soft + sym_off : nullptr;
+        cx.o_phase = prm.out_phase ? prm.out_phase + sym_off : nullptr;
+        cx.o_bits = prm.out_bits ? prm.out_bits + dgp->bits_off : nullptr;
+        cx.o_sidx = prm.out_sidx ? prm.out_sidx + sym_off : nullptr;
+        cx.sri_xdelta = prm.sri_xdelta;
+        cx.tail_len = tail_len; cx.pkt_len = pkt_len;
+        cx.n_pkts = n_pkts; cx.pk1 = pk1; cx.K = K; cx.A = A; cx.M = dgp->M; cx.P = P; cx.bpb = dgp->bpb; cx.diff = dgp->D;
+        cx.pkt = pk0; cx.kchain = kA; cx.nbuf = 0; cx.cz_valid = 0; cx.unit_done = 0;
+        cx.fP1 = (float)(P - 1);
+        cx.pk_hi = (pk0 + 1 == n_pkts) ? K : (int)first_symbol_at((long long)(pk0 + 1) * pkt_len, tail_len, S, A, K);
+        cx.kA = kA; cx.kB = kB; cx.lag = lag; cx.RR = RR; cx.NS = RR / 32;
+        cx.tc = C::PADDED ? ((lag % R) ? (lag % R) : R) : R;              // R - ((-lag) mod R)
+        cx.c_lo = c_lo; cx.c_hi = c_hi; cx.nchunks = nchunks;
+        cx.gather_in = ((long long)kA * S >= tail_len) ? 1 : 0;           // every gather of this unit falls into `in`
+        cx.ch = ch; cx.ug = ug; cx.V = V;
+    }
+    for (int j = lane; j < P; j += 32) yh[j] = __ldcg(gring + j);
+    __syncwarp();
+    if (lane == 0) { cx.wraps0 = cx.st.wraps; selb[1] = cx.st.last; fz_prologue(cx, yh); }
+    __syncwarp();
+
+    // ---- prime the energy ring with rows [kA, kA+lag) and the carried window sum -------------------
+    double Cw = 0.0;               // lane (p, g): sum over the window of output k0 WITHOUT its newest row
+    if (nchunks > 0) {
+        const long long s0 = (long long)kA * S;
+        for (int s = lane; s < lag * S; s += 32) {
+            const long long v = s0 + s;
+            float2 x = make_float2(0.f, 0.f);
+            if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
+            const int row = s / S, p = s - row * S;
+            ring[C::fpos(RR - lag + row) + p] = energy_f32(x.x, x.y);
+        }
+        __syncwarp();
+        {
+            double acc = 0.0;
+            for (int i = wg; i < lag; i += G) acc = daddr(acc, (double)ring[C::fpos(RR - lag + i) + wp]);
+            if (wact) ebuf[wg * ES + wp] = acc;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int g2 = 0; g2 < G; g2++) Cw = daddr(Cw, ebuf[g2 * ES + wp]);
+        __syncwarp();
+    }
+    ebuf[lane] = Cw;
+    __syncwarp();
+    return nchunks;
+}
+
+// fz_unit_end: hand the channel's state to the next unit / the next call
+template <int S, int RRC, int PC>
+static __device__ __noinline__ void fz_unit_end(const FusedParams& prm, const unsigned wofs)
+{
+    using L = FzL<S, RRC, PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    const int lane = threadIdx.x & 31;
+    const int P = cx.P, ch = cx.ch;
+    float* gring = prm.ring_base + cx.desc->ring_off;
+    if (cx.st.fit.head != 0 && cx.st.fit.pts == P)
+        fz_normalize_ring(yh, reinterpret_cast<float*>(wb + L::OFF_ALIAS), cx.st.fit, P, lane);
+    for (int j = lane; j < P; j += 32) __stcg(gring + j, yh[j]);
+    if (lane == 0) {
+        if (cx.diff && cx.kB > cx.kA) cx.st.last = selb[1];                               // :489
+        const int4* src = reinterpret_cast<const int4*>(&cx.st);
+        int4* dst = reinterpret_cast<int4*>(prm.state + ch);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(ChanState) / 16); i++) __stcg(dst + i, src[i]);
+        if (cx.st.wraps != cx.wraps0) atomicAdd(&prm.counters->wraps, cx.st.wraps - cx.wraps0);
+        if (cx.blocks) atomicAdd(&prm.counters->spec_chunks, (unsigned long long)cx.blocks);
+        if (cx.passes) atomicAdd(&prm.counters->spec_misses, (unsigned long long)cx.passes);
+        if (cx.seq_blocks) atomicAdd(&prm.counters->seq_channels, (unsigned long long)cx.seq_blocks);
+    }
+    __syncwarp();
+    __threadfence();
+    if (lane == 0) st_release(prm.done + ch, cx.ug + 1);
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int S, int RRC, int PC>
 __global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZ_MIN_CTAS)
 k_fused(const FusedParams prm)
 {
     using C = FzCfg<S>;
+    using L = FzL<S, RRC, PC>;
     constexpr int G = C::G, R = C::R, ES = C::ES, NQ = C::NQ;
-    extern __shared__ __align__(16) unsigned char fz_smem[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char* wb = fz_smem + (size_t)wid * prm.lay.bytes;
+    constexpr int CHS = FZ_CH * S;                       // samples per chunk
+    const int lane = threadIdx.x & 31;
+    const unsigned wofs = (threadIdx.x >> 5) * (unsigned)L::BYTES;
+    unsigned char* wb = fz_smem + wofs;
     float*  ring = reinterpret_cast<float*>(wb);
-    float*  th   = reinterpret_cast<float*>(wb + prm.lay.off_th);
-    float2* selb = reinterpret_cast<float2*>(wb + prm.lay.off_sel);     // [1] = previous symbol's sample, [2..] = block
-    float*  yh   = reinterpret_cast<float*>(wb + prm.lay.off_yh);
-    FzWarp& sh   = *reinterpret_cast<FzWarp*>(wb + prm.lay.off_st);
-    unsigned char* alias = wb + prm.lay.off_alias;
-    double* ebuf = reinterpret_cast<double*>(alias);                    // [32][ES] window sums (ingest phase)
-    float*  yblk = reinterpret_cast<float*>(alias + FZ_B * 8);          // chain phase: the block's y values
-    float*  estv = yblk + FZ_B;                                         // chain phase: est per symbol (sequential path)
-
-    // lane roles of the timing step
-    const int wg = lane / S, wp = lane - wg * S;       // row group, phase
-    const bool wact = lane < G * S;
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);       // [32][ES] window sums (ingest phase)
 
     for (;;) {
         int u = 0;
         if (lane == 0) u = atomicAdd(prm.ticket, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= prm.n_units) break;
-        const int ug = u / prm.n_list;
-        const int ch = __ldg(prm.list + (u - ug * prm.n_list));
-        const ChanDesc& dg = prm.desc[ch];
-        const int n_pkts = dg.n_pkts;
-        const int pk0 = ug * prm.pkts_per_unit;
-        if (pk0 >= n_pkts) continue;
-        const int pk1 = min(pk0 + prm.pkts_per_unit, n_pkts);
-        const int A = dg.A, M = dg.M, P = dg.P, bpb = dg.bpb;
-        const bool diff = dg.D != 0;
-        const long long tail_len = dg.tail_len, pkt_len = dg.pkt_len;
-        const long long V = tail_len + dg.n_in;
-        const int K = (int)dg.K;
-        const int lag = A - 1;
-        const int RR = C::ring_rows(A), NS = RR / 32;
-        VStream vs{dg.tail, dg.in, tail_len};
-        const int kA = (int)first_symbol_at((long long)pk0 * pkt_len, tail_len, S, A, K);
-        const int kB = (pk1 == n_pkts) ? K : (int)first_symbol_at((long long)pk1 * pkt_len, tail_len, S, A, K);
-        double* cz = reinterpret_cast<double*>(alias) - (P + 1);        // cz[0..P] history prefix, cz[P+1..] block prefix
-
-        // ---- ingest prefetch of chunk 0 (in flight while we wait for the predecessor unit) -------
-        const int nchunks = (kB - kA + FZ_CH - 1) / FZ_CH;
-        float4 xq[NQ];
-        bool xq_valid = false;
-        auto chunk_fast = [&](int c) -> bool {          // whole chunk inside `in`, 16-byte aligned
-            const long long sA = (long long)(kA + c * FZ_CH + lag) * S;
-            if (sA < tail_len || sA + 32 * S > V) return false;
-            return (reinterpret_cast<uintptr_t>(dg.in + (sA - tail_len)) & 15) == 0;
-        };
-        auto chunk_issue = [&](int c) {
-            const long long sA = (long long)(kA + c * FZ_CH + lag) * S;
-            const float4* g4 = reinterpret_cast<const float4*>(dg.in + (sA - tail_len));
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                const int f = lane + 32 * q;
-                if ((S * 16) % 32 == 0 || f < S * 16) xq[q] = __ldg(g4 + f);
-            }
-        };
-        if (nchunks > 0 && chunk_fast(0)) { chunk_issue(0); xq_valid = true; }
-
-        // ---- wait for the previous unit of this channel, then load its carried state --------------
-        if (ug > 0) {
-            if (lane == 0) { while (ld_acquire(prm.done + ch) < ug) __nanosleep(200); }
-            __syncwarp();
-        }
-        float* gring = prm.ring_base + dg.ring_off;
-        if (lane == 0) {
-            const int4* src = reinterpret_cast<const int4*>(prm.state + ch);
-            int4* dst = reinterpret_cast<int4*>(&sh.st);
-#pragma unroll
-            for (int i = 0; i < (int)(sizeof(ChanState) / 16); i++) dst[i] = __ldcg(src + i);
-            sh.flags = (ug == 0) ? dg.flags : (dg.flags & ~(CH_RESET_NUMSYMS | CH_RESET_PHASEAVG));
-            sh.passes = 0; sh.seq_blocks = 0; sh.blocks = 0;
-        }
-        for (int j = lane; j < P; j += 32) yh[j] = __ldcg(gring + j);
+        const int nchunks = fz_unit_begin<S, RRC, PC>(prm, wofs, u);
+        if (nchunks < 0) continue;
+        double Cw = ebuf[lane];        // lane (p, g): sum over the window of output k0 WITHOUT its newest row
         __syncwarp();
-        const unsigned long long wraps0 = sh.st.wraps;
-        const float fP1 = (float)(P - 1);
-        if (lane == 0) selb[1] = sh.st.last;
-
-        // ---- prime the energy ring with rows [kA, kA+lag) and the carried window sum ---------------
-        double Cw = 0.0;               // lane (p, g): sum over the window of output k0 WITHOUT its newest row
-        if (nchunks > 0) {
-            const long long s0 = (long long)kA * S;
-            for (int s = lane; s < lag * S; s += 32) {
-                const long long v = s0 + s;
-                const float2 x = (v < V) ? vs.at(v) : make_float2(0.f, 0.f);
-                const int row = s / S, p = s - row * S;
-                ring[C::fpos(RR - lag + row) + p] = energy_f32(x.x, x.y);
-            }
-            __syncwarp();
-            if (wact) {
-                double acc = 0.0;
-                for (int i = wg; i < lag; i += G) acc = daddr(acc, (double)ring[C::fpos(RR - lag + i) + wp]);
-                ebuf[wg * ES + wp] = acc;
-            }
-            __syncwarp();
-            if (wact) {
-#pragma unroll
-                for (int g2 = 0; g2 < G; g2++) Cw = daddr(Cw, ebuf[g2 * ES + wp]);
-            }
-            __syncwarp();
-        }
-
-        // ---- chain bookkeeping -------------------------------------------------------------------
-        int pkt = pk0;                 // packet whose prologue has run
-        int kchain = kA;               // next symbol the chain consumes
-        int nbuf = 0;                  // symbols waiting in (th, selb)
-        bool cz_valid = false;
-        if (lane == 0) {
-            SmemRing r{yh};
-            chain_packet_prologue(sh.st, r, dg, prm.sri_xdelta, sh.flags);
-            if (sh.st.fit.pts == sh.st.fit.n && sh.st.fit.pts > 1) sh.fc = fit_const(sh.st.fit);
-        }
-        __syncwarp();
-        int pk_hi = (pkt + 1 == n_pkts) ? K : (int)first_symbol_at((long long)(pkt + 1) * pkt_len, tail_len, S, A, K);
-        bool unit_done = false;
-
-        // consume buffered symbols: blocks of FZ_B (shorter at a packet end); run the packet
-        // epilogue / next prologue whenever a packet is exhausted
-        auto drain = [&]() {
-            while (!unit_done) {
-                const int rem = pk_hi - kchain;
-                if (rem == 0) {
-                    if (lane == 0) {
-                        SmemRing r{yh};
-                        const unsigned long long w0 = sh.st.wraps;
-                        chain_packet_epilogue(sh.st, r, M);                                   // :592-603
-                        sh.flags = (sh.flags & ~(1 << 30)) | ((sh.st.wraps != w0) ? (1 << 30) : 0);
-                    }
-                    __syncwarp();
-                    if (sh.flags & (1 << 30)) cz_valid = false;
-                    pkt++;
-                    if (pkt == pk1) { unit_done = true; break; }
-                    if (lane == 0) {
-                        SmemRing r{yh};
-                        const int c0 = sh.st.fit.count, h0 = sh.st.fit.head;
-                        chain_packet_prologue(sh.st, r, dg, prm.sri_xdelta, sh.flags);       // :393-426
-                        if (sh.st.fit.pts == sh.st.fit.n && sh.st.fit.pts > 1) sh.fc = fit_const(sh.st.fit);
-                        (void)c0; (void)h0;
-                    }
-                    __syncwarp();
-                    pk_hi = (pkt + 1 == n_pkts) ? K : (int)first_symbol_at((long long)(pkt + 1) * pkt_len, tail_len, S, A, K);
-                    continue;
-                }
-                const int want = min(FZ_B, rem);
-                if (nbuf < want) break;
-
-                // ---- one sub-block of m symbols at buffer offset 0 ---------------------------------
-                int m = want;
-                const int pts = sh.st.fit.pts, cnt = sh.st.fit.count;
-                bool fast = (pts == P) && (P > 1);
-                if (fast && cnt + m > 1048576) {
-                    if (cnt == 1048576) {                                                     // :51-52 at a block edge
-                        if (lane == 0) { SmemRing r{yh}; fit_resum(sh.st.fit, r); }
-                        __syncwarp();
-                        continue;
-                    }
-                    m = 1048576 - cnt;                                                        // stop at the re-sum point
-                }
-                if (!fast) m = min(m, max(1, P - pts));                                       // fill-up runs sequentially
-                const int i0 = lane * 4;
-                const float4 t4 = *reinterpret_cast<const float4*>(th + i0);
-                const float tl[4] = {t4.x, t4.y, t4.z, t4.w};
-                const float est0 = sh.st.est;
-                float el[4];
-                bool done = false;
-                if (fast) {
-                    if (sh.st.fit.head != 0) { fz_normalize_ring(yh, estv, sh.st.fit, P, lane); cz_valid = false; }
-                    if (!cz_valid) { fz_rebuild_cz(yh, cz, P, lane); cz_valid = true; }
-                    const FitConst fc = sh.fc;
-                    const float xdelta = sh.st.fit.xdelta;
-                    const double xd = (double)xdelta;
-                    const double X0 = sh.st.fit.xySum;
-                    const double HPP = cz[P];
-                    // classic-unwrap prediction of n (integer scan), first symbol by the reference's rule
-                    int nloc[4];
-                    {
-                        const float tprev = __shfl_up_sync(0xffffffffu, t4.w, 1);
-                        int run = 0;
-#pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            const float pv = (v == 0) ? tprev : tl[v - 1];
-                            int dn = -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
-                            if (v == 0 && lane == 0) dn = unwrap_count(est0, tl[0]);
-                            if (i0 + v >= m) dn = 0;
-                            run += dn; nloc[v] = run;
-                        }
-                        const int off = warp_scan_int(run, lane) - run;
-#pragma unroll
-                        for (int v = 0; v < 4; v++) nloc[v] += off;
-                    }
-                    int iter = 0;
-                    float yl[4]; double Ys[4], Xl[4];
-                    while (true) {
-                        double Cl[4];
-                        {
-                            double run = 0.0;
-#pragma unroll
-                            for (int v = 0; v < 4; v++) {
-                                float y = 0.0f;
-                                if (i0 + v < m) y = __double2float_rn(daddr((double)tl[v], dmulr((double)nloc[v], PSKD_M_2PI)));   // :478,481
-                                yl[v] = y; run = daddr(run, (double)y); Cl[v] = run;
-                            }
-                            const double off = daddr(HPP, dsubr(warp_scan_dbl(run, lane), run));
-#pragma unroll
-                            for (int v = 0; v < 4; v++) Cl[v] = daddr(off, Cl[v]);             // cz[P+1+i]
-                            Ys[0] = off;                                                      // cz[P+i0]
-                        }
-                        *reinterpret_cast<float4*>(yblk + i0) = make_float4(yl[0], yl[1], yl[2], yl[3]);
-                        *reinterpret_cast<double2*>(cz + P + 1 + i0) = make_double2(Cl[0], Cl[1]);
-                        *reinterpret_cast<double2*>(cz + P + 3 + i0) = make_double2(Cl[2], Cl[3]);
-                        __syncwarp();
-                        double trun = 0.0;
-#pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            const int i = i0 + v;
-                            const double hi = (v == 0) ? Ys[0] : Cl[v - 1];                   // cz[P+i]
-                            const double W = dsubr(hi, cz[i + 1]);                            // ySum after :70
-                            const double a = dmulr(xd, W);                                    // :72
-                            const double T = (double)fmulr(fmulr(yl[v], fP1), xdelta);        // :78
-                            trun = daddr(trun, dsubr(T, a)); Xl[v] = trun;
-                            Ys[v] = daddr(W, (double)yl[v]);                                  // :75
-                        }
-                        const double xoff = daddr(X0, dsubr(warp_scan_dbl(trun, lane), trun));
-#pragma unroll
-                        for (int v = 0; v < 4; v++) {
-                            Xl[v] = daddr(xoff, Xl[v]);
-                            el[v] = fit_eval_fast(fc, Ys[v], Xl[v], nullptr, nullptr);        // :135-162
-                        }
-                        // verify every predicted n against the reference's rule (:477) with est_{i-1}
-                        const float eprev = __shfl_up_sync(0xffffffffu, el[3], 1);
-                        int mymis = 0x7fffffff, mydelta = 0;
-#pragma unroll
-                        for (int v = 3; v >= 0; v--) {
-                            const int i = i0 + v;
-                            if (i >= 1 && i < m) {
-                                const int nt = unwrap_count((v == 0) ? eprev : el[v - 1], tl[v]);
-                                if (nt != nloc[v]) { mymis = i; mydelta = nt - nloc[v]; }
-                            }
-                        }
-                        const int mis = (int)__reduce_min_sync(0xffffffffu, (unsigned)mymis);
-                        if (mis == 0x7fffffff) { done = true; break; }
-                        if (++iter > FZ_MAX_ITERS) break;
-                        const int delta = __shfl_sync(0xffffffffu, mydelta, mis >> 2);
-#pragma unroll
-                        for (int v = 0; v < 4; v++) if (i0 + v >= mis) nloc[v] += delta;
-                        __syncwarp();
-                    }
-                    if (iter && lane == 0) sh.passes += (unsigned)iter;
-                    if (done) {
-                        const int last = m - 1;
-                        if ((last >> 2) == lane) {
-                            double Yv = Ys[0], Xv = Xl[0];
-#pragma unroll
-                            for (int v = 1; v < 4; v++) if (v == (last & 3)) { Yv = Ys[v]; Xv = Xl[v]; }
-                            FitState& f = sh.st.fit;
-                            float mm, bb;
-                            sh.st.est = fit_eval_fast(fc, Yv, Xv, &mm, &bb);
-                            f.ySum = Yv; f.xySum = Xv; f.m = mm; f.b = bb; f.count += m;
-                        }
-                        __syncwarp();
-                        // new history = last P of (history ++ block): shift the prefix and the values by m
-                        const double czm = cz[m];
-                        for (int base = 0; base <= P; base += 32) {
-                            const int j = base + lane;
-                            double pv = 0.0; float yv = 0.0f;
-                            if (j <= P) pv = dsubr(cz[m + j], czm);
-                            if (j < P) yv = (m + j < P) ? yh[m + j] : yblk[m + j - P];
-                            __syncwarp();
-                            if (j <= P) cz[j] = pv;
-                            if (j < P) yh[j] = yv;
-                            __syncwarp();
-                        }
-                    } else {
-                        if (lane == 0) sh.seq_blocks++;
-                        cz_valid = false;
-                    }
-                }
-                if (!done) {
-                    __syncwarp();
-                    if (lane == 0) {
-                        fz_block_sequential(sh.st, yh, th, estv, m);
-                        if (sh.st.fit.pts == sh.st.fit.n && sh.st.fit.pts > 1) sh.fc = fit_const(sh.st.fit);
-                    }
-                    cz_valid = false;
-                    __syncwarp();
-#pragma unroll
-                    for (int v = 0; v < 4; v++) el[v] = (i0 + v < m) ? estv[i0 + v] : 0.0f;
-                    __syncwarp();
-                }
-                if (lane == 0) sh.blocks++;
-
-                // ---- back: derotate / differential decode / slice (cpp/psk_soft.cpp:484-566) ----------
-                const float2 prev_new = selb[2 + m - 1];
-                float2 sv[4];
-                {
-                    const float4 a = *reinterpret_cast<const float4*>(selb + 2 + i0);
-                    const float4 b = *reinterpret_cast<const float4*>(selb + 4 + i0);
-                    sv[0] = make_float2(a.x, a.y); sv[1] = make_float2(a.z, a.w);
-                    sv[2] = make_float2(b.x, b.y); sv[3] = make_float2(b.z, b.w);
-                }
-                const float2 sprev = selb[1 + i0];
-                __syncwarp();
-                // phase_dataFloat_out (:482): stage in th[0..m), consumed entries only
-                *reinterpret_cast<float4*>(th + i0) = (i0 + 3 < m) ? make_float4(el[0], el[1], el[2], el[3]) : t4;
-                if (i0 < m && i0 + 3 >= m) {
-#pragma unroll
-                    for (int v = 0; v < 4; v++) if (i0 + v < m) th[i0 + v] = el[v];
-                }
-                unsigned bw[6] = {0, 0, 0, 0, 0, 0};        // this lane's 4*bpb bits as shorts, packed in words
-                {
-                    const float inv_m = 1.0f / (float)M;
-                    const bool m_pow2 = (M & (M - 1)) == 0;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        float2 s = sv[v];
-                        float pc = 0.0f;
-                        if (diff) s = cdiv_f32(s, (v == 0) ? sprev : sv[v - 1]);                               // :488
-                        else pc = m_pow2 ? fmulr(-el[v], inv_m) : __fdiv_rn(-el[v], (float)M);                  // :494 (exact for 2^n)
-                        if (M == 4) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                     // :497-498
-                        const float2 c = derotate(s, pc);                                                      // :499-501
-                        if (i0 + v < m) selb[2 + i0 + v] = c;
-                        unsigned b = 0;
-                        if (bpb == 3) b = slice8_fast(c);
-                        else if (bpb == 1) b = (c.x < 0.0f) ? 1u : 0u;
-                        else if (bpb == 2) b = slice_bits(c, 2);
-                        // shorts: symbol v occupies shorts [v*bpb, (v+1)*bpb)
-#pragma unroll
-                        for (int j = 0; j < 3; j++) {
-                            if (j < bpb) {
-                                const int sidx = v * bpb + j;
-                                bw[sidx >> 1] |= ((b >> j) & 1u) << ((sidx & 1) * 16);
-                            }
-                        }
-                    }
-                }
-                short* bstage = reinterpret_cast<short*>(alias);           // chain buffers are dead now
-                if (bpb > 0 && prm.out_bits) {
-                    unsigned* bs32 = reinterpret_cast<unsigned*>(bstage) + lane * 2 * bpb;
-#pragma unroll
-                    for (int w = 0; w < 6; w++) if (w < 2 * bpb) bs32[w] = bw[w];
-                }
-                __syncwarp();
-                {
-                    const long long so = dg.sym_off + kchain;
-                    if (prm.out_phase) {
-                        float* o = prm.out_phase + so;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) o[i] = th[i]; }
-                    }
-                    if (prm.out_soft) {
-                        float2* o = prm.out_soft + so;
-#pragma unroll
-                        for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) o[i] = selb[2 + i]; }
-                    }
-                    if (bpb > 0 && prm.out_bits) {
-                        // bits_dataShort_out: one short per bit, LSB first (:512, 525-526, 559-563)
-                        int16_t* o = prm.out_bits + dg.bits_off + (long long)kchain * bpb;
-                        const int nsh = m * bpb;
-                        if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
-                            const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage);
-                            unsigned* o32 = reinterpret_cast<unsigned*>(o);
-                            for (int t = lane; t < (nsh >> 1); t += 32) o32[t] = s32[t];
-                            if ((nsh & 1) && lane == 0) o[nsh - 1] = bstage[nsh - 1];
-                        } else {
-                            for (int t = lane; t < nsh; t += 32) o[t] = bstage[t];
-                        }
-                    }
-                }
-                __syncwarp();
-                // ---- drop the consumed symbols from the buffer ----------------------------------------
-                const int left = nbuf - m;
-                for (int base = 0; base < left; base += 32) {
-                    const int i = base + lane;
-                    float tv = 0.f; float2 sv2 = make_float2(0.f, 0.f);
-                    if (i < left) { tv = th[m + i]; sv2 = selb[2 + m + i]; }
-                    __syncwarp();
-                    if (i < left) { th[i] = tv; selb[2 + i] = sv2; }
-                    __syncwarp();
-                }
-                if (lane == 0) selb[1] = prev_new;
-                __syncwarp();
-                nbuf = left; kchain += m;
-            }
-        };
-
-        drain();     // packets without symbols before the first chunk (and units without any symbol)
+        fz_drain<S, RRC, PC>(wofs);    // packets without symbols before the first chunk (and units without any symbol)
 
         // ---- the chunk loop ------------------------------------------------------------------------
-        for (int c = 0; c < nchunks && !unit_done; c++) {
-            const int k0 = kA + c * FZ_CH;
-            const int nrows = min(FZ_CH, kB - k0);
-            const int slot = c % NS;
-            float* slotp = ring + C::fpos(32 * slot);
-            // ingest: energies of the chunk's 32 newest rows (the windows' leading edge, :448-451)
-            if (xq_valid) {
+        // lane roles of the timing step; lanes beyond G*S (S = 9, 10) run along on (0, 0) and store nothing
+        const bool wact = lane < G * S;
+        const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
+        const float2* in_mt = cx.in_mt;
+        const int M = cx.M;
+        int slot = 0;
+        int nprev = 0;                 // rows of the previous chunk whose gathered sample waits in gx
+        int krow = cx.kA;              // first output row of chunk c
+        float2 gx = make_float2(0.f, 0.f);
+        for (int c = 0; c <= nchunks; c++, krow += FZ_CH) {
+            const bool have = c < nchunks;
+            const bool fastc = have && c >= cx.c_lo && c < cx.c_hi;
+            float4 xq[NQ];
+            if (fastc) {
+                // this chunk's samples (an L2 hit: prefetched two chunks ago); consumed after the
+                // previous chunk's angle computation below
+                const float2* cptr = in_mt + (long long)(krow + cx.lag) * S;
+                const float4* g4 = reinterpret_cast<const float4*>(cptr) + lane;
 #pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    const int f = lane + 32 * q;
-                    if ((S * 16) % 32 == 0 || f < S * 16) {
-                        const int s = 2 * f;
-                        const int off = s + (C::PADDED ? ((s / S) / R) * C::PAD : 0);
-                        const float2 e = make_float2(energy_f32(xq[q].x, xq[q].y), energy_f32(xq[q].z, xq[q].w));
-                        if (S % 2 == 0) {
-                            *reinterpret_cast<float2*>(slotp + off) = e;
-                            if (slot == 0 && s < R * S) *reinterpret_cast<float2*>(ring + C::fpos(RR) + s) = e;
-                        } else {
-                            slotp[s] = e.x; slotp[s + 1] = e.y;
-                            if (slot == 0) {
-                                if (s < R * S) ring[C::fpos(RR) + s] = e.x;
-                                if (s + 1 < R * S) ring[C::fpos(RR) + s + 1] = e.y;
+                for (int q = 0; q < NQ; q++)
+                    if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) xq[q] = __ldg(g4 + 32 * q);
+                if (lane == 0 && c + 2 < cx.c_hi) fz_prefetch_l2(cptr + 2 * CHS, CHS * 8);
+            }
+            // M-th power angle (:474) of the PREVIOUS chunk's samples (their gather has landed by now)
+            bool th_bad = false;
+            int th_at = 0;
+            if (nprev > 0) {
+                const int nb0 = cx.nbuf;
+                th_at = nb0 + lane;
+                if (lane < nprev) {
+                    th[th_at] = fz_theta(gx, M, th_bad);
+                    selb[2 + th_at] = gx;
+                }
+                __syncwarp();
+                if (lane == 0) cx.nbuf = nb0 + nprev;
+                nprev = 0;
+            }
+            if (have) {
+                const int RR = cx.RR;
+                float* slotp = ring + C::fpos(32 * slot);
+                // ingest: energies of the chunk's 32 newest rows (the windows' leading edge, :448-451)
+                if (fastc) {
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const int f = lane + 32 * q;
+                        if ((S * 16) % 32 == 0 || f < S * 16) {
+                            const int s = 2 * f;
+                            const int off = s + (C::PADDED ? ((s / S) / R) * C::PAD : 0);
+                            const float2 e = make_float2(energy_f32(xq[q].x, xq[q].y), energy_f32(xq[q].z, xq[q].w));
+                            if (S % 2 == 0) {
+                                *reinterpret_cast<float2*>(slotp + off) = e;
+                                if (slot == 0 && s < R * S) *reinterpret_cast<float2*>(ring + C::fpos(RR) + s) = e;
+                            } else {
+                                slotp[s] = e.x; slotp[s + 1] = e.y;
+                                if (slot == 0) {
+                                    if (s < R * S) ring[C::fpos(RR) + s] = e.x;
+                                    if (s + 1 < R * S) ring[C::fpos(RR) + s + 1] = e.y;
+                                }
                             }
                         }
                     }
-                }
-            } else {
-                const long long sA = (long long)(k0 + lag) * S;
-                for (int s = lane; s < 32 * S; s += 32) {
-                    const long long v = sA + s;
-                    const float2 x = (v < V) ? vs.at(v) : make_float2(0.f, 0.f);
-                    const int row = s / S, p = s - row * S;
-                    const float e = energy_f32(x.x, x.y);
-                    ring[C::fpos(32 * slot + row) + p] = e;
-                    if (slot == 0 && row < R) ring[C::fpos(RR + row) + p] = e;
-                }
-            }
-            xq_valid = false;
-            if (c + 1 < nchunks && chunk_fast(c + 1)) { chunk_issue(c + 1); xq_valid = true; }
-            __syncwarp();
-
-            // timing, part 1: exact sliding window sums, lane = (phase wp, row group wg).  Lanes
-            // beyond G*S (S = 9, 10) run along on group 0 and store nothing.
-            {
-                const int g = wact ? wg : 0, p = wact ? wp : 0;
-                const float* addp = slotp + (C::PADDED ? g * (R * S + C::PAD) : g * R * S) + p;
-                int P0 = 32 * slot + R * g - lag;
-                if (P0 < 0) P0 += RR;
-                const float* subp = ring + C::fpos(P0) + p;
-                const int tcar = C::PADDED ? (R - (P0 % R)) : 2 * R;   // rows i >= tcar sit behind one more pad
-                double Eloc[R];
-                double x = 0.0;
-#pragma unroll
-                for (int i = 0; i < R; i++) {
-                    if (G * R == 32 || R * g + i < 32) {
-                        const float a = addp[i * S];
-                        const float sb = subp[i * S + ((C::PADDED && i >= tcar) ? C::PAD : 0)];
-                        x = daddr(x, (double)a);                                          // :451
-                        Eloc[i] = x;
-                        x = dsubr(x, (double)sb);                                         // :576
-                    } else Eloc[i] = 0.0;
-                }
-                // exclusive scan of the group totals over the row groups
-                double off = Cw, tot = 0.0;
-#pragma unroll
-                for (int g2 = 0; g2 < G; g2++) {
-                    const double tg = __shfl_sync(0xffffffffu, x, g2 * S + p, 32);
-                    if (g2 < g) off = daddr(off, tg);
-                    tot = daddr(tot, tg);
-                }
-                Cw = daddr(Cw, tot);
-                if (wact) {
-#pragma unroll
-                    for (int i = 0; i < R; i++) {
-                        const int mrow = R * g + i;
-                        if (G * R == 32 || mrow < 32) ebuf[mrow * ES + p] = daddr(off, Eloc[i]);
+                } else {
+                    const long long sA = (long long)(krow + cx.lag) * S;
+                    const long long V = cx.V, tail_len = cx.tail_len;
+                    const float2* tailp = cx.tail;
+                    for (int s = lane; s < CHS; s += 32) {
+                        const long long v = sA + s;
+                        float2 x = make_float2(0.f, 0.f);
+                        if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
+                        const int row = s / S, p = s - row * S;
+                        const float e = energy_f32(x.x, x.y);
+                        ring[C::fpos(32 * slot + row) + p] = e;
+                        if (slot == 0 && row < R) ring[C::fpos(RR + row) + p] = e;
                     }
                 }
+                __syncwarp();
+                if (__any_sync(0xffffffffu, th_bad)) {          // rare: literal angle for odd inputs (no load in flight here)
+                    if (th_bad) fz_theta_fixup(th, selb + 2, th_at, (unsigned)M);
+                    __syncwarp();
+                    th_bad = false;
+                }
+
+                // timing, part 1: exact sliding window sums, lane = (phase wp, row group wg)
+                {
+                    const float* addp = slotp + (C::PADDED ? wg * (R * S + C::PAD) : wg * R * S) + wp;
+                    int P0 = 32 * slot + R * wg - cx.lag;
+                    if (P0 < 0) P0 += RR;
+                    const float* subp = ring + C::fpos(P0) + wp;
+                    double Eloc[R];
+                    const double x = fz_window<S>(addp, subp, wg, cx.tc, Eloc);
+                    // exclusive scan of the group totals over the row groups
+                    double off = Cw, tot = 0.0;
+#pragma unroll
+                    for (int g2 = 0; g2 < G; g2++) {
+                        const double tg = __shfl_sync(0xffffffffu, x, g2 * S + wp, 32);
+                        if (g2 < wg) off = daddr(off, tg);
+                        tot = daddr(tot, tg);
+                    }
+                    Cw = daddr(Cw, tot);
+                    if (wact) {
+                        double* eo = ebuf + (R * wg) * ES + wp;
+#pragma unroll
+                        for (int i = 0; i < R; i++)
+                            if (G * R == 32 || R * wg + i < 32) eo[i * ES] = daddr(off, Eloc[i]);
+                    }
+                }
+                __syncwarp();
+
+                // timing, part 2: lane = row: first maximum (:462), issue the gather (:465)
+                const int nrows = min(FZ_CH, cx.kB - krow);
+                if (lane < nrows) {
+                    const double* er = ebuf + lane * ES;
+                    double e[S];
+#pragma unroll
+                    for (int q = 0; q < S; q++) e[q] = er[q];
+                    // tournament over contiguous ranges keeps std::max_element's FIRST maximum
+                    int ix[S];
+#pragma unroll
+                    for (int q = 0; q < S; q++) ix[q] = q;
+#pragma unroll
+                    for (int lv = 0; lv < 5; lv++) {
+                        const int w = 1 << lv;
+#pragma unroll
+                        for (int q = 0; q < S; q++) {
+                            if (w < S && (q % (2 * w)) == 0 && q + w < S) {
+                                if (e[q] < e[q + w]) { e[q] = e[q + w]; ix[q] = ix[q + w]; }
+                            }
+                        }
+                    }
+                    const int idx = ix[0];
+                    int16_t* o_sidx = cx.o_sidx;
+                    if (o_sidx) __stcs(o_sidx + krow + lane, (int16_t)idx);                    // :466
+                    const long long v = (long long)(krow + lane) * S + idx;
+                    if (cx.gather_in || v >= cx.tail_len) gx = __ldg(in_mt + v);
+                    else gx = cx.tail[v];
+                }
+                nprev = nrows;
+                if (++slot == cx.NS) slot = 0;
             }
             __syncwarp();
-
-            // timing, part 2: lane = row: first maximum (:462), gather (:465), M-th power angle (:474)
-            if (lane < nrows) {
-                const double* er = ebuf + lane * ES;
-                double best = er[0]; int idx = 0;
-#pragma unroll
-                for (int q = 1; q < S; q++) { const double e = er[q]; if (best < e) { best = e; idx = q; } }
-                const int k = k0 + lane;
-                if (prm.out_sidx) prm.out_sidx[dg.sym_off + k] = (int16_t)idx;            // :466
-                const float2 x = vs.at((long long)k * S + idx);
-                th[nbuf + lane] = mth_power_angle_fast(x, (unsigned)M);
-                selb[2 + nbuf + lane] = x;
+            if (__any_sync(0xffffffffu, th_bad)) {
+                if (th_bad) fz_theta_fixup(th, selb + 2, th_at, (unsigned)M);
+                __syncwarp();
             }
-            __syncwarp();
-            nbuf += nrows;
-            drain();
+            if (cx.nbuf >= min(FZ_B, cx.pk_hi - cx.kchain)) fz_drain<S, RRC, PC>(wofs);
         }
-
-        // ---- hand the channel's state to the next unit / the next call -----------------------------
-        if (sh.st.fit.head != 0 && sh.st.fit.pts == P) fz_normalize_ring(yh, estv, sh.st.fit, P, lane);
-        for (int j = lane; j < P; j += 32) __stcg(gring + j, yh[j]);
-        if (lane == 0) {
-            if (diff && kB > kA) sh.st.last = selb[1];                                    // :489
-            const int4* src = reinterpret_cast<const int4*>(&sh.st);
-            int4* dst = reinterpret_cast<int4*>(prm.state + ch);
-#pragma unroll
-            for (int i = 0; i < (int)(sizeof(ChanState) / 16); i++) __stcg(dst + i, src[i]);
-            if (sh.st.wraps != wraps0) atomicAdd(&prm.counters->wraps, sh.st.wraps - wraps0);
-            if (sh.blocks) atomicAdd(&prm.counters->spec_chunks, (unsigned long long)sh.blocks);
-            if (sh.passes) atomicAdd(&prm.counters->spec_misses, (unsigned long long)sh.passes);
-            if (sh.seq_blocks) atomicAdd(&prm.counters->seq_channels, (unsigned long long)sh.seq_blocks);
-        }
-        __syncwarp();
-        __threadfence();
-        if (lane == 0) st_release(prm.done + ch, ug + 1);
-        __syncwarp();
+        fz_unit_end<S, RRC, PC>(prm, wofs);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int RRC, int PC>
 static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
-    using C = FzCfg<S>;
-    (void)sizeof(C);
+    using L = FzL<S, RRC, PC>;
     FusedParams p{};
     p.desc = c.d_desc; p.state = c.d_state; p.ring_base = c.d_ring;
     p.list = f.d_list; p.n_list = f.n_list;
@@ -673,24 +950,18 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     p.ticket = f.d_ticket; p.done = f.d_done;
     p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_sidx = c.out_sidx;
     p.sri_xdelta = c.sri_xdelta;
-    p.Pcap = (f.Pmax + 3) & ~3;
-    p.lay = fz_layout<S>(f.Amax, p.Pcap);
     p.counters = c.d_counters;
-    const size_t smem = (size_t)p.lay.bytes * FZ_WARPS;
-    static size_t configured = 0;
+    constexpr size_t smem = (size_t)L::BYTES * FZ_WARPS;
     static int ctas_per_sm = 0, n_sm = 0;
     cudaError_t e;
-    if (smem > configured || ctas_per_sm == 0) {
-        e = cudaFuncSetAttribute(k_fused<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ctas_per_sm == 0) {
+        e = cudaFuncSetAttribute(k_fused<S, RRC, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_fused<S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(k_fused<S, RRC, PC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fused<S>, FZ_WARPS * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (ctas_per_sm < 1) return cudaErrorInvalidConfiguration;
-    if (n_sm == 0) {
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fused<S, RRC, PC>, FZ_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) { ctas_per_sm = 0; return cudaErrorInvalidConfiguration; }
         int dev = 0;
         e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
@@ -700,7 +971,7 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     c.prof->begin(KID_FUSED, c.stream);
-    k_fused<S><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
+    k_fused<S, RRC, PC><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
     c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
@@ -713,13 +984,16 @@ bool fused_supports(int S, int A, int P) {
     return true;
 }
 
+// two shared-memory size classes: the component's defaults and below (numAvg <= 129, phaseAvg <= 52:
+// 5 CTAs of 4 warps per SM at S = 8) and everything up to FUSED_AMAX / FUSED_PMAX
 cudaError_t launch_fused(const LaunchCtx& c, const FusedLaunch& f) {
     if (f.n_list == 0) return cudaSuccess;
+    const bool small = f.Amax <= 129 && f.Pmax <= 52;
     switch (f.S) {
-        case 8:  return launch_fused_t<8>(c, f);
-        case 9:  return launch_fused_t<9>(c, f);
-        case 10: return launch_fused_t<10>(c, f);
-        case 16: return launch_fused_t<16>(c, f);
+        case 8:  return small ? launch_fused_t<8, 160, 52>(c, f) : launch_fused_t<8, 288, 128>(c, f);
+        case 9:  return small ? launch_fused_t<9, 160, 52>(c, f) : launch_fused_t<9, 288, 128>(c, f);
+        case 10: return small ? launch_fused_t<10, 160, 52>(c, f) : launch_fused_t<10, 288, 128>(c, f);
+        case 16: return launch_fused_t<16, 288, 128>(c, f);
     }
     return cudaErrorInvalidValue;
 }
