@@ -35,13 +35,16 @@
 
 namespace pskd {
 
-constexpr int FZ_WARPS = 4;            // warps (= concurrent units) per CTA
+#ifndef PSKD_FZ_WARPS
+#define PSKD_FZ_WARPS 4
+#endif
+constexpr int FZ_WARPS = PSKD_FZ_WARPS; // warps (= concurrent units) per CTA
 constexpr int FZ_CH = 32;              // input rows per ingest chunk
 constexpr int FZ_B = 128;              // symbols per chain block (4 per lane)
 constexpr int FZ_BUF = 160;            // capacity of the (theta, sample) block buffer
 constexpr int FZ_MAX_ITERS = 16;
 #ifndef PSKD_FZ_MIN_CTAS
-#define PSKD_FZ_MIN_CTAS 5
+#define PSKD_FZ_MIN_CTAS 4
 #endif
 
 struct FzCtx {                         // one per warp, shared memory
@@ -59,6 +62,7 @@ struct FzCtx {                         // one per warp, shared memory
     float fP1;
     // chunk-loop constants of the unit (parked here to keep the loop's register set small)
     int kA, kB, lag, RR, NS, tc, c_lo, c_hi, nchunks, gather_in, ch, ug;
+    int c, krow, slot, nprev;          // chunk-loop state (fz_chunk)
     long long V;
     int16_t* o_sidx;
     unsigned long long wraps0;
@@ -83,7 +87,10 @@ template <int S> struct FzCfg {
 template <int S, int RRC, int PC> struct FzL {
     using C = FzCfg<S>;
     static constexpr int RING_F = (C::fpos(RRC + C::R) + 3) & ~3;
-    static constexpr int OFF_TH = RING_F * 4;                              // float  th[FZ_BUF]
+    static constexpr int OFF_RAW = RING_F * 4;                             // float2 raw[32*S]  cp.async landing of the next chunk
+    static constexpr int OFF_GL = OFF_RAW + 32 * S * 8;                    // float2 gland[32]  cp.async landing of the gathered samples
+    static constexpr int OFF_CW = OFF_GL + 32 * 8;                         // double cwl[32]    per-lane carried window sum
+    static constexpr int OFF_TH = OFF_CW + 32 * 8;                         // float  th[FZ_BUF]
     static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                    // float2 selb[FZ_BUF + 2]; [1] = previous sample
     static constexpr int OFF_YH = fz_align16(OFF_SEL + (FZ_BUF + 2) * 8);  // float  yh[PC]   y history, logical order
     static constexpr int OFF_CTX = fz_align16(OFF_YH + PC * 4);
@@ -107,6 +114,27 @@ struct FusedParams {
 };
 
 extern __shared__ __align__(16) unsigned char fz_smem[];
+
+__device__ __forceinline__ void fz_prefetch_line(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ int fz_lane() {
+#ifdef PSKD_FZ_LANE_TID
+    return threadIdx.x & 31;
+#endif
+    int l;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));     // volatile: kept in a register, not re-derived from tid at every use
+    return l;
+}
+__device__ __forceinline__ void fz_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fz_cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fz_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -243,7 +271,7 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
     double* czblk = reinterpret_cast<double*>(wb + L::OFF_ALIAS);                    // cz[P+1 ...]
     float*  yblk = reinterpret_cast<float*>(wb + L::OFF_ALIAS + FZ_B * 8);
     float*  estv = yblk + FZ_B;
-    const int lane = threadIdx.x & 31;
+    const int lane = fz_lane();
     const int P = cx.P, M = cx.M, bpb = cx.bpb;
     double* cz = czblk - (P + 1);
 
@@ -476,9 +504,11 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
                 int16_t* o = o_bits + (long long)kchain * bpb;
                 const int nsh = m * bpb;
                 if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
-                    const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage);
-                    unsigned* o32 = reinterpret_cast<unsigned*>(o);
-                    for (int t = lane; t < (nsh >> 1); t += 32) __stcs(o32 + t, s32[t]);
+                    const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage) + lane;
+                    unsigned* o32 = reinterpret_cast<unsigned*>(o) + lane;
+                    const int nw = nsh >> 1;                  // <= 192 words
+#pragma unroll
+                    for (int q = 0; q < 6; q++) if (lane + 32 * q < nw) __stcs(o32 + 32 * q, s32[32 * q]);
                     if ((nsh & 1) && lane == 0) o[nsh - 1] = bstage[nsh - 1];
                 } else {
                     for (int t = lane; t < nsh; t += 32) o[t] = bstage[t];
@@ -536,13 +566,21 @@ __device__ __forceinline__ float2 fz_csq(float2 x) {
     return make_float2(fsubr(fmulr(x.x, x.x), fmulr(x.y, x.y)), faddr(fmulr(x.x, x.y), fmulr(x.y, x.x)));
 }
 __device__ __forceinline__ float fz_theta(float2 s, int M, bool& bad) {
+#ifdef PSKD_FZ_THETA_BRANCHY
     float2 y = s;
     if (M == 8) y = fz_csq(fz_csq(fz_csq(s)));
     else if (M == 4) y = fz_csq(fz_csq(s));
     else if (M == 2) y = fz_csq(s);
-    const float th = fz_atan2(y.y, y.x, bad);
-    bad = bad || !(M == 2 || M == 4 || M == 8);
-    return th;
+    return fz_atan2(y.y, y.x, bad);
+#else
+    // M = 2, 4, 8: one, two or three squarings, selected without branches (M is warp-uniform)
+    const float2 y1 = fz_csq(s);
+    const float2 y2 = fz_csq(y1);
+    const float2 y3 = fz_csq(y2);
+    float2 y = (M >= 8) ? y3 : y2;
+    y = (M >= 4) ? y : y1;
+    return fz_atan2(y.y, y.x, bad);
+#endif
 }
 // literal path for the lanes that asked for it: th[i] = atan2f(pow(sel[i], M)) with the library call
 static __device__ __noinline__ void fz_theta_fixup(float* th, const float2* sel, int i, unsigned M) {
@@ -607,6 +645,7 @@ __device__ __forceinline__ double fz_window(const float* addp, const float* subp
 __device__ __forceinline__ void fz_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // fz_unit_begin: claim-independent set-up of one unit: geometry, wait for the predecessor unit,
@@ -719,7 +758,8 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
         for (int g2 = 0; g2 < G; g2++) Cw = daddr(Cw, ebuf[g2 * ES + wp]);
         __syncwarp();
     }
-    ebuf[lane] = Cw;
+    reinterpret_cast<double*>(wb + L::OFF_CW)[lane] = Cw;
+    if (lane == 0) { cx.c = 0; cx.krow = kA; cx.slot = 0; cx.nprev = 0; }
     __syncwarp();
     return nchunks;
 }
@@ -757,22 +797,187 @@ static __device__ __noinline__ void fz_unit_end(const FusedParams& prm, const un
 }
 
 // ---------------------------------------------------------------------------------------------
+// fz_chunk: one iteration of the front stage (its own register allocation; all state in FzCtx):
+//   wait for the asynchronous copies; M-th power angle of the PREVIOUS chunk's gathered samples
+//   (appended to the block buffer); energies of this chunk's 32 newest rows into the ring; issue
+//   the next chunk's copy; exact sliding window sums; first maximum per row; issue the gather.
+// Global loads are cp.async copies into shared memory, so nothing is held in registers between
+// the stages: chunk c+1's samples are issued once chunk c's have been consumed, the gathered
+// samples of chunk c at its end; both are waited for at the top of iteration c+1.
+// ---------------------------------------------------------------------------------------------
+template <int S, int RRC, int PC>
+static __device__ __noinline__ void fz_chunk(const unsigned wofs)
+{
+    using C = FzCfg<S>;
+    using L = FzL<S, RRC, PC>;
+    constexpr int G = C::G, R = C::R, ES = C::ES, NQ = C::NQ;
+    constexpr int CHS = FZ_CH * S;                       // samples per chunk
+    unsigned char* wb = fz_smem + wofs;
+    float*  ring = reinterpret_cast<float*>(wb);
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);       // [32][ES] window sums
+    const int lane = threadIdx.x & 31;
+    float4* rawq = reinterpret_cast<float4*>(wb + L::OFF_RAW) + lane;
+    float2* gland = reinterpret_cast<float2*>(wb + L::OFF_GL) + lane;
+    double* cwl = reinterpret_cast<double*>(wb + L::OFF_CW) + lane;
+
+    const int c = cx.c, krow = cx.krow, slot = cx.slot, nprev = cx.nprev;
+    const int c_lo = cx.c_lo, c_hi = cx.c_hi, lag = cx.lag;
+    const float2* in_mt = cx.in_mt;
+    const int M = cx.M;
+    const bool have = c < cx.nchunks;
+    const bool fastc = have && c >= c_lo && c < c_hi;
+
+    fz_cp_async_wait_all();
+    // M-th power angle (:474) of the PREVIOUS chunk's samples
+    bool th_bad = false;
+    int th_at = 0;
+    if (nprev > 0) {
+        const int nb0 = cx.nbuf;
+        th_at = nb0 + lane;
+        if (lane < nprev) {
+            const float2 gx = *gland;
+            th[th_at] = fz_theta(gx, M, th_bad);
+            th_bad = th_bad || !(M == 2 || M == 4 || M == 8);          // other M: literal angle path
+            selb[2 + th_at] = gx;
+        }
+        __syncwarp();
+        if (lane == 0) cx.nbuf = nb0 + nprev;
+    }
+    int nrows = 0;
+    if (have) {
+        const int RR = cx.RR;
+        float* slotp = ring + C::fpos(32 * slot);
+        // ingest: energies of the chunk's 32 newest rows (the windows' leading edge, :448-451)
+        if (fastc) {
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const int f = lane + 32 * q;
+                if ((S * 16) % 32 == 0 || f < S * 16) {
+                    const float4 x = rawq[32 * q];
+                    const int s = 2 * f;
+                    const int off = s + (C::PADDED ? ((s / S) / R) * C::PAD : 0);
+                    const float2 e = make_float2(energy_f32(x.x, x.y), energy_f32(x.z, x.w));
+                    if (S % 2 == 0) {
+                        *reinterpret_cast<float2*>(slotp + off) = e;
+                        if (slot == 0 && s < R * S) *reinterpret_cast<float2*>(ring + C::fpos(RR) + s) = e;
+                    } else {
+                        slotp[s] = e.x; slotp[s + 1] = e.y;
+                        if (slot == 0) {
+                            if (s < R * S) ring[C::fpos(RR) + s] = e.x;
+                            if (s + 1 < R * S) ring[C::fpos(RR) + s + 1] = e.y;
+                        }
+                    }
+                }
+            }
+        } else {
+            const long long sA = (long long)(krow + lag) * S;
+            const long long V = cx.V, tail_len = cx.tail_len;
+            const float2* tailp = cx.tail;
+            for (int s = lane; s < CHS; s += 32) {
+                const long long v = sA + s;
+                float2 x = make_float2(0.f, 0.f);
+                if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
+                const int row = s / S, p = s - row * S;
+                const float e = energy_f32(x.x, x.y);
+                ring[C::fpos(32 * slot + row) + p] = e;
+                if (slot == 0 && row < R) ring[C::fpos(RR + row) + p] = e;
+            }
+        }
+        __syncwarp();
+        if (c + 1 >= c_lo && c + 1 < c_hi) {           // next chunk -> raw staging (own words only: no hazard)
+            const float4* g4 = reinterpret_cast<const float4*>(in_mt + (long long)(krow + FZ_CH + lag) * S) + lane;
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+                if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) fz_cp_async16(rawq + 32 * q, g4 + 32 * q);
+            // and the chunk after it towards L2, one 128-byte line per lane
+            if (c + 2 < c_hi && lane * 8 < CHS / 2) fz_prefetch_line(g4 - lane + (CHS / 2) + lane * 8);
+        }
+
+        // timing, part 1: exact sliding window sums, lane = (phase wp, row group wg); lanes beyond
+        // G*S (S = 9, 10) run along on (0, 0) and store nothing
+        {
+            const bool wact = lane < G * S;
+            const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
+            const float* addp = slotp + (C::PADDED ? wg * (R * S + C::PAD) : wg * R * S) + wp;
+            int P0 = 32 * slot + R * wg - lag;
+            if (P0 < 0) P0 += RR;
+            const float* subp = ring + C::fpos(P0) + wp;
+            double Eloc[R];
+            const double x = fz_window<S>(addp, subp, wg, cx.tc, Eloc);
+            // exclusive scan of the group totals over the row groups
+            const double Cw = *cwl;
+            double off = Cw, tot = 0.0;
+#pragma unroll
+            for (int g2 = 0; g2 < G; g2++) {
+                const double tg = __shfl_sync(0xffffffffu, x, g2 * S + wp, 32);
+                if (g2 < wg) off = daddr(off, tg);
+                tot = daddr(tot, tg);
+            }
+            *cwl = daddr(Cw, tot);
+            if (wact) {
+                double* eo = ebuf + (R * wg) * ES + wp;
+#pragma unroll
+                for (int i = 0; i < R; i++)
+                    if (G * R == 32 || R * wg + i < 32) eo[i * ES] = daddr(off, Eloc[i]);
+            }
+        }
+        __syncwarp();
+
+        // timing, part 2: lane = row: first maximum (:462), issue the gather (:465)
+        nrows = min(FZ_CH, cx.kB - krow);
+        if (lane < nrows) {
+            const double* er = ebuf + lane * ES;
+            double e[S];
+#pragma unroll
+            for (int q = 0; q < S; q++) e[q] = er[q];
+            // tournament over contiguous ranges keeps std::max_element's FIRST maximum
+            int ix[S];
+#pragma unroll
+            for (int q = 0; q < S; q++) ix[q] = q;
+#pragma unroll
+            for (int lv = 0; lv < 5; lv++) {
+                const int w = 1 << lv;
+#pragma unroll
+                for (int q = 0; q < S; q++) {
+                    if (w < S && (q % (2 * w)) == 0 && q + w < S) {
+                        if (e[q] < e[q + w]) { e[q] = e[q + w]; ix[q] = ix[q + w]; }
+                    }
+                }
+            }
+            const int idx = ix[0];
+            int16_t* o_sidx = cx.o_sidx;
+            if (o_sidx) __stcs(o_sidx + krow + lane, (int16_t)idx);                    // :466
+            const long long v = (long long)(krow + lane) * S + idx;
+            const float2* src = (cx.gather_in || v >= cx.tail_len) ? in_mt + v : cx.tail + v;
+            fz_cp_async8(gland, src);
+        }
+    }
+    if (lane == 0) {
+        int ns = slot + (have ? 1 : 0);
+        if (ns == cx.NS) ns = 0;
+        cx.c = c + 1; cx.krow = krow + FZ_CH; cx.slot = ns; cx.nprev = nrows;
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, th_bad)) {          // rare: literal angle for odd inputs
+        if (th_bad) fz_theta_fixup(th, selb + 2, th_at, (unsigned)M);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 template <int S, int RRC, int PC>
 __global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZ_MIN_CTAS)
 k_fused(const FusedParams prm)
 {
     using C = FzCfg<S>;
     using L = FzL<S, RRC, PC>;
-    constexpr int G = C::G, R = C::R, ES = C::ES, NQ = C::NQ;
-    constexpr int CHS = FZ_CH * S;                       // samples per chunk
+    constexpr int NQ = C::NQ;
     const int lane = threadIdx.x & 31;
     const unsigned wofs = (threadIdx.x >> 5) * (unsigned)L::BYTES;
-    unsigned char* wb = fz_smem + wofs;
-    float*  ring = reinterpret_cast<float*>(wb);
-    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
-    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
-    double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);       // [32][ES] window sums (ingest phase)
+    FzCtx& cx = *reinterpret_cast<FzCtx*>(fz_smem + wofs + L::OFF_CTX);
 
     for (;;) {
         int u = 0;
@@ -781,155 +986,16 @@ k_fused(const FusedParams prm)
         if (u >= prm.n_units) break;
         const int nchunks = fz_unit_begin<S, RRC, PC>(prm, wofs, u);
         if (nchunks < 0) continue;
-        double Cw = ebuf[lane];        // lane (p, g): sum over the window of output k0 WITHOUT its newest row
-        __syncwarp();
         fz_drain<S, RRC, PC>(wofs);    // packets without symbols before the first chunk (and units without any symbol)
-
-        // ---- the chunk loop ------------------------------------------------------------------------
-        // lane roles of the timing step; lanes beyond G*S (S = 9, 10) run along on (0, 0) and store nothing
-        const bool wact = lane < G * S;
-        const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
-        const float2* in_mt = cx.in_mt;
-        const int M = cx.M;
-        int slot = 0;
-        int nprev = 0;                 // rows of the previous chunk whose gathered sample waits in gx
-        int krow = cx.kA;              // first output row of chunk c
-        float2 gx = make_float2(0.f, 0.f);
-        for (int c = 0; c <= nchunks; c++, krow += FZ_CH) {
-            const bool have = c < nchunks;
-            const bool fastc = have && c >= cx.c_lo && c < cx.c_hi;
-            float4 xq[NQ];
-            if (fastc) {
-                // this chunk's samples (an L2 hit: prefetched two chunks ago); consumed after the
-                // previous chunk's angle computation below
-                const float2* cptr = in_mt + (long long)(krow + cx.lag) * S;
-                const float4* g4 = reinterpret_cast<const float4*>(cptr) + lane;
+        if (nchunks > 0 && cx.c_lo == 0 && cx.c_hi > 0) {              // chunk 0 -> raw staging
+            float4* rawq = reinterpret_cast<float4*>(fz_smem + wofs + L::OFF_RAW) + lane;
+            const float4* g4 = reinterpret_cast<const float4*>(cx.in_mt + (long long)(cx.kA + cx.lag) * S) + lane;
 #pragma unroll
-                for (int q = 0; q < NQ; q++)
-                    if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) xq[q] = __ldg(g4 + 32 * q);
-                if (lane == 0 && c + 2 < cx.c_hi) fz_prefetch_l2(cptr + 2 * CHS, CHS * 8);
-            }
-            // M-th power angle (:474) of the PREVIOUS chunk's samples (their gather has landed by now)
-            bool th_bad = false;
-            int th_at = 0;
-            if (nprev > 0) {
-                const int nb0 = cx.nbuf;
-                th_at = nb0 + lane;
-                if (lane < nprev) {
-                    th[th_at] = fz_theta(gx, M, th_bad);
-                    selb[2 + th_at] = gx;
-                }
-                __syncwarp();
-                if (lane == 0) cx.nbuf = nb0 + nprev;
-                nprev = 0;
-            }
-            if (have) {
-                const int RR = cx.RR;
-                float* slotp = ring + C::fpos(32 * slot);
-                // ingest: energies of the chunk's 32 newest rows (the windows' leading edge, :448-451)
-                if (fastc) {
-#pragma unroll
-                    for (int q = 0; q < NQ; q++) {
-                        const int f = lane + 32 * q;
-                        if ((S * 16) % 32 == 0 || f < S * 16) {
-                            const int s = 2 * f;
-                            const int off = s + (C::PADDED ? ((s / S) / R) * C::PAD : 0);
-                            const float2 e = make_float2(energy_f32(xq[q].x, xq[q].y), energy_f32(xq[q].z, xq[q].w));
-                            if (S % 2 == 0) {
-                                *reinterpret_cast<float2*>(slotp + off) = e;
-                                if (slot == 0 && s < R * S) *reinterpret_cast<float2*>(ring + C::fpos(RR) + s) = e;
-                            } else {
-                                slotp[s] = e.x; slotp[s + 1] = e.y;
-                                if (slot == 0) {
-                                    if (s < R * S) ring[C::fpos(RR) + s] = e.x;
-                                    if (s + 1 < R * S) ring[C::fpos(RR) + s + 1] = e.y;
-                                }
-                            }
-                        }
-                    }
-                } else {
-                    const long long sA = (long long)(krow + cx.lag) * S;
-                    const long long V = cx.V, tail_len = cx.tail_len;
-                    const float2* tailp = cx.tail;
-                    for (int s = lane; s < CHS; s += 32) {
-                        const long long v = sA + s;
-                        float2 x = make_float2(0.f, 0.f);
-                        if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
-                        const int row = s / S, p = s - row * S;
-                        const float e = energy_f32(x.x, x.y);
-                        ring[C::fpos(32 * slot + row) + p] = e;
-                        if (slot == 0 && row < R) ring[C::fpos(RR + row) + p] = e;
-                    }
-                }
-                __syncwarp();
-                if (__any_sync(0xffffffffu, th_bad)) {          // rare: literal angle for odd inputs (no load in flight here)
-                    if (th_bad) fz_theta_fixup(th, selb + 2, th_at, (unsigned)M);
-                    __syncwarp();
-                    th_bad = false;
-                }
-
-                // timing, part 1: exact sliding window sums, lane = (phase wp, row group wg)
-                {
-                    const float* addp = slotp + (C::PADDED ? wg * (R * S + C::PAD) : wg * R * S) + wp;
-                    int P0 = 32 * slot + R * wg - cx.lag;
-                    if (P0 < 0) P0 += RR;
-                    const float* subp = ring + C::fpos(P0) + wp;
-                    double Eloc[R];
-                    const double x = fz_window<S>(addp, subp, wg, cx.tc, Eloc);
-                    // exclusive scan of the group totals over the row groups
-                    double off = Cw, tot = 0.0;
-#pragma unroll
-                    for (int g2 = 0; g2 < G; g2++) {
-                        const double tg = __shfl_sync(0xffffffffu, x, g2 * S + wp, 32);
-                        if (g2 < wg) off = daddr(off, tg);
-                        tot = daddr(tot, tg);
-                    }
-                    Cw = daddr(Cw, tot);
-                    if (wact) {
-                        double* eo = ebuf + (R * wg) * ES + wp;
-#pragma unroll
-                        for (int i = 0; i < R; i++)
-                            if (G * R == 32 || R * wg + i < 32) eo[i * ES] = daddr(off, Eloc[i]);
-                    }
-                }
-                __syncwarp();
-
-                // timing, part 2: lane = row: first maximum (:462), issue the gather (:465)
-                const int nrows = min(FZ_CH, cx.kB - krow);
-                if (lane < nrows) {
-                    const double* er = ebuf + lane * ES;
-                    double e[S];
-#pragma unroll
-                    for (int q = 0; q < S; q++) e[q] = er[q];
-                    // tournament over contiguous ranges keeps std::max_element's FIRST maximum
-                    int ix[S];
-#pragma unroll
-                    for (int q = 0; q < S; q++) ix[q] = q;
-#pragma unroll
-                    for (int lv = 0; lv < 5; lv++) {
-                        const int w = 1 << lv;
-#pragma unroll
-                        for (int q = 0; q < S; q++) {
-                            if (w < S && (q % (2 * w)) == 0 && q + w < S) {
-                                if (e[q] < e[q + w]) { e[q] = e[q + w]; ix[q] = ix[q + w]; }
-                            }
-                        }
-                    }
-                    const int idx = ix[0];
-                    int16_t* o_sidx = cx.o_sidx;
-                    if (o_sidx) __stcs(o_sidx + krow + lane, (int16_t)idx);                    // :466
-                    const long long v = (long long)(krow + lane) * S + idx;
-                    if (cx.gather_in || v >= cx.tail_len) gx = __ldg(in_mt + v);
-                    else gx = cx.tail[v];
-                }
-                nprev = nrows;
-                if (++slot == cx.NS) slot = 0;
-            }
-            __syncwarp();
-            if (__any_sync(0xffffffffu, th_bad)) {
-                if (th_bad) fz_theta_fixup(th, selb + 2, th_at, (unsigned)M);
-                __syncwarp();
-            }
+            for (int q = 0; q < NQ; q++)
+                if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) fz_cp_async16(rawq + 32 * q, g4 + 32 * q);
+        }
+        for (int c = 0; c <= nchunks; c++) {
+            fz_chunk<S, RRC, PC>(wofs);
             if (cx.nbuf >= min(FZ_B, cx.pk_hi - cx.kchain)) fz_drain<S, RRC, PC>(wofs);
         }
         fz_unit_end<S, RRC, PC>(prm, wofs);
