@@ -32,6 +32,7 @@
 // allocation; everything it shares with the chunk loop lives in the warp's FzCtx in shared memory.
 #include "pskd_internal.h"
 #include "pskd_device.cuh"
+#include <cstdlib>
 
 namespace pskd {
 
@@ -831,6 +832,115 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
     const bool fastc = have && c >= c_lo && c < c_hi;
 
     fz_cp_async_wait_all();
+#ifndef PSKD_FZ_NO_STEADY
+    // ---- steady state: full previous chunk, full fast chunk, M in {2,4,8}.  Same work as the general
+    // path below, without lane predicates, so that the angle computation, the energies and the shared-
+    // memory traffic of the stages sit in few large basic blocks and overlap in the instruction stream.
+    if (fastc && nprev == FZ_CH && cx.kB - krow >= FZ_CH && (M == 2 || M == 4 || M == 8)) {
+        const int RR = cx.RR;
+        float* slotp = ring + C::fpos(32 * slot);
+        const int nb0 = cx.nbuf;
+        const float2 gx = *gland;
+        float4 xr[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+            if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) xr[q] = rawq[32 * q];
+        bool bad = false;
+        const float thv = fz_theta(gx, M, bad);
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int f = lane + 32 * q;
+            if ((S * 16) % 32 == 0 || f < S * 16) {
+                const int s = 2 * f;
+                const int off = s + (C::PADDED ? ((s / S) / R) * C::PAD : 0);
+                const float2 e = make_float2(energy_f32(xr[q].x, xr[q].y), energy_f32(xr[q].z, xr[q].w));
+                if (S % 2 == 0) {
+                    *reinterpret_cast<float2*>(slotp + off) = e;
+                    if (slot == 0 && s < R * S) *reinterpret_cast<float2*>(ring + C::fpos(RR) + s) = e;
+                } else {
+                    slotp[s] = e.x; slotp[s + 1] = e.y;
+                    if (slot == 0) {
+                        if (s < R * S) ring[C::fpos(RR) + s] = e.x;
+                        if (s + 1 < R * S) ring[C::fpos(RR) + s + 1] = e.y;
+                    }
+                }
+            }
+        }
+        th[nb0 + lane] = thv;
+        selb[2 + nb0 + lane] = gx;
+        __syncwarp();
+        if (c + 1 < c_hi) {                            // next chunk -> raw staging (own words only: no hazard)
+            const float4* g4 = reinterpret_cast<const float4*>(in_mt + (long long)(krow + FZ_CH + lag) * S) + lane;
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+                if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) fz_cp_async16(rawq + 32 * q, g4 + 32 * q);
+            if (c + 2 < c_hi && lane * 8 < CHS / 2) fz_prefetch_line(g4 - lane + (CHS / 2) + lane * 8);
+        }
+        {
+            const bool wact = lane < G * S;
+            const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
+            const float* addp = slotp + (C::PADDED ? wg * (R * S + C::PAD) : wg * R * S) + wp;
+            int P0 = 32 * slot + R * wg - lag;
+            if (P0 < 0) P0 += RR;
+            const float* subp = ring + C::fpos(P0) + wp;
+            double Eloc[R];
+            const double x = fz_window<S>(addp, subp, wg, cx.tc, Eloc);
+            const double Cw = *cwl;
+            double off = Cw, tot = 0.0;
+#pragma unroll
+            for (int g2 = 0; g2 < G; g2++) {
+                const double tg = __shfl_sync(0xffffffffu, x, g2 * S + wp, 32);
+                if (g2 < wg) off = daddr(off, tg);
+                tot = daddr(tot, tg);
+            }
+            *cwl = daddr(Cw, tot);
+            if (wact) {
+                double* eo = ebuf + (R * wg) * ES + wp;
+#pragma unroll
+                for (int i = 0; i < R; i++)
+                    if (G * R == 32 || R * wg + i < 32) eo[i * ES] = daddr(off, Eloc[i]);
+            }
+        }
+        __syncwarp();
+        {
+            const double* er = ebuf + lane * ES;
+            double e[S];
+#pragma unroll
+            for (int q = 0; q < S; q++) e[q] = er[q];
+            int ix[S];
+#pragma unroll
+            for (int q = 0; q < S; q++) ix[q] = q;
+#pragma unroll
+            for (int lv = 0; lv < 5; lv++) {
+                const int w = 1 << lv;
+#pragma unroll
+                for (int q = 0; q < S; q++) {
+                    if (w < S && (q % (2 * w)) == 0 && q + w < S) {
+                        if (e[q] < e[q + w]) { e[q] = e[q + w]; ix[q] = ix[q + w]; }
+                    }
+                }
+            }
+            const int idx = ix[0];
+            int16_t* o_sidx = cx.o_sidx;
+            if (o_sidx) __stcs(o_sidx + krow + lane, (int16_t)idx);                        // :466
+            const long long v = (long long)(krow + lane) * S + idx;
+            const float2* src = (cx.gather_in || v >= cx.tail_len) ? in_mt + v : cx.tail + v;
+            fz_cp_async8(gland, src);
+        }
+        if (lane == 0) {
+            int ns = slot + 1;
+            if (ns == cx.NS) ns = 0;
+            cx.nbuf = nb0 + FZ_CH;
+            cx.c = c + 1; cx.krow = krow + FZ_CH; cx.slot = ns;       // nprev stays FZ_CH
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, bad)) {            // rare: literal angle for odd inputs
+            if (bad) fz_theta_fixup(th, selb + 2, nb0 + lane, (unsigned)M);
+            __syncwarp();
+        }
+        return;
+    }
+#endif
     // M-th power angle (:474) of the PREVIOUS chunk's samples
     bool th_bad = false;
     int th_at = 0;
@@ -1017,7 +1127,8 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_sidx = c.out_sidx;
     p.sri_xdelta = c.sri_xdelta;
     p.counters = c.d_counters;
-    constexpr size_t smem = (size_t)L::BYTES * FZ_WARPS;
+    static size_t pad = getenv("PSKD_FZ_PAD_SMEM") ? (size_t)atoi(getenv("PSKD_FZ_PAD_SMEM")) : 0;   // tuning: lowers occupancy
+    const size_t smem = (size_t)L::BYTES * FZ_WARPS + pad;
     static int ctas_per_sm = 0, n_sm = 0;
     cudaError_t e;
     if (ctas_per_sm == 0) {
