@@ -257,6 +257,107 @@ __device__ __forceinline__ void fz_store_bits(unsigned* dst, const unsigned b[4]
 }
 
 // ---------------------------------------------------------------------------------------------
+// sincosf for the derotation phasor (cpp/psk_soft.cpp:499, std::polar(1.0f, pc)).  Three-term
+// Cody-Waite reduction by pi/2 and the Cephes single-precision kernels: |error| <= 1e-7 for
+// |pc| < 1e4 (glibc's and CUDA's sincosf are "about an ulp" functions as well; the soft output's
+// tolerance is 1e-4).  Larger / non-finite arguments take the library call.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fz_sincos(float x, float& sn, float& cs, bool& bad) {
+    bad = bad || !(fabsf(x) < 1.0e4f);
+    const float t = fmaf(x, 0.63661977236758134f, 12582912.0f);      // x * 2/pi, rounded to an integer in the low bits
+    const int q = __float_as_int(t);
+    const float j = t - 12582912.0f;
+    float r = fmaf(-j, 1.5707962513e+0f, x);
+    r = fmaf(-j, 7.5497894159e-8f, r);
+    r = fmaf(-j, 5.3903029534e-15f, r);
+    const float r2 = r * r;
+    float ps = fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f);
+    ps = fmaf(ps, r2, -1.6666654611e-1f);
+    const float s0 = fmaf(r * r2, ps, r);
+    float pc = fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f);
+    pc = fmaf(pc, r2, 4.166664568298827e-2f);
+    const float c0 = fmaf(r2 * r2, pc, fmaf(-0.5f, r2, 1.0f));
+    const float ss = (q & 1) ? c0 : s0, cc = (q & 1) ? s0 : c0;
+    sn = (q & 2) ? -ss : ss;
+    cs = ((q + 1) & 2) ? -cc : cc;
+}
+
+// 8-PSK slicer (cpp/psk_soft.cpp:547-563) as a sector test against the rays at odd multiples of
+// pi/8; inside a guard band of the rays (or for zero / non-finite input) `bad` asks for the literal
+// atan2f -> /pi*4 -> roundf path.
+__device__ __forceinline__ unsigned fz_slice8_flag(float2 c, bool& bad) {
+    const float a = fabsf(c.x), b = fabsf(c.y);
+    const float T = 0.41421356237309503f;       // tan(pi/8)
+    const float sum = a + b;
+    const float d1 = b - T * a, d2 = a - T * b;
+    const float g = 1.0e-5f * sum;
+    bad = bad || !(sum > 0.0f) || !(sum < 3.0e38f) || fabsf(d1) <= g || fabsf(d2) <= g;
+    const unsigned quad = (c.x > 0.0f) ? ((c.y > 0.0f) ? 1u : 7u) : ((c.y > 0.0f) ? 3u : 5u);
+    const unsigned ax = (c.x > 0.0f) ? 0u : 4u, ay = (c.y > 0.0f) ? 2u : 6u;
+    return (d1 < 0.0f) ? ax : ((d2 < 0.0f) ? ay : quad);
+}
+
+// sample / last (libgcc __divsc3: evaluated in double, narrowed to float; cpp/psk_soft.cpp:488) with
+// one reciprocal: the double quotients are within 2 ulp(double) of the divided ones, i.e. the
+// narrowed floats differ in ~1e-8 of the cases by one float ulp.  Zero / non-finite operands or
+// results ask for the literal path.
+__device__ __forceinline__ float2 fz_cdiv_fast(float2 n, float2 dn, bool& bad) {
+    const double a = n.x, b = n.y, c = dn.x, d = dn.y;
+    const double denom = fma(c, c, d * d);
+    const double r = 1.0 / denom;
+    const float x = __double2float_rn((a * c + b * d) * r);
+    const float y = __double2float_rn((b * c - a * d) * r);
+    bad = bad || !(denom > 1.0e-300 && denom < 1.0e300) || !(fabsf(x) < 3.0e38f) || !(fabsf(y) < 3.0e38f);
+    return make_float2(x, y);
+}
+
+// the literal path of one symbol: libgcc-style division, library sincosf, checked complex
+// multiply, atan2f slicer -- for the symbols whose fast evaluation raised a flag
+static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float est, int M, int bpb, int diff,
+                                                    float2* c_stage, short* b_stage) {
+    float2 x = s;
+    if (diff) x = cdiv_f32(s, prev);
+    const float pc = phase_correction(est, M, diff != 0);
+    const float2 c = derotate(x, pc);
+    *c_stage = c;
+    const unsigned b = slice_bits(c, bpb);
+    for (int j = 0; j < bpb; j++) b_stage[j] = (short)((b >> j) & 1u);
+}
+
+// derotate / differential decode / slice of a lane's four symbols (cpp/psk_soft.cpp:484-566),
+// specialised on bits per symbol and on differential decoding so that the four symbols form one
+// branch-free, call-free instruction stream.  QPSK <=> BPB == 2 (constelationSize 4).  Returns
+// the mask of symbols that need fz_back_literal.
+template <int BPB, bool DIFF>
+__device__ __forceinline__ unsigned fz_back4(const float2 (&sv)[4], float2 sprev, const float (&el)[4], int M,
+                                             float2 (&cv)[4], unsigned (&bsym)[4]) {
+    const float inv_m = 1.0f / (float)M;
+    unsigned badmask = (BPB == 0 && (M & (M - 1)) != 0) ? 0xfu : 0u;       // -est/M not an exact multiply
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        bool bad = false;
+        float2 s = sv[v];
+        float pc = 0.0f;
+        if (DIFF) s = fz_cdiv_fast(s, (v == 0) ? sprev : sv[v - 1], bad);                         // :488
+        else pc = fmulr(-el[v], inv_m);                                                           // :494 (exact for M = 2^n)
+        if (BPB == 2) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                     // :497-498
+        float sn, cs;
+        fz_sincos(pc, sn, cs, bad);                                                               // :499
+        const float x = fsubr(fmulr(s.x, cs), fmulr(s.y, sn));                                    // :500-501, unfused
+        const float y = faddr(fmulr(s.x, sn), fmulr(s.y, cs));
+        bad = bad || (isnan(x) && isnan(y));                                                      // __mulsc3 recovery
+        cv[v] = make_float2(x, y);
+        unsigned b = 0;
+        if (BPB == 3) b = fz_slice8_flag(cv[v], bad);
+        else if (BPB == 1) b = (x < 0.0f) ? 1u : 0u;
+        else if (BPB == 2) b = ((x != 0.0f) != (y != 0.0f) ? 1u : 0u) | ((y != 0.0f) ? 0u : 2u);   // :523-526 (float -> bool, sic)
+        bsym[v] = b;
+        badmask |= bad ? (1u << v) : 0u;
+    }
+    return badmask;
+}
+
+// ---------------------------------------------------------------------------------------------
 // fz_drain: consume buffered symbols: chain blocks of FZ_B (shorter at a packet end) followed by
 // the output stage; runs the packet epilogue / next prologue whenever a packet is exhausted.
 // ---------------------------------------------------------------------------------------------
@@ -453,23 +554,19 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
             for (int v = 0; v < 3; v++) if (i0 + v < m) th[i0 + v] = el[v];
         }
         unsigned bsym[4];
+        unsigned fixmask = 0;
         {
-            const float inv_m = 1.0f / (float)M;
-            const bool m_pow2 = (M & (M - 1)) == 0;
             float2 cv[4];
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                float2 s = sv[v];
-                float pc = 0.0f;
-                if (diff) s = fz_cdiv(s, (v == 0) ? sprev : sv[v - 1]);                                 // :488
-                else pc = m_pow2 ? fmulr(-el[v], inv_m) : __fdiv_rn(-el[v], (float)M);                   // :494 (exact for 2^n)
-                if (M == 4) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                      // :497-498
-                cv[v] = derotate(s, pc);                                                                // :499-501
-                unsigned b = 0;
-                if (bpb == 3) b = fz_slice8(cv[v]);
-                else if (bpb == 1) b = (cv[v].x < 0.0f) ? 1u : 0u;
-                else if (bpb == 2) b = slice_bits(cv[v], 2);
-                bsym[v] = b;
+            unsigned badmask;
+            switch (bpb * 2 + (diff ? 1 : 0)) {
+                case 6: badmask = fz_back4<3, false>(sv, sprev, el, M, cv, bsym); break;
+                case 7: badmask = fz_back4<3, true>(sv, sprev, el, M, cv, bsym); break;
+                case 4: badmask = fz_back4<2, false>(sv, sprev, el, M, cv, bsym); break;
+                case 5: badmask = fz_back4<2, true>(sv, sprev, el, M, cv, bsym); break;
+                case 2: badmask = fz_back4<1, false>(sv, sprev, el, M, cv, bsym); break;
+                case 3: badmask = fz_back4<1, true>(sv, sprev, el, M, cv, bsym); break;
+                case 0: badmask = fz_back4<0, false>(sv, sprev, el, M, cv, bsym); break;
+                default: badmask = fz_back4<0, true>(sv, sprev, el, M, cv, bsym); break;
             }
             if (i0 + 3 < m) {
                 *reinterpret_cast<float4*>(selb + 2 + i0) = make_float4(cv[0].x, cv[0].y, cv[1].x, cv[1].y);
@@ -478,6 +575,9 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
 #pragma unroll
                 for (int v = 0; v < 3; v++) if (i0 + v < m) selb[2 + i0 + v] = cv[v];
             }
+#pragma unroll
+            for (int v = 0; v < 4; v++) if (i0 + v >= m) badmask &= ~(1u << v);
+            fixmask = badmask;
         }
         short* bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS);           // chain buffers are dead now
         int16_t* o_bits = cx.o_bits;
@@ -486,6 +586,14 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
             if (bpb == 3) fz_store_bits<3>(dst, bsym);
             else if (bpb == 2) fz_store_bits<2>(dst, bsym);
             else fz_store_bits<1>(dst, bsym);
+        }
+        if (__any_sync(0xffffffffu, fixmask != 0)) {            // rare: literal evaluation of the flagged symbols
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                if ((fixmask >> v) & 1u)
+                    fz_back_literal(sv[v], (v == 0) ? sprev : sv[(v + 3) & 3], el[v], M, bpb, diff ? 1 : 0,
+                                    selb + 2 + i0 + v, bstage + (i0 + v) * bpb);
+            }
         }
         __syncwarp();
         {
