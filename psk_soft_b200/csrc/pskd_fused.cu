@@ -207,14 +207,17 @@ static __device__ __noinline__ int fz_unwrap_count_slow(float est_prev, float th
     const double dlt = dsubr((double)est_prev, (double)theta);
     return (int)(long long)round(__ddiv_rn(dlt, PSKD_M_2PI));
 }
-// the reference's unwrap count (cpp/psk_soft.cpp:477), fast form with a guard band (see unwrap_count)
-__device__ __forceinline__ int fz_unwrap_count(float est_prev, float theta) {
+// the reference's unwrap count (cpp/psk_soft.cpp:477), fast form: multiply by 1/2pi and round to
+// nearest; `bad` is raised whenever the quotient is within 1e-7 of a half-integer (where the
+// division's last bit or the tie rule could matter) -- the caller then takes the literal
+// division + round().
+__device__ __forceinline__ int fz_unwrap_count(float est_prev, float theta, bool& bad) {
     const double dlt = dsubr((double)est_prev, (double)theta);       // exact
     const double q = dmulr(dlt, 0.15915494309189535);
     const double t = daddr(q, 6755399441055744.0);                   // 1.5 * 2^52: round to nearest integer
     const double qr = dsubr(t, 6755399441055744.0);
     const double fr = fabs(dsubr(q, qr));
-    if (fr > 0.4999999 || !(fabs(q) < 1.0e9)) return fz_unwrap_count_slow(est_prev, theta);
+    bad = bad || fr > 0.4999999 || !(fabs(q) < 1.0e9);
     return __double2loint(t);
 }
 
@@ -435,7 +438,7 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
                 for (int v = 0; v < 4; v++) {
                     const float pv = (v == 0) ? tprev : tl[v - 1];
                     int dn = -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
-                    if (v == 0 && lane == 0) dn = fz_unwrap_count(est0, tl[0]);
+                    if (v == 0 && lane == 0) dn = fz_unwrap_count_slow(est0, tl[0]);
                     run += dn; nloc[v] = run;
                 }
                 const int off = warp_scan_int(run, lane) - run;
@@ -480,12 +483,19 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
                 // verify every predicted n against the reference's rule (:477) with est_{i-1}
                 const float eprev = __shfl_up_sync(0xffffffffu, el[3], 1);
                 int mymis = 0x7fffffff, mydelta = 0;
+                {
+                    int nt[4];
+                    bool knife = false;
 #pragma unroll
-                for (int v = 3; v >= 0; v--) {
-                    const int i = i0 + v;
-                    if (i >= 1 && i < m) {
-                        const int nt = fz_unwrap_count((v == 0) ? eprev : el[v - 1], tl[v]);
-                        if (nt != nloc[v]) { mymis = i; mydelta = nt - nloc[v]; }
+                    for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count((v == 0) ? eprev : el[v - 1], tl[v], knife);
+                    if (__any_sync(0xffffffffu, knife)) {           // rare: a quotient next to a half-integer
+#pragma unroll
+                        for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count_slow((v == 0) ? eprev : el[v - 1], tl[v]);
+                    }
+#pragma unroll
+                    for (int v = 3; v >= 0; v--) {
+                        const int i = i0 + v;
+                        if (i >= 1 && i < m && nt[v] != nloc[v]) { mymis = i; mydelta = nt[v] - nloc[v]; }
                     }
                 }
                 const int mis = (int)__reduce_min_sync(0xffffffffu, (unsigned)mymis);
