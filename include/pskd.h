@@ -146,6 +146,16 @@ void* pskd_stream(pskd_handle h);
 int pskd_get_sri(pskd_handle h, int ch, pskd_sri_out* sri);
 int pskd_get_stats(pskd_handle h, pskd_stats* st);
 
+/* ---- checkpoint / resume of a bank's carried state (reference: the members at cpp/psk_soft.h:66-86 of
+ * every channel: the timing window's samples, the LinearFit history and sums, phaseEstimate, `last`,
+ * sampleRate, the three reset flags; plus the live properties and the out-SRI bookkeeping).  The
+ * reference has no checkpointing -- its state dies with the process; this lets a
+ * caller migrate a live bank to another process / GPU or survive a restart without re-acquisition.
+ * The blob is self-describing (magic, version, n_channels) and position-independent. */
+size_t pskd_state_size(pskd_handle h);                         /* bytes pskd_state_export writes right now */
+int pskd_state_export(pskd_handle h, void* host_buf, size_t cap, size_t* written);
+int pskd_state_import(pskd_handle h, const void* host_buf, size_t n_bytes);   /* bank must have the same n_channels */
+
 /* number of kernel launches this bank has issued since create (bench.py's gpu_launches) */
 uint64_t pskd_launch_count(pskd_handle h);
 

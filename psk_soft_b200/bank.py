@@ -113,6 +113,19 @@ class Bank:
         self._check(self.lib.pskd_profile_read(self._h, arr, 16, C.byref(n), int(reset)))
         return {arr[i].name.decode(): (arr[i].ms_total, int(arr[i].launches)) for i in range(min(n.value, 16))}
 
+    # -- checkpoint / resume -----------------------------------------------------------------
+    def export_state(self) -> bytes:
+        """the bank's carried state (cpp/psk_soft.h:66-86 of every channel) as one blob"""
+        n = int(self.lib.pskd_state_size(self._h))
+        buf = C.create_string_buffer(n)
+        w = C.c_size_t(0)
+        self._check(self.lib.pskd_state_export(self._h, buf, n, C.byref(w)))
+        return buf.raw[:w.value]
+
+    def import_state(self, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(self.lib.pskd_state_import(self._h, buf, len(blob)))
+
     # -- the hot path ----------------------------------------------------------------------
     def process_raw(self, iq_ptr, iq_stride, n_complex, soft_ptr, bits_ptr, phase_ptr, sidx_ptr, sym_stride,
                     bits_stride, xdelta=0.01, packet_len=64000, flags=0, sri_mode=1, counts=True):

@@ -20,7 +20,7 @@ FLAG_HOST_BUFFERS, FLAG_QUEUE_FLUSHED, FLAG_SRI_CHANGED, FLAG_NO_SYNC = 1, 2, 4,
 EXPORTS = ("pskd_default_props", "pskd_create", "pskd_destroy", "pskd_set_props", "pskd_get_props",
            "pskd_max_symbols", "pskd_process", "pskd_sync", "pskd_stream", "pskd_get_sri", "pskd_get_stats",
            "pskd_launch_count", "pskd_last_error", "pskd_abi_version", "pskd_synth_fill",
-           "pskd_profile_enable", "pskd_profile_read")
+           "pskd_profile_enable", "pskd_profile_read", "pskd_state_size", "pskd_state_export", "pskd_state_import")
 
 
 class Props(C.Structure):
@@ -95,6 +95,9 @@ def load(build_if_missing: bool = True):
     lib.pskd_profile_enable.argtypes = [H, C.c_int]; lib.pskd_profile_enable.restype = C.c_int
     lib.pskd_profile_read.argtypes = [H, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int), C.c_int]
     lib.pskd_profile_read.restype = C.c_int
+    lib.pskd_state_size.argtypes = [H]; lib.pskd_state_size.restype = C.c_size_t
+    lib.pskd_state_export.argtypes = [H, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]; lib.pskd_state_export.restype = C.c_int
+    lib.pskd_state_import.argtypes = [H, C.c_void_p, C.c_size_t]; lib.pskd_state_import.restype = C.c_int
     lib.pskd_synth_fill.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t, C.POINTER(Synth), C.c_void_p]
     lib.pskd_synth_fill.restype = C.c_int
     _lib = lib

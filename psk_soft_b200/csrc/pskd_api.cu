@@ -342,6 +342,111 @@ int pskd_get_stats(pskd_handle b, pskd_stats* st) {
     return PSKD_OK;
 }
 
+// ---- checkpoint / resume ----------------------------------------------------------------------
+namespace {
+struct StateHeader { uint32_t magic, version; int32_t n_channels, ring_cap; uint64_t total_bytes; };
+struct StateChan {           // host-side view of one channel (ChanHost without the device offsets)
+    pskd_props props, latched;
+    long long tail_len;
+    int32_t resetNumSymbols, resetPhaseAvg, resetSamplesPerBaud, first_packet, fit_n;
+    uint64_t symbolEnergySize;
+    pskd_sri_out sri;
+    ChanState dev;
+};
+constexpr uint32_t STATE_MAGIC = 0x444b5350u /* "PSKD" */, STATE_VERSION = 1;
+}
+
+size_t pskd_state_size(pskd_handle b) {
+    if (!b) return 0;
+    size_t n = sizeof(StateHeader) + (size_t)b->n_channels * (sizeof(StateChan) + (size_t)b->ring_cap * sizeof(float));
+    for (auto& c : b->ch) n += (size_t)c.tail_len * sizeof(float2);
+    return n;
+}
+
+int pskd_state_export(pskd_handle b, void* host_buf, size_t cap, size_t* written) {
+    if (!b || !host_buf) return fail(PSKD_ERR_ARG, "pskd_state_export: bad arguments");
+    const size_t need = pskd_state_size(b);
+    if (cap < need) return fail(PSKD_ERR_CAPACITY, "pskd_state_export: %zu bytes needed, %zu given", need, cap);
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    const int nch = b->n_channels;
+    std::vector<ChanState> dev(nch);
+    CUDA_TRY(cudaMemcpy(dev.data(), b->d_state, sizeof(ChanState) * nch, cudaMemcpyDeviceToHost));
+    unsigned char* p = static_cast<unsigned char*>(host_buf);
+    StateHeader h{STATE_MAGIC, STATE_VERSION, nch, b->ring_cap, (uint64_t)need};
+    memcpy(p, &h, sizeof(h)); p += sizeof(h);
+    for (int i = 0; i < nch; i++) {
+        const ChanHost& c = b->ch[i];
+        StateChan sc;
+        memset(&sc, 0, sizeof(sc));
+        sc.props = c.props; sc.latched = c.latched; sc.tail_len = c.tail_len;
+        sc.resetNumSymbols = c.resetNumSymbols; sc.resetPhaseAvg = c.resetPhaseAvg; sc.resetSamplesPerBaud = c.resetSamplesPerBaud;
+        sc.first_packet = c.first_packet; sc.fit_n = c.fit_n; sc.symbolEnergySize = c.symbolEnergySize; sc.sri = c.sri;
+        sc.dev = dev[i];
+        memcpy(p, &sc, sizeof(sc)); p += sizeof(sc);
+    }
+    CUDA_TRY(cudaMemcpy(p, b->d_ring, (size_t)nch * b->ring_cap * sizeof(float), cudaMemcpyDeviceToHost));
+    p += (size_t)nch * b->ring_cap * sizeof(float);
+    for (int i = 0; i < nch; i++) {
+        const ChanHost& c = b->ch[i];
+        if (c.tail_len > 0) {
+            CUDA_TRY(cudaMemcpy(p, b->d_tail[b->tail_cur] + c.tail_off, (size_t)c.tail_len * sizeof(float2), cudaMemcpyDeviceToHost));
+            p += (size_t)c.tail_len * sizeof(float2);
+        }
+    }
+    if (written) *written = (size_t)(p - static_cast<unsigned char*>(host_buf));
+    return PSKD_OK;
+}
+
+int pskd_state_import(pskd_handle b, const void* host_buf, size_t n_bytes) {
+    if (!b || !host_buf || n_bytes < sizeof(StateHeader)) return fail(PSKD_ERR_ARG, "pskd_state_import: bad arguments");
+    const unsigned char* p = static_cast<const unsigned char*>(host_buf);
+    StateHeader h;
+    memcpy(&h, p, sizeof(h)); p += sizeof(h);
+    if (h.magic != STATE_MAGIC || h.version != STATE_VERSION) return fail(PSKD_ERR_ARG, "pskd_state_import: not a pskd state blob (or another version)");
+    if (h.n_channels != b->n_channels) return fail(PSKD_ERR_ARG, "pskd_state_import: blob has %d channels, bank has %d", h.n_channels, b->n_channels);
+    if (h.total_bytes > n_bytes || h.ring_cap < 0) return fail(PSKD_ERR_ARG, "pskd_state_import: truncated blob");
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    const int nch = b->n_channels;
+    std::vector<StateChan> sc(nch);
+    memcpy(sc.data(), p, sizeof(StateChan) * nch); p += sizeof(StateChan) * nch;
+    for (int i = 0; i < nch; i++) {
+        int rc = check_props(sc[i].props);
+        if (rc != PSKD_OK) return rc;
+        if (sc[i].tail_len < 0) return fail(PSKD_ERR_ARG, "pskd_state_import: corrupt blob");
+    }
+    for (int i = 0; i < nch; i++) {
+        ChanHost& c = b->ch[i];
+        c.props = sc[i].props; c.latched = sc[i].latched;
+        c.resetNumSymbols = sc[i].resetNumSymbols != 0; c.resetPhaseAvg = sc[i].resetPhaseAvg != 0;
+        c.resetSamplesPerBaud = sc[i].resetSamplesPerBaud != 0; c.first_packet = sc[i].first_packet != 0;
+        c.fit_n = sc[i].fit_n; c.symbolEnergySize = (size_t)sc[i].symbolEnergySize; c.sri = sc[i].sri;
+        c.tail_len = 0;          // set below once the regions are large enough
+    }
+    int rc = ensure_tails(b);
+    if (rc == PSKD_OK) rc = ensure_rings(b);
+    if (rc != PSKD_OK) return rc;
+    if (h.ring_cap > b->ring_cap) return fail(PSKD_ERR_ARG, "pskd_state_import: history ring of the blob does not fit the bank");
+    std::vector<ChanState> dev(nch);
+    for (int i = 0; i < nch; i++) dev[i] = sc[i].dev;
+    CUDA_TRY(cudaMemcpy(b->d_state, dev.data(), sizeof(ChanState) * nch, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy2D(b->d_ring, (size_t)b->ring_cap * sizeof(float), p, (size_t)h.ring_cap * sizeof(float),
+                          (size_t)h.ring_cap * sizeof(float), nch, cudaMemcpyHostToDevice));
+    p += (size_t)nch * h.ring_cap * sizeof(float);
+    for (int i = 0; i < nch; i++) {
+        ChanHost& c = b->ch[i];
+        const long long tl = sc[i].tail_len;
+        if (tl > c.tail_cap) return fail(PSKD_ERR_ARG, "pskd_state_import: carried window of channel %d does not fit", i);
+        if (tl > 0) {
+            CUDA_TRY(cudaMemcpy(b->d_tail[b->tail_cur] + c.tail_off, p, (size_t)tl * sizeof(float2), cudaMemcpyHostToDevice));
+            p += (size_t)tl * sizeof(float2);
+        }
+        c.tail_len = tl;
+    }
+    return PSKD_OK;
+}
+
 int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     if (!b || !in || !out) return fail(PSKD_ERR_ARG, "pskd_process: null argument");
     if (!in->iq && (in->n_complex || in->n_complex_all)) return fail(PSKD_ERR_ARG, "pskd_process: iq is NULL");

@@ -94,3 +94,58 @@ def test_cpp_host_mirror_demo_runs():
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "total symbols 7901" in res.stdout
+
+
+def test_checkpoint_resume_matches_uninterrupted(oracle_built):
+    """pskd_state_export -> new bank -> pskd_state_import continues the streams exactly where the
+    first bank stopped (carried state = the members at cpp/psk_soft.h:66-86 of every channel)."""
+    import psk_soft_b200 as pk
+    props = [dict(samplesPerBaud=8, constelationSize=8, numAvg=100, phaseAvg=50),
+             dict(samplesPerBaud=10, constelationSize=4, numAvg=50, phaseAvg=25, differentialDecoding=1),
+             dict(samplesPerBaud=9, constelationSize=2, numAvg=64, phaseAvg=100)]
+    n, cut = 90000, 41234
+    iq = np.zeros((3, n), np.complex64)
+    for c, p in enumerate(props):
+        iq[c] = siggen.gen_shaped(n, p["samplesPerBaud"], p["constelationSize"], seed=40 + c, sigma=0.03, freq=2e-5, timing_shift=c)
+    whole = pk.Bank(3, props)
+    w1 = whole.process_host(iq[:, :cut].copy(), xdelta=0.01, packet_len=8000)
+    w2 = whole.process_host(iq[:, cut:].copy(), xdelta=0.01, packet_len=8000)
+    first = pk.Bank(3, props)
+    f1 = first.process_host(iq[:, :cut].copy(), xdelta=0.01, packet_len=8000)
+    blob = first.export_state()
+    first.close()
+    second = pk.Bank(3)                       # default properties: everything comes from the blob
+    second.import_state(blob)
+    assert second.get_props(1)["differentialDecoding"] == 1
+    f2 = second.process_host(iq[:, cut:].copy(), xdelta=0.01, packet_len=8000)
+    for c in range(3):
+        for k in ("sidx", "bits", "phase", "soft"):
+            assert np.array_equal(w1[c][k], f1[c][k], equal_nan=(k in ("phase", "soft"))), (c, k)
+            assert np.array_equal(w2[c][k], f2[c][k], equal_nan=(k in ("phase", "soft"))), (c, k)
+        ref = oracle_built.OracleComponent(**props[c])
+        r1 = ref.demod(iq[c, :cut], packet_len=8000, xdelta=0.01)
+        r2 = ref.demod(iq[c, cut:], packet_len=8000, xdelta=0.01)
+        d = bool(props[c].get("differentialDecoding", 0))
+        assert_parity(f1[c], r1, differential=d, tag=f"ch{c} before the checkpoint")
+        assert_parity(f2[c], r2, differential=False if np.isfinite(r2["soft"]).all() else d, tag=f"ch{c} after the restore")
+    with pytest.raises(pk.binding.PskdError):
+        pk.Bank(2).import_state(blob)         # channel count mismatch is an argument error
+
+
+def test_tiny_and_ragged_calls(oracle_built):
+    """calls that emit 0, 1, 31, 32, 33 ... symbols and packets shorter than one symbol: the fused
+    kernel's partial chunks / partial chain blocks / empty packets against the oracle"""
+    import psk_soft_b200 as pk
+    props = dict(samplesPerBaud=8, constelationSize=8, numAvg=20, phaseAvg=10)
+    iq = siggen.gen_shaped(40000, 8, 8, seed=77, sigma=0.03, freq=3e-5, timing_shift=4)
+    orc = oracle_built.OracleComponent(**props)
+    dev = pk.PskSoft(**props)
+    cuts = [0, 5, 150, 159, 160, 168, 168 + 8 * 31, 168 + 8 * 63, 168 + 8 * 96, 2000, 2001, 2003, 9000, 9007, 30000, 40000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ref = orc.push(iq[a:b], xdelta=0.01)
+        got = dev.push(iq[a:b], xdelta=0.01)
+        assert_parity(got, ref, tag=f"call {a}:{b}")
+    # the same stream in one call, cut into 3-sample packets (most packets emit nothing)
+    ref = oracle_built.OracleComponent(**props).demod(iq[:6000], packet_len=3, xdelta=0.01)
+    got = pk.PskSoft(**props).demod(iq[:6000], packet_len=3, xdelta=0.01)
+    assert_parity(got, ref, tag="3-sample packets")
