@@ -303,8 +303,15 @@ def main():
         abytes_step = algorithmic_bytes(w, nch, n)
         abytes_dom = own.get(dom, nch * K * 4)               # chain kernels: the 4-byte phase output
         achieved = abytes_dom / launches_per_step / (ms_launch * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes of the same kernel from the committed ncu --set full capture, scaled per launch
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if dom == "k_fused" and tr.get("workload") == args.workload:
+                traffic = tr["dram_bytes_per_sample"] * nch * n / launches_per_step
+        except (OSError, KeyError, ValueError):
+            traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes_dom / launches_per_step,
                 "note": "achieved = this kernel's own algorithmic bytes (SURVEY 8d split per kernel) / its CUDA-event time per launch",
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
