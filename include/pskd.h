@@ -108,6 +108,7 @@ typedef struct pskd_stats {
     uint64_t spec_chunks;        /* phase-chain chunks run speculatively */
     uint64_t spec_misses;        /* chunks whose speculation failed verification and were re-run exactly */
     uint64_t seq_channels;       /* channel-calls that took the sequential (non-speculative) chain */
+    uint64_t tp_packets;         /* emulated packets whose phase chain ran time-parallel and whose hand-over was proven */
 } pskd_stats;
 
 typedef struct pskd_bank* pskd_handle;

@@ -96,6 +96,9 @@ struct pskd_bank {
     int* h_list_slot[2] = {nullptr, nullptr};
     int* d_done = nullptr;     // [n_channels] units completed per channel in the current call
     int* d_ticket = nullptr;   // [16 slabs x 4 samplesPerBaud values] unit ticket counters
+    int tp_mode = -1;          // time-parallel chain of the staged path: -1 auto (few channels, many packets), 0 never, 1 whenever possible (PSKD_TP)
+    DevBuf<TpItem> tp_items; DevBuf<TpChan> tp_chans; DevBuf<TpPacket> tp_pkts; DevBuf<TpEnd> tp_ends;
+    DevBuf<float> tp_end_ring, tp_start_ring; DevBuf<int> tp_fail;
     Profiler prof;
 };
 
@@ -198,6 +201,7 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     if (const char* e = getenv("PSKD_CHAIN")) b->chain_mode = (strcmp(e, "seq") == 0) ? 1 : 0;
     if (const char* e = getenv("PSKD_FUSED")) b->fused_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
     if (const char* e = getenv("PSKD_FUSED_MIN")) b->fused_min_channels = std::max(1, atoi(e));
+    if (const char* e = getenv("PSKD_TP")) b->tp_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
     cudaError_t e;
 #define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
     CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
@@ -251,6 +255,8 @@ int pskd_destroy(pskd_handle b) {
     cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]);
     b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
     b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release();
+    b->tp_items.release(); b->tp_chans.release(); b->tp_pkts.release(); b->tp_ends.release();
+    b->tp_end_ring.release(); b->tp_start_ring.release(); b->tp_fail.release();
     b->prof.destroy();
     for (int i = 0; i < 16; i++) { if (b->slab_in[i]) cudaEventDestroy(b->slab_in[i]); if (b->slab_done[i]) cudaEventDestroy(b->slab_done[i]); }
     if (b->copy_in) cudaStreamDestroy(b->copy_in);
@@ -339,6 +345,7 @@ int pskd_get_stats(pskd_handle b, pskd_stats* st) {
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     *st = b->stats;
     st->wraps = c.wraps; st->spec_chunks = c.spec_chunks; st->spec_misses = c.spec_misses; st->seq_channels = c.seq_channels;
+    st->tp_packets = c.tp_packets;
     return PSKD_OK;
 }
 
@@ -582,6 +589,35 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     }
     const bool any_staged = (n_fast + n_seq) > 0;
 
+    // ---- time-parallel chain plan (staged path): channels with many packets whose chain would otherwise
+    // run packet after packet on one warp.  Heads = packets before the first packet that is certain to start
+    // with a full history; one item per later packet.
+    std::vector<TpItem> tp_heads, tp_items;
+    std::vector<TpChan> tp_chans;
+    int tp_slots = 0, tp_records = 0, tp_Pmax = 1;
+    if (b->tp_mode != 0 && (!host_bufs || n_slabs == 1) && n_fast > 0 && (b->tp_mode == 1 || n_fast <= 2048) && in->sri_xdelta != 1.0) {
+        for (int i = 0; i < nch; i++) {
+            ChanDesc& d = b->h_desc[i];
+            if (!(d.flags & CH_FAST) || (d.flags & CH_FUSED) || d.P < 2 || d.K <= 0) continue;
+            if (d.pkt_len / d.S - 1 < d.P + 2) continue;                   // every full packet must hold the whole history
+            int j0 = -1;
+            for (int j = 1; j < d.n_pkts; j++)
+                if (first_symbol_at((long long)j * d.pkt_len, d.tail_len, d.S, d.A, d.K) >= d.P) { j0 = j; break; }
+            if (j0 < 0 || d.n_pkts - j0 < (b->tp_mode == 1 ? 2 : 4)) continue;
+            d.flags |= CH_TP;
+            TpChan tc{i, j0, d.n_pkts, tp_records, tp_slots, 0};
+            tp_chans.push_back(tc);
+            tp_heads.push_back(TpItem{i, 0, j0, 0, -1, tp_records, -1, 0});
+            for (int j = j0; j < d.n_pkts; j++) {
+                const int rec = tp_records + 1 + (j - j0);
+                tp_items.push_back(TpItem{i, j, j + 1, j == j0 ? 2 : 1, tp_records, rec, tp_slots + (j - j0), 0});
+            }
+            tp_records += 1 + (d.n_pkts - j0);
+            tp_slots += d.n_pkts - j0;
+            tp_Pmax = std::max(tp_Pmax, d.P);
+        }
+    }
+
     // ---- buffers ------------------------------------------------------------------------------
     CUDA_TRY(b->sel.reserve((size_t)scr_total + 4));
     CUDA_TRY(b->theta.reserve((size_t)scr_total + 4));
@@ -613,6 +649,21 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         CUDA_TRY(cudaMemsetAsync(b->d_ticket, 0, sizeof(int) * 64, b->stream));
     }
     CUDA_TRY(cudaEventRecord(b->desc_ev[b->desc_slot], b->stream));
+    const int tp_stride = (tp_Pmax + 3) & ~3;
+    if (!tp_chans.empty()) {
+        CUDA_TRY(b->tp_items.reserve(tp_heads.size() + tp_items.size()));
+        CUDA_TRY(b->tp_chans.reserve(tp_chans.size()));
+        CUDA_TRY(b->tp_pkts.reserve((size_t)tp_slots));
+        CUDA_TRY(b->tp_ends.reserve((size_t)tp_records));
+        CUDA_TRY(b->tp_end_ring.reserve((size_t)tp_records * tp_stride));
+        CUDA_TRY(b->tp_start_ring.reserve((size_t)tp_records * tp_stride));
+        CUDA_TRY(b->tp_fail.reserve((size_t)nch));
+        // pageable sources: the copies are staged before the calls return
+        CUDA_TRY(cudaMemcpyAsync(b->tp_items.p, tp_heads.data(), sizeof(TpItem) * tp_heads.size(), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->tp_items.p + tp_heads.size(), tp_items.data(), sizeof(TpItem) * tp_items.size(), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->tp_chans.p, tp_chans.data(), sizeof(TpChan) * tp_chans.size(), cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaMemsetAsync(b->tp_fail.p, 0, sizeof(int) * nch, b->stream));
+    }
 
     LaunchCtx L{};
     L.stream = b->stream; L.n_channels = nch; L.Kmax = Kmax; L.Smax = Smax; L.Amax = Amax;
@@ -621,6 +672,13 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     L.d_sel = b->sel.p; L.d_theta = b->theta.p; L.d_phase_tmp = b->phase_tmp.p;
     L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;
     L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches; L.prof = &b->prof;
+    if (!tp_chans.empty()) {
+        L.tp_head_items = b->tp_items.p; L.tp_n_head = (int)tp_heads.size();
+        L.tp_items = b->tp_items.p + tp_heads.size(); L.tp_n_items = (int)tp_items.size();
+        L.tp_chans = b->tp_chans.p; L.tp_n_chans = (int)tp_chans.size(); L.tp_n_slots = tp_slots;
+        L.tp_pkts = b->tp_pkts.p; L.tp_ends = b->tp_ends.p; L.tp_end_ring = b->tp_end_ring.p; L.tp_start_ring = b->tp_start_ring.p;
+        L.tp_ring_stride = tp_stride; L.tp_fail = b->tp_fail.p;
+    }
 
     // the kernels of one slab of channels [lo, hi)
     auto run_slab = [&](const LaunchCtx& Ls, int slab, int lo) -> int {

@@ -29,7 +29,8 @@ struct ChanDesc {
 enum { CH_RESET_NUMSYMS = 1, CH_RESET_PHASEAVG = 2, CH_SRI_CHANGED = 4,
        CH_FAST = 8 /* phase chain + back run in k_chain_par (scan-based), else k_chain_seq + k_back */,
        CH_FRONT_FAST = 16 /* timing runs in k_front_t<S>, else in the generic k_front */,
-       CH_FUSED = 32 /* the whole path of this channel runs in k_fused<S> (pskd_fused.cu); the staged kernels skip it */ };
+       CH_FUSED = 32 /* the whole path of this channel runs in k_fused<S> (pskd_fused.cu); the staged kernels skip it */,
+       CH_TP = 64 /* staged path: the phase chain of this channel runs time-parallel over its packets (TpCtl) */ };
 constexpr int FRONT_FAST_AMAX = 768;   // largest numAvg the specialised front tile (1024 symbols) still uses efficiently
 constexpr int CHAIN_PAR_PMAX = 1024;
 constexpr int FUSED_AMAX = 256;        // largest numAvg whose energy ring the fused kernel keeps in shared memory
@@ -45,7 +46,7 @@ struct ChanState {
 };
 
 struct DevCounters {
-    unsigned long long wraps, spec_chunks, spec_misses, seq_channels;
+    unsigned long long wraps, spec_chunks, spec_misses, seq_channels, tp_packets;
 };
 
 // first call-local output symbol whose emission sample lies at or after input position x
@@ -58,8 +59,57 @@ __host__ __device__ inline long long first_symbol_at(long long x, long long tail
     return k;
 }
 
+// ---- time-parallel phase chain (staged path, few channels with many packets) -------------------
+// The chain of a channel is sequential only through (a) the history ring handed from packet to
+// packet and (b) the integer level of the unwrapped phase, which the packet-end wrap
+// (cpp/psk_soft.cpp:592-603) turns into a scalar recurrence over packets.  So: every packet's classic
+// (sample-to-sample) unwrap and an estimate of its end phase are formed in parallel (k_tp_scan), a
+// scan over the packets of a channel resolves the integer levels and the wrap counts (k_tp_resolve),
+// every packet then runs the exact chain from a history ring SYNTHESISED from those integers
+// (k_chain_par over TpItems), and k_tp_check proves the hand-overs: the ring a packet started from
+// must equal, bit for bit, the ring its predecessor ended with, and its first unwrap count must be
+// the one the predecessor's exact end estimate gives.  Channels that fail the proof are re-run by
+// the sequential chain from their untouched carried state.
+struct TpItem {            // one warp of work for k_chain_par
+    int ch;                // channel (index into d_desc)
+    int pk_a, pk_b;        // emulated packets [pk_a, pk_b)
+    int kind;              // 0: start from state[ch]; 1: synthesised start of packet pk_a; 2: start from end record `src`
+    int src;               // kind 2: end record to start from; kind 1: end record holding the channel's fit constants
+    int dst;               // end record this item writes
+    int pkt_slot;          // index of packet pk_a in the TpPacket array
+    int pad;
+};
+struct TpPacket {          // per (channel, packet) of the time-parallel range
+    int cEnd;              // classic unwrap count at the packet's last symbol, relative to its first symbol
+    int dLink;             // classic increment from the previous packet's last symbol to this packet's first
+    int A;                 // resolved: unwrap count of the packet's first symbol
+    int w;                 // resolved: numWraps the packet-end wrap applies (0: none)
+    double estRelEnd;      // estimate at the packet end for the relative phases (A = 0)
+    long long klo, khi;    // symbols of the packet
+};
+struct TpEnd {             // what a chain item leaves behind
+    ChanState st;          // state after the item's last packet epilogue
+    float est_start_used;  // the estimate the item's first symbol was unwrapped against
+    int   has_symbols;
+    unsigned long long wraps_delta;
+};
+struct TpChan {            // per time-parallel channel
+    int ch, pkt0, n_pkts;  // first time-parallel packet, packets in the call
+    int first_item;        // index of the channel's first TpItem (the sequential head); items follow in packet order
+    int first_slot;        // index of packet pkt0 in the TpPacket array
+    int pad;
+};
+struct TpCtl {
+    const TpItem* items; int n_items;
+    const TpChan* chans; int n_chans;
+    TpPacket* pkts;
+    TpEnd* ends; float* end_ring; float* start_ring; int ring_stride;   // per item: ring after the last epilogue / ring the item started from
+    int* fail;             // [n_channels] set by k_tp_check when a hand-over could not be proven
+    int fallback;          // launch flag: process only channels with fail[ch] != 0, from state[ch]
+};
+
 // ---- optional per-kernel event timing --------------------------------------------------------
-enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_FUSED, KID_COUNT };
+enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_FUSED, KID_TP, KID_COUNT };
 struct Profiler {
     bool enabled = false;
     struct Pair { cudaEvent_t a, b; int kid; };
@@ -95,6 +145,12 @@ struct LaunchCtx {
     DevCounters* d_counters;
     unsigned long long* launches;   // host counter
     Profiler* prof;
+    // time-parallel chain (all null / 0 when unused)
+    const TpItem* tp_head_items; int tp_n_head;      // sequential heads: packets [0, pkt0) of every TP channel
+    const TpItem* tp_items; int tp_n_items;          // one item per time-parallel packet
+    const TpChan* tp_chans; int tp_n_chans; int tp_n_slots;
+    TpPacket* tp_pkts; TpEnd* tp_ends; float* tp_end_ring; float* tp_start_ring; int tp_ring_stride;
+    int* tp_fail;
 };
 
 // one launch of the fused kernel: the CH_FUSED channels of one samplesPerBaud value

@@ -14,7 +14,7 @@
 namespace pskd {
 
 const char* kernel_name(int kid) {
-    static const char* names[KID_COUNT] = {"k_front", "k_chain_seq", "k_chain_par", "k_back_par", "k_chain_exact", "k_back", "k_finish", "k_fused"};
+    static const char* names[KID_COUNT] = {"k_front", "k_chain_seq", "k_chain_par", "k_back_par", "k_chain_exact", "k_back", "k_finish", "k_fused", "k_tp_aux"};
     return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "?";
 }
 cudaEvent_t Profiler::get() {
@@ -634,15 +634,31 @@ static __device__ __noinline__ void chain_normalize_ring(float* yb, float* tmp, 
     __syncwarp();
 }
 
+// classic sample-to-sample unwrap increment (the chain's prediction rule; also the time-parallel
+// chain's integer bookkeeping -- both must use the same arithmetic)
+__device__ __forceinline__ int classic_dn(float th, float th_prev) {
+    return -__float2int_rn((th - th_prev) * 0.15915494309189535f);
+}
+
 __global__ void __launch_bounds__(CW_WARPS * 32, CW_MIN_CTAS)
 k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, float* __restrict__ ring_base,
             const float* __restrict__ theta, float* __restrict__ out_phase,
-            double sri_xdelta, int Pcap, int n_channels, DevCounters* counters)
+            double sri_xdelta, int Pcap, int n_channels, DevCounters* counters, const TpCtl tp)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int ch = blockIdx.x * CW_WARPS + wid;
-    if (ch >= n_channels) return;
-    if (!(desc[ch].flags & CH_FAST) || (desc[ch].flags & CH_FUSED)) return;
+    const int widx = blockIdx.x * CW_WARPS + wid;
+    int ch, pk_a = 0, pk_b = -1, kind = 0, src = -1, dst = -1, pkt_slot = -1;
+    if (tp.items) {
+        if (widx >= tp.n_items) return;
+        const TpItem it = tp.items[widx];
+        ch = it.ch; pk_a = it.pk_a; pk_b = it.pk_b; kind = it.kind; src = it.src; dst = it.dst; pkt_slot = it.pkt_slot;
+    } else {
+        ch = widx;
+        if (ch >= n_channels) return;
+        if (!(desc[ch].flags & CH_FAST) || (desc[ch].flags & CH_FUSED)) return;
+        if (tp.fallback) { if (!(desc[ch].flags & CH_TP) || !tp.fail[ch]) return; }   // re-run of a channel whose hand-overs were not proven
+        else if (desc[ch].flags & CH_TP) return;                                        // handled through TpItems
+    }
 
     extern __shared__ double smem_d[];
     const size_t per_warp_d = (size_t)CW_B + Pcap + 2;                       // ps[CW_B], hs[Pcap+1] (+1 pad)
@@ -663,22 +679,63 @@ k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, fl
     const float* thg = theta + desc[ch].scr_off;
     float* phg = out_phase + desc[ch].sym_off;
     float* gring = ring_base + desc[ch].ring_off;
+    if (pk_b < 0) pk_b = n_pkts;
+    const int k_begin = (pk_a == 0) ? 0 : (int)first_symbol_at((long long)pk_a * pkt_len, tail_len, S, A, K);
 
-    if (lane == 0) { sh.st = state[ch]; sh.flags = desc[ch].flags; sh.passes = 0; sh.seq_blocks = 0; }
-    for (int j = lane; j < P; j += 32) yb[j] = gring[j];
+    if (kind == 0) {
+        if (lane == 0) { sh.st = state[ch]; sh.flags = desc[ch].flags; sh.passes = 0; sh.seq_blocks = 0; }
+        for (int j = lane; j < P; j += 32) yb[j] = gring[j];
+    } else if (kind == 2) {
+        if (lane == 0) { sh.st = tp.ends[src].st; sh.flags = desc[ch].flags & ~(CH_RESET_NUMSYMS | CH_RESET_PHASEAVG); sh.passes = 0; sh.seq_blocks = 0; }
+        for (int j = lane; j < P; j += 32) yb[j] = tp.end_ring[(size_t)src * tp.ring_stride + j];
+    } else {
+        // synthesised start of packet pk_a: the history ring the previous packet leaves behind, from the
+        // resolved integers: y = f32(theta + 2pi(c + A)), then the packet-end shift f32(y - w*wrapValue)
+        const TpPacket pp = tp.pkts[pkt_slot - 1];
+        const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)M));
+        const float shift = fmulr((float)pp.w, wrapValue);
+        int carry = 0;                                      // sum of the increments of the symbols after the current chunk
+        for (int e = k_begin; e > k_begin - P; e -= 32) {
+            const int m = e - 1 - lane;                     // lanes run backwards from the packet's last symbol
+            int dn = 0;
+            float t = 0.0f;
+            const bool in = m >= k_begin - P;
+            if (in) { t = __ldg(thg + m); dn = classic_dn(t, __ldg(thg + m - 1)); }
+            const int incl = warp_scan_int(dn, lane);       // increments of symbols m .. e-1
+            if (in) {
+                const int c = pp.cEnd - (carry + incl - dn);
+                float y = __double2float_rn(daddr((double)t, dmulr((double)(c + pp.A), PSKD_M_2PI)));
+                if (pp.w != 0) y = fsubr(y, shift);                                      // :131 (subtractConst)
+                yb[m - (k_begin - P)] = y;
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            sh.st = tp.ends[src].st;                        // fit constants (xdelta, denominator, n) of the channel
+            sh.st.fit.head = 0; sh.st.fit.pts = P; sh.st.wraps = 0;
+            SmemRing ring{yb};
+            sh.st.est = fit_resum(sh.st.fit, ring);         // exact after a wrap (:601-602); else within rounding of the
+                                                            // carried estimate, which only feeds the first unwrap count
+            sh.flags = desc[ch].flags & ~(CH_RESET_NUMSYMS | CH_RESET_PHASEAVG); sh.passes = 0; sh.seq_blocks = 0;
+        }
+        __syncwarp();
+        if (dst >= 0) for (int j = lane; j < P; j += 32) tp.start_ring[(size_t)dst * tp.ring_stride + j] = yb[j];
+    }
     __syncwarp();
+    const float est_start_used = sh.st.est;
     const unsigned long long wraps0 = sh.st.wraps;
     const float fP1 = (float)(P - 1);
 
     // software prefetch of the next sub-block's theta: strided layout, element i = lane + 32*q
-    int pf_k = 0;
+    int pf_k = k_begin;
     float pf_th[CW_V];
 #pragma unroll
-    for (int q = 0; q < CW_V; q++) { const int kk = lane + 32 * q; pf_th[q] = (kk < K) ? __ldg(thg + kk) : 0.0f; }
+    for (int q = 0; q < CW_V; q++) { const int kk = k_begin + lane + 32 * q; pf_th[q] = (kk < K) ? __ldg(thg + kk) : 0.0f; }
 
     bool hs_valid = false;
-    int k = 0;
-    for (int pkt = 0; pkt < n_pkts; pkt++) {
+    int k = k_begin;
+    for (int pkt = pk_a; pkt < pk_b; pkt++) {
         if (lane == 0) {
             SmemRing ring{yb};
             chain_packet_prologue(sh.st, ring, desc[ch], sri_xdelta, sh.flags);
@@ -736,7 +793,7 @@ k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, fl
                         int dn = 0;
                         if (i0 + v < nb) {
                             const float pv = (v == 0) ? tprev : tl[v - 1];
-                            dn = (i0 + v == 0) ? unwrap_count(est0, tl[0]) : -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
+                            dn = (i0 + v == 0) ? unwrap_count(est0, tl[0]) : classic_dn(tl[v], pv);
                         }
                         run += dn; nloc[v] = run;
                     }
@@ -867,11 +924,23 @@ k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, fl
         __syncwarp();
         if (sh.flags & (1 << 30)) { hs_valid = false; if (lane == 0) sh.flags &= ~(1 << 30); __syncwarp(); }
     }
-    for (int j = lane; j < P; j += 32) gring[j] = yb[j];
+    if (dst >= 0) {
+        // time-parallel item: leave the end state in its record (k_tp_check installs the last one)
+        if (sh.st.fit.head != 0 && sh.st.fit.pts == P) chain_normalize_ring(yb, reinterpret_cast<float*>(hs), sh.st.fit, P, lane);
+        __syncwarp();
+        for (int j = lane; j < P; j += 32) tp.end_ring[(size_t)dst * tp.ring_stride + j] = yb[j];
+        if (lane == 0) {
+            TpEnd& e = tp.ends[dst];
+            e.st = sh.st; e.est_start_used = est_start_used; e.has_symbols = (k > k_begin) ? 1 : 0;
+            e.wraps_delta = sh.st.wraps - wraps0;
+        }
+    } else {
+        for (int j = lane; j < P; j += 32) gring[j] = yb[j];
+        if (lane == 0) state[ch] = sh.st;              // `last` is carried by k_finish
+    }
     if (lane == 0) {
-        state[ch] = sh.st;              // `last` is carried by k_finish
         if (sh.st.wraps != wraps0) atomicAdd(&counters->wraps, sh.st.wraps - wraps0);
-        atomicAdd(&counters->spec_chunks, (unsigned long long)((K + CW_B - 1) / CW_B));
+        atomicAdd(&counters->spec_chunks, (unsigned long long)((k - k_begin + CW_B - 1) / CW_B));
         if (sh.passes) atomicAdd(&counters->spec_misses, (unsigned long long)sh.passes);
         if (sh.seq_blocks) atomicAdd(&counters->seq_channels, (unsigned long long)sh.seq_blocks);
     }
@@ -953,6 +1022,164 @@ k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ stat
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// time-parallel chain, auxiliary kernels (see TpCtl in pskd_internal.h)
+// ---------------------------------------------------------------------------------------------
+// k_tp_scan: one warp per (channel, packet): classic unwrap over the packet (integer scan) and the
+// linear-fit estimate of the relative phases at the packet end (double, regression over the last P)
+__global__ void __launch_bounds__(128)
+k_tp_scan(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, const TpChan* __restrict__ chans,
+          int n_chans, TpPacket* __restrict__ pkts, int n_slots)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= n_slots) return;
+    // which channel owns this slot (few channels: linear search)
+    int ci = 0;
+    while (ci + 1 < n_chans && chans[ci + 1].first_slot <= slot) ci++;
+    const TpChan tc = chans[ci];
+    const ChanDesc& d = desc[tc.ch];
+    const int pkt = tc.pkt0 + (slot - tc.first_slot);
+    const int K = (int)d.K, P = d.P;
+    const int klo = (int)first_symbol_at((long long)pkt * d.pkt_len, d.tail_len, d.S, d.A, K);
+    const int khi = (pkt + 1 == d.n_pkts) ? K : (int)first_symbol_at((long long)(pkt + 1) * d.pkt_len, d.tail_len, d.S, d.A, K);
+    const float* thg = theta + d.scr_off;
+    int c = 0;                                             // count at the last symbol processed so far
+    for (int base = klo + 1; base < khi; base += 32) {
+        const int m = base + lane;
+        int dn = 0;
+        if (m < khi) dn = classic_dn(__ldg(thg + m), __ldg(thg + m - 1));
+        c += __shfl_sync(0xffffffffu, warp_scan_int(dn, lane), 31);
+    }
+    // regression of phi = theta + 2pi*c over the last min(P, n) symbols, evaluated at the newest one
+    const int n = khi - klo, np = min(P, n);
+    double s0 = 0.0, s1 = 0.0, q2 = 0.0;
+    {
+        int carry = 0;
+        const double mid = 0.5 * (double)(np - 1);
+        for (int e = khi; e > khi - np; e -= 32) {
+            const int m = e - 1 - lane;
+            const bool in = m >= khi - np;
+            int dn = 0; float t = 0.0f;
+            if (in) { t = __ldg(thg + m); if (m > klo) dn = classic_dn(t, __ldg(thg + m - 1)); }
+            const int incl = warp_scan_int(dn, lane);
+            if (in) {
+                const int cm = c - (carry + incl - dn);
+                const double phi = (double)t + PSKD_M_2PI * (double)cm;
+                const double x = (double)(m - (khi - np)) - mid;
+                s0 += phi; s1 += x * phi; q2 += x * x;
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+        }
+    }
+    if (lane == 0) {
+        TpPacket p;
+        p.cEnd = c;
+        p.dLink = (klo > 0 && n > 0) ? classic_dn(thg[klo], thg[klo - 1]) : 0;
+        p.A = 0; p.w = 0;
+        p.estRelEnd = (np > 0) ? s0 / (double)np + ((q2 > 0.0) ? (s1 / q2) * 0.5 * (double)(np - 1) : 0.0) : 0.0;
+        p.klo = klo; p.khi = khi;
+        pkts[slot] = p;
+    }
+}
+
+// k_tp_resolve: one thread per channel: the scalar recurrence over its packets: unwrap level of every
+// packet's first symbol and the wrap count of every packet end (cpp/psk_soft.cpp:592-603)
+__global__ void k_tp_resolve(const ChanDesc* __restrict__ desc, const float* __restrict__ theta,
+                             const TpChan* __restrict__ chans, int n_chans, TpPacket* __restrict__ pkts,
+                             const TpEnd* __restrict__ ends)
+{
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= n_chans) return;
+    const TpChan tc = chans[ci];
+    const ChanDesc& d = desc[tc.ch];
+    const float* thg = theta + d.scr_off;
+    const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)d.M));
+    const int np = tc.n_pkts - tc.pkt0;
+    // level of the first time-parallel packet: the reference's rule with the exact estimate the head left
+    long long A = 0;
+    {
+        const TpPacket p0 = pkts[tc.first_slot];
+        if (p0.khi > p0.klo) { long long n = 0; (void)unwrap_against(ends[tc.first_item].st.est, thg[p0.klo], &n); A = n; }
+    }
+    for (int j = 0; j < np; j++) {
+        TpPacket& p = pkts[tc.first_slot + j];
+        p.A = (int)A;
+        const float est_end = (float)(p.estRelEnd + PSKD_M_2PI * (double)A);
+        int w = 0;
+        if (p.khi > p.klo && wrap_needed(est_end, wrapValue)) w = (int)roundf(__fdiv_rn(est_end, wrapValue));
+        p.w = w;
+        if (j + 1 < np) {
+            const TpPacket& q = pkts[tc.first_slot + j + 1];
+            A = A + p.cEnd + q.dLink - (long long)d.M * w;
+        }
+    }
+}
+
+// k_tp_check: one warp per channel: prove every hand-over, then install the last packet's end state
+__global__ void __launch_bounds__(128)
+k_tp_check(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, float* __restrict__ ring_base,
+           const float* __restrict__ theta, const TpCtl tp, DevCounters* counters)
+{
+    const int lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ci >= tp.n_chans) return;
+    const TpChan tc = tp.chans[ci];
+    const ChanDesc& d = desc[tc.ch];
+    const float* thg = theta + d.scr_off;
+    const int P = d.P, np = tc.n_pkts - tc.pkt0;
+    bool ok = true;
+    unsigned long long wraps = tp.ends[tc.first_item].wraps_delta;
+    for (int j = 1; j < np && ok; j++) {
+        const int it = tc.first_item + 1 + j, prev = it - 1;           // items: head, pkt0, pkt0+1, ...
+        bool same = true;
+        for (int i = lane; i < P; i += 32)
+            same = same && (__float_as_uint(tp.start_ring[(size_t)it * tp.ring_stride + i]) ==
+                            __float_as_uint(tp.end_ring[(size_t)prev * tp.ring_stride + i]));
+        same = __all_sync(0xffffffffu, same);
+        if (same && tp.ends[it].has_symbols) {
+            long long n_used = 0, n_true = 0;
+            const float t0 = thg[tp.pkts[tc.first_slot + j].klo];
+            (void)unwrap_against(tp.ends[it].est_start_used, t0, &n_used);
+            (void)unwrap_against(tp.ends[prev].st.est, t0, &n_true);
+            same = n_used == n_true;
+        }
+        ok = same;
+        wraps += tp.ends[it].wraps_delta;
+    }
+    if (np >= 1) wraps += tp.ends[tc.first_item + 1].wraps_delta;
+    if (ok) {
+        const int last = tc.first_item + np;                          // item of the last packet
+        for (int i = lane; i < P; i += 32) ring_base[d.ring_off + i] = tp.end_ring[(size_t)last * tp.ring_stride + i];
+        if (lane == 0) {
+            ChanState st = tp.ends[last].st;
+            st.wraps = state[tc.ch].wraps + wraps;
+            state[tc.ch] = st;
+            tp.fail[tc.ch] = 0;
+            atomicAdd(&counters->tp_packets, (unsigned long long)np);
+        }
+    } else if (lane == 0) {
+        tp.fail[tc.ch] = 1;
+        atomicAdd(&counters->seq_channels, 1ULL);
+    }
+}
+
+static cudaError_t launch_chain_kernel(const LaunchCtx& c, int Pcap, size_t smem, int n_warps, const TpCtl& tp) {
+    float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
+    int blocks = (n_warps + CW_WARPS - 1) / CW_WARPS;
+    if (blocks < 1) return cudaSuccess;
+    c.prof->begin(KID_CHAIN_PAR, c.stream);
+    k_chain_par<<<blocks, CW_WARPS * 32, smem, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, phase,
+                                                          c.sri_xdelta, Pcap, c.n_channels, c.d_counters, tp);
+    c.prof->end(c.stream);
+    (*c.launches)++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_chain_par(const LaunchCtx& c) {
     if (c.n_fast_channels == 0) return cudaSuccess;
     int Pcap = c.Pmax_fast < 1 ? 1 : c.Pmax_fast;
@@ -968,14 +1195,39 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
         configured = smem;
     }
     float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
-    int blocks = (c.n_channels + CW_WARPS - 1) / CW_WARPS;
-    c.prof->begin(KID_CHAIN_PAR, c.stream);
-    k_chain_par<<<blocks, CW_WARPS * 32, smem, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, phase,
-                                                          c.sri_xdelta, Pcap, c.n_channels, c.d_counters);
-    c.prof->end(c.stream);
-    (*c.launches)++;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    TpCtl tp{};
+    tp.chans = c.tp_chans; tp.n_chans = c.tp_n_chans; tp.pkts = c.tp_pkts; tp.ends = c.tp_ends;
+    tp.end_ring = c.tp_end_ring; tp.start_ring = c.tp_start_ring; tp.ring_stride = c.tp_ring_stride; tp.fail = c.tp_fail;
+    if (c.n_fast_channels > c.tp_n_chans) {            // channels whose chain runs packet after packet
+        e = launch_chain_kernel(c, Pcap, smem, c.n_channels, tp);
+        if (e != cudaSuccess) return e;
+    }
+    if (c.tp_n_chans > 0) {
+        // heads (packets before the time-parallel range), scan, resolve, all packets in parallel, proof, re-runs
+        TpCtl t1 = tp; t1.items = c.tp_head_items; t1.n_items = c.tp_n_head;
+        e = launch_chain_kernel(c, Pcap, smem, c.tp_n_head, t1);
+        if (e != cudaSuccess) return e;
+        c.prof->begin(KID_TP, c.stream);
+        k_tp_scan<<<(c.tp_n_slots + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_n_slots);
+        k_tp_resolve<<<(c.tp_n_chans + 63) / 64, 64, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_ends);
+        c.prof->end(c.stream);
+        (*c.launches) += 2;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        TpCtl t2 = tp; t2.items = c.tp_items; t2.n_items = c.tp_n_items;
+        e = launch_chain_kernel(c, Pcap, smem, c.tp_n_items, t2);
+        if (e != cudaSuccess) return e;
+        c.prof->begin(KID_TP, c.stream);
+        k_tp_check<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, tp, c.d_counters);
+        c.prof->end(c.stream);
+        (*c.launches)++;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        TpCtl t3 = tp; t3.fallback = 1;
+        e = launch_chain_kernel(c, Pcap, smem, c.n_channels, t3);
+        if (e != cudaSuccess) return e;
+    }
     if ((c.out_soft || c.out_bits) && c.Kmax > 0) {
         dim3 grid((unsigned)((c.Kmax + BP_TILE - 1) / BP_TILE), (unsigned)c.n_channels);
         c.prof->begin(KID_BACK_PAR, c.stream);
@@ -983,8 +1235,9 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
         c.prof->end(c.stream);
         (*c.launches)++;
         e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
     }
-    return e;
+    return cudaSuccess;
 }
 
 }  // namespace pskd

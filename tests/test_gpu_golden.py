@@ -14,10 +14,12 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.n
 PROP_NAMES = ("samplesPerBaud", "numAvg", "constelationSize", "phaseAvg", "differentialDecoding")
 
 
-@pytest.fixture(params=["1", "0"], ids=["fused", "staged"], autouse=True)
+@pytest.fixture(params=["fused", "staged", "tp"], autouse=True)
 def fused_mode(request, monkeypatch):
-    """every test of this module runs through the fused kernel and through the staged kernels"""
-    monkeypatch.setenv("PSKD_FUSED", request.param)
+    """every test of this module runs through the fused kernel, the staged kernels, and the staged
+    kernels with the time-parallel chain"""
+    monkeypatch.setenv("PSKD_FUSED", "1" if request.param == "fused" else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if request.param == "tp" else "0")
     return request.param
 
 

@@ -23,12 +23,14 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["fused", "par", "seq"])
+@pytest.fixture(params=["fused", "tp", "par", "seq"])
 def chain_mode(request, monkeypatch):
     """run every case through the fused kernel (where the configuration qualifies), the staged
-    kernels with the scan-based chain, and the staged kernels with the literal sequential chain"""
-    monkeypatch.setenv("PSKD_CHAIN", "par" if request.param == "fused" else request.param)
+    kernels with the time-parallel chain (where the packets qualify), the staged kernels with the
+    packet-after-packet scan chain, and the staged kernels with the literal sequential chain"""
+    monkeypatch.setenv("PSKD_CHAIN", "seq" if request.param == "seq" else "par")
     monkeypatch.setenv("PSKD_FUSED", "1" if request.param == "fused" else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if request.param == "tp" else "0")
     return request.param
 
 
@@ -110,12 +112,13 @@ LOW_SNR = [
 ]
 
 
-@pytest.mark.parametrize("fused", ["1", "0"], ids=["fused", "staged"])
+@pytest.mark.parametrize("mode", ["fused", "staged", "tp"])
 @pytest.mark.parametrize("t", LOW_SNR, ids=lambda t: f"M{t['M']}sig{t['sig']}")
-def test_low_snr_unwrap_repairs(t, fused, oracle_built, monkeypatch):
+def test_low_snr_unwrap_repairs(t, mode, oracle_built, monkeypatch):
     import psk_soft_b200 as pk
     monkeypatch.setenv("PSKD_CHAIN", "par")
-    monkeypatch.setenv("PSKD_FUSED", fused)
+    monkeypatch.setenv("PSKD_FUSED", "1" if mode == "fused" else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if mode == "tp" else "0")
     iq = siggen.gen_shaped(t["n"], t["S"], t["M"], seed=21, sigma=t["sig"], freq=t["f"], timing_shift=1)
     ref = oracle_built.OracleComponent(**_props(t)).demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
     dev = pk.PskSoft(**_props(t))
@@ -124,3 +127,31 @@ def test_low_snr_unwrap_repairs(t, fused, oracle_built, monkeypatch):
     print("chain stats", st)
     assert st["spec_chunks"] > 0
     assert_parity(got, ref, tag=str(t))
+
+
+def test_time_parallel_chain_long_single_channel(oracle_built, monkeypatch):
+    """config-2 shape (BPSK, S=10, carrier offset so the packet-end wrap fires every packet, phase
+    noise): the chain of one long channel runs time-parallel over its packets; every hand-over is
+    proven on the device and the result equals the reference's sequential recursion"""
+    import psk_soft_b200 as pk
+    monkeypatch.setenv("PSKD_FUSED", "0")
+    monkeypatch.setenv("PSKD_TP", "auto")
+    props = dict(samplesPerBaud=10, constelationSize=2, numAvg=100, phaseAvg=50)
+    iq = siggen.gen_shaped(1_280_000, 10, 2, seed=2, sigma=0.05, freq=1e-4, pn_sigma=0.002, timing_shift=4)
+    ref = oracle_built.OracleComponent(**props).demod(iq, packet_len=64000, xdelta=0.01)
+    dev = pk.PskSoft(**props)
+    got = dev.demod(iq, packet_len=64000, xdelta=0.01)
+    st = dev.stats()
+    assert st["wraps"] >= 15, st            # the wrap really fires at the packet ends
+    assert st["seq_channels"] == 0, st      # no hand-over failed its proof
+    assert st["tp_packets"] >= 18, st       # ... and the packets really ran time-parallel
+    assert_parity(got, ref, tag="time-parallel chain, 20 packets")
+    # and streamed in two calls (the second call starts from the state the first one installed)
+    dev2 = pk.PskSoft(**props)
+    a = dev2.push(iq[:640000], xdelta=0.01)
+    got2 = dev2._bank.process_host(iq[640000:].reshape(1, -1), xdelta=0.01, packet_len=64000)[0]
+    ref2 = oracle_built.OracleComponent(**props)
+    r1 = ref2.push(iq[:640000], xdelta=0.01)
+    r2 = ref2.demod(iq[640000:], packet_len=64000, xdelta=0.01)
+    assert_parity(a, r1, tag="first call")
+    assert_parity(got2, r2, tag="second call, time-parallel from carried state")
