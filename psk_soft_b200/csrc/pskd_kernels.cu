@@ -1087,84 +1087,104 @@ k_tp_scan(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, co
     }
 }
 
-// k_tp_resolve: one thread per channel: the scalar recurrence over its packets: unwrap level of every
-// packet's first symbol and the wrap count of every packet end (cpp/psk_soft.cpp:592-603)
-__global__ void k_tp_resolve(const ChanDesc* __restrict__ desc, const float* __restrict__ theta,
-                             const TpChan* __restrict__ chans, int n_chans, TpPacket* __restrict__ pkts,
-                             const TpEnd* __restrict__ ends)
+// k_tp_resolve: one warp per channel: the scalar recurrence over its packets: unwrap level of every
+// packet's first symbol and the wrap count of every packet end (cpp/psk_soft.cpp:592-603).  The
+// packet records are read 32 at a time (one per lane); lane 0's recurrence walks them by shuffles.
+__global__ void __launch_bounds__(128)
+k_tp_resolve(const ChanDesc* __restrict__ desc, const float* __restrict__ theta,
+             const TpChan* __restrict__ chans, int n_chans, TpPacket* __restrict__ pkts,
+             const TpEnd* __restrict__ ends)
 {
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ci >= n_chans) return;
     const TpChan tc = chans[ci];
     const ChanDesc& d = desc[tc.ch];
     const float* thg = theta + d.scr_off;
     const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)d.M));
     const int np = tc.n_pkts - tc.pkt0;
+    const int M = d.M;
     // level of the first time-parallel packet: the reference's rule with the exact estimate the head left
     long long A = 0;
     {
         const TpPacket p0 = pkts[tc.first_slot];
         if (p0.khi > p0.klo) { long long n = 0; (void)unwrap_against(ends[tc.first_item].st.est, thg[p0.klo], &n); A = n; }
     }
-    for (int j = 0; j < np; j++) {
-        TpPacket& p = pkts[tc.first_slot + j];
-        p.A = (int)A;
-        const float est_end = (float)(p.estRelEnd + PSKD_M_2PI * (double)A);
-        int w = 0;
-        if (p.khi > p.klo && wrap_needed(est_end, wrapValue)) w = (int)roundf(__fdiv_rn(est_end, wrapValue));
-        p.w = w;
-        if (j + 1 < np) {
-            const TpPacket& q = pkts[tc.first_slot + j + 1];
-            A = A + p.cEnd + q.dLink - (long long)d.M * w;
+    for (int base = 0; base < np; base += 32) {
+        const int j = base + lane;
+        int cEnd = 0, dNext = 0, has = 0; double er = 0.0;
+        if (j < np) {
+            const TpPacket p = pkts[tc.first_slot + j];
+            cEnd = p.cEnd; er = p.estRelEnd; has = p.khi > p.klo;
+            if (j + 1 < np) dNext = pkts[tc.first_slot + j + 1].dLink;
         }
+        int myA = 0, myW = 0;
+        const int cnt = min(32, np - base);
+        for (int l = 0; l < cnt; l++) {                       // uniform loop: every lane follows the same recurrence
+            const int c_l = __shfl_sync(0xffffffffu, cEnd, l), d_l = __shfl_sync(0xffffffffu, dNext, l), h_l = __shfl_sync(0xffffffffu, has, l);
+            const double e_l = __shfl_sync(0xffffffffu, er, l);
+            const float est_end = (float)(e_l + PSKD_M_2PI * (double)A);
+            int w = 0;
+            if (h_l && wrap_needed(est_end, wrapValue)) w = (int)roundf(__fdiv_rn(est_end, wrapValue));
+            if (l == lane) { myA = (int)A; myW = w; }
+            A = A + c_l + d_l - (long long)M * w;
+        }
+        if (j < np) { pkts[tc.first_slot + j].A = myA; pkts[tc.first_slot + j].w = myW; }
     }
 }
 
-// k_tp_check: one warp per channel: prove every hand-over, then install the last packet's end state
+// k_tp_check: one warp per (channel, time-parallel packet): prove the hand-over INTO this packet: the ring it
+// started from equals, bit for bit, the ring its predecessor ended with, and its first unwrap count is the
+// one the predecessor's exact end estimate gives.  A failed proof raises the channel's flag.
 __global__ void __launch_bounds__(128)
-k_tp_check(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, float* __restrict__ ring_base,
-           const float* __restrict__ theta, const TpCtl tp, DevCounters* counters)
+k_tp_check(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, const TpCtl tp)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= tp.n_items) return;
+    const TpItem item = tp.items[slot];
+    if (item.kind != 1) return;                                      // the first packet starts from the head's exact state
+    const ChanDesc& d = desc[item.ch];
+    const int P = d.P, it = item.dst, prev = it - 1;
+    bool same = true;
+    for (int i = lane; i < P; i += 32)
+        same = same && (__float_as_uint(tp.start_ring[(size_t)it * tp.ring_stride + i]) ==
+                        __float_as_uint(tp.end_ring[(size_t)prev * tp.ring_stride + i]));
+    same = __all_sync(0xffffffffu, same);
+    if (same && tp.ends[it].has_symbols) {
+        long long n_used = 0, n_true = 0;
+        const float t0 = theta[d.scr_off + tp.pkts[item.pkt_slot].klo];
+        (void)unwrap_against(tp.ends[it].est_start_used, t0, &n_used);
+        (void)unwrap_against(tp.ends[prev].st.est, t0, &n_true);
+        same = n_used == n_true;
+    }
+    if (!same && lane == 0) tp.fail[item.ch] = 1;
+}
+
+// k_tp_install: one warp per channel: all hand-overs proven -> the last packet's end state becomes the
+// channel's carried state
+__global__ void __launch_bounds__(128)
+k_tp_install(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, float* __restrict__ ring_base,
+             const TpCtl tp, DevCounters* counters)
 {
     const int lane = threadIdx.x & 31;
     const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ci >= tp.n_chans) return;
     const TpChan tc = tp.chans[ci];
     const ChanDesc& d = desc[tc.ch];
-    const float* thg = theta + d.scr_off;
     const int P = d.P, np = tc.n_pkts - tc.pkt0;
-    bool ok = true;
-    unsigned long long wraps = tp.ends[tc.first_item].wraps_delta;
-    for (int j = 1; j < np && ok; j++) {
-        const int it = tc.first_item + 1 + j, prev = it - 1;           // items: head, pkt0, pkt0+1, ...
-        bool same = true;
-        for (int i = lane; i < P; i += 32)
-            same = same && (__float_as_uint(tp.start_ring[(size_t)it * tp.ring_stride + i]) ==
-                            __float_as_uint(tp.end_ring[(size_t)prev * tp.ring_stride + i]));
-        same = __all_sync(0xffffffffu, same);
-        if (same && tp.ends[it].has_symbols) {
-            long long n_used = 0, n_true = 0;
-            const float t0 = thg[tp.pkts[tc.first_slot + j].klo];
-            (void)unwrap_against(tp.ends[it].est_start_used, t0, &n_used);
-            (void)unwrap_against(tp.ends[prev].st.est, t0, &n_true);
-            same = n_used == n_true;
-        }
-        ok = same;
-        wraps += tp.ends[it].wraps_delta;
-    }
-    if (np >= 1) wraps += tp.ends[tc.first_item + 1].wraps_delta;
-    if (ok) {
-        const int last = tc.first_item + np;                          // item of the last packet
-        for (int i = lane; i < P; i += 32) ring_base[d.ring_off + i] = tp.end_ring[(size_t)last * tp.ring_stride + i];
-        if (lane == 0) {
-            ChanState st = tp.ends[last].st;
-            st.wraps = state[tc.ch].wraps + wraps;
-            state[tc.ch] = st;
-            tp.fail[tc.ch] = 0;
-            atomicAdd(&counters->tp_packets, (unsigned long long)np);
-        }
-    } else if (lane == 0) {
-        tp.fail[tc.ch] = 1;
-        atomicAdd(&counters->seq_channels, 1ULL);
+    if (tp.fail[tc.ch]) { if (lane == 0) atomicAdd(&counters->seq_channels, 1ULL); return; }
+    unsigned long long wraps = 0;
+    for (int j = lane; j <= np; j += 32) wraps += tp.ends[tc.first_item + j].wraps_delta;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) wraps += __shfl_xor_sync(0xffffffffu, wraps, o);
+    const int last = tc.first_item + np;                              // record of the last packet
+    for (int i = lane; i < P; i += 32) ring_base[d.ring_off + i] = tp.end_ring[(size_t)last * tp.ring_stride + i];
+    if (lane == 0) {
+        ChanState st = tp.ends[last].st;
+        st.wraps = state[tc.ch].wraps + wraps;
+        state[tc.ch] = st;
+        atomicAdd(&counters->tp_packets, (unsigned long long)np);
     }
 }
 
@@ -1210,7 +1230,7 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
         if (e != cudaSuccess) return e;
         c.prof->begin(KID_TP, c.stream);
         k_tp_scan<<<(c.tp_n_slots + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_n_slots);
-        k_tp_resolve<<<(c.tp_n_chans + 63) / 64, 64, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_ends);
+        k_tp_resolve<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_ends);
         c.prof->end(c.stream);
         (*c.launches) += 2;
         e = cudaGetLastError();
@@ -1219,9 +1239,10 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
         e = launch_chain_kernel(c, Pcap, smem, c.tp_n_items, t2);
         if (e != cudaSuccess) return e;
         c.prof->begin(KID_TP, c.stream);
-        k_tp_check<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, tp, c.d_counters);
+        k_tp_check<<<(c.tp_n_items + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2);
+        k_tp_install<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_state, c.d_ring, tp, c.d_counters);
         c.prof->end(c.stream);
-        (*c.launches)++;
+        (*c.launches) += 2;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         TpCtl t3 = tp; t3.fallback = 1;
