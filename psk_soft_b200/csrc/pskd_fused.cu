@@ -3,8 +3,8 @@
 //   k_fused<S,..> ingest + symbol timing + M-th power angle + unwrap/LinearFit chain + derotate /
 //                differential decode / slice, per channel, with every intermediate (energies,
 //                window sums, selected samples, angles, unwrapped phases) living in shared memory
-//                or registers.  HBM sees only the algorithmic bytes: each IQ sample read once,
-//                each output written once.
+//                or registers.  HBM sees only the algorithmic bytes: each IQ sample is read from
+//                DRAM once (a second time from L2), each output written once.
 //                reference rows: cpp/psk_soft.cpp:380-603, 619-636 and LinearFit :35-185.
 //
 // Work decomposition: ONE WARP PER UNIT, warp-synchronous (no block barriers).  A unit is a run
@@ -12,24 +12,28 @@
 // pulls units from a ticket counter in packet-major order; unit (ch, j) waits for (ch, j-1)
 // (its phase-chain state travels through global memory), which was ticketed n_channels earlier.
 //
-// Per unit the warp streams over its symbols in chunks of 32 input rows (1 row = 1 symbol = S
-// samples):
-//   ingest : coalesced 128-bit loads (prefetched one chunk ahead in registers), e = f32(re^2+im^2)
-//            (std::norm<float>, :448) into a ring of the last numAvg-1+32 rows' energies
-//   timing : lane (phase p, row group g) forms the exact (double) sliding window sums of its rows
-//            (:451, :576), an exclusive scan over the row groups adds the carried window sum; the
-//            sums are transposed through shared memory so that lane = row takes the FIRST maximum
-//            over the phases (:462), gathers that sample of the window's oldest symbol (:465,
-//            an L2 hit: the row was streamed numAvg-1 rows ago; consumed one chunk later so the
-//            latency is hidden) and forms atan2f(s^M) (:474)
+// Per unit the warp streams over its symbols in chunks of 32 rows (1 row = 1 symbol = S samples).
+// A chunk needs two blocks of 32 rows of raw samples in shared memory, both copied by cp.async one
+// chunk ahead: the LEAD block (the rows entering the 32 energy windows: the stream's new samples,
+// from HBM, prefetched into L2 two chunks ahead) and the TRAIL block (the rows leaving the windows,
+// numAvg-1 rows behind: an L2 hit, they were the lead block three chunks ago).  There is no energy
+// ring: a warp's shared-memory footprint does not depend on numAvg and stays below 9.3 KB, which
+// is what lets 24 warps share an SM.
+//   timing : lane (phase p, row group g) forms e = f32(re^2+im^2) (std::norm<float>, :448) of its
+//            rows' lead and trail samples and from them the exact (double) sliding window sums
+//            (:451, :576); a scan over the row groups adds the carried window sum; the sums are
+//            transposed through shared memory so that lane = row takes the FIRST maximum over the
+//            phases (:462), picks that sample of its row out of the trail block (:465) and forms
+//            atan2f(s^M) (:474)
 //   chain  : every 128 symbols (or at a packet end): classic-unwrap prediction of the integer
 //            unwrap counts, double prefix sums for LinearFit's ySum / xySum, point-wise verification
 //            of every count against the reference's rule round((est_{k-1}-theta_k)/2pi) (:477) and
 //            repair -- the emitted integers are exactly those of the sequential recursion
 //   back   : derotate by -est/M (+pi/4) or divide by the previous sample (:484-501), slice
 //            (:503-566); phase, soft and bits are staged in shared memory and written coalesced.
-// The chain + back stage is one non-inlined function (fz_drain) so that it gets its own register
-// allocation; everything it shares with the chunk loop lives in the warp's FzCtx in shared memory.
+// The front stage (fz_chunk) and the chain + back stage (fz_drain) are non-inlined functions so
+// that each gets its own register allocation; what they share lives in the warp's FzCtx in
+// shared memory.
 #include "pskd_internal.h"
 #include "pskd_device.cuh"
 #include <cstdlib>
@@ -40,12 +44,12 @@ namespace pskd {
 #define PSKD_FZ_WARPS 4
 #endif
 constexpr int FZ_WARPS = PSKD_FZ_WARPS; // warps (= concurrent units) per CTA
-constexpr int FZ_CH = 32;              // input rows per ingest chunk
+constexpr int FZ_CH = 32;              // rows per chunk
 constexpr int FZ_B = 128;              // symbols per chain block (4 per lane)
 constexpr int FZ_BUF = 160;            // capacity of the (theta, sample) block buffer
 constexpr int FZ_MAX_ITERS = 16;
 #ifndef PSKD_FZ_MIN_CTAS
-#define PSKD_FZ_MIN_CTAS 4
+#define PSKD_FZ_MIN_CTAS 5
 #endif
 
 struct FzCtx {                         // one per warp, shared memory
@@ -55,18 +59,19 @@ struct FzCtx {                         // one per warp, shared memory
     const float2* tail;
     const ChanDesc* desc;
     float2* o_soft; float* o_phase; int16_t* o_bits;       // this channel's output rows (or null)
+    int16_t* o_sidx;
     double sri_xdelta;
-    long long tail_len, pkt_len;
+    long long tail_len, pkt_len, V;
+    unsigned long long wraps0;
     int n_pkts, pk1, K, A, M, P, bpb, diff;
     int pkt, pk_hi, kchain, nbuf, cz_valid, unit_done, flags;
     unsigned int passes, seq_blocks, blocks;
     float fP1;
-    // chunk-loop constants of the unit (parked here to keep the loop's register set small)
-    int kA, kB, lag, RR, NS, tc, c_lo, c_hi, nchunks, gather_in, ch, ug;
-    int c, krow, slot, nprev;          // chunk-loop state (fz_chunk)
-    long long V;
-    int16_t* o_sidx;
-    unsigned long long wraps0;
+    // front-stage constants of the unit and its loop state (fz_chunk)
+    int kA, kB, lag, c_lo, c_hi, nchunks, ch, ug;
+    int a16;                           // staged blocks are copied in 16-byte pieces (else 8-byte)
+    int c;                             // next chunk
+    int inflight;                      // chunk c's blocks are already on their way (cp.async)
 };
 
 constexpr int fz_align16(int x) { return (x + 15) & ~15; }
@@ -74,31 +79,30 @@ constexpr int fz_align16(int x) { return (x + 15) & ~15; }
 template <int S> struct FzCfg {
     static constexpr int G = 32 / S;                         // row groups (lane = g*S + p)
     static constexpr int R = (32 + G - 1) / G;               // rows per group
-    static constexpr bool PADDED = ((R * S) % 32) == 0;      // groups would collide on the banks: pad
-    static constexpr int PAD = PADDED ? 32 / G : 0;          // floats of padding after every R rows
     static constexpr int ES = (S & 1) ? S : S + 1;           // row stride of the transposition buffer (doubles)
-    static constexpr int NQ = (S * 16 + 31) / 32;            // float4 loads per lane per chunk
-    static_assert(!PADDED || (32 % R) == 0, "padded groups must tile a chunk");
-    __host__ __device__ static constexpr int fpos(int pos) { return pos * S + (PADDED ? (pos / R) * PAD : 0); }
-    __host__ __device__ static constexpr int ring_rows(int A) { return ((A - 1 + 32 + 31) / 32) * 32; }
+    static constexpr int CHS = FZ_CH * S;                    // samples per staged block
+    static constexpr int NQ16 = (S * 16 + 31) / 32;          // 16-byte pieces per lane per block
+    // physical position of logical sample n (= row*S + phase) inside a staged block.  S = 8: rows
+    // 8..15 and 24..31 swap places in pairs, which puts the four row groups of one 64-bit read
+    // (lane = (phase, group), same row of every group) on disjoint banks.
+    __host__ __device__ static constexpr int phys(int n) { return S == 8 ? (n ^ (((n >> 6) & 1) << 3)) : n; }
 };
 
-// compile-time layout of one warp's shared-memory region.  RRC = ring capacity in rows (covers
-// numAvg <= RRC - 31), PC = phaseAvg capacity.
-template <int S, int RRC, int PC> struct FzL {
+// compile-time layout of one warp's shared-memory region.  PC = phaseAvg capacity.
+template <int S, int PC> struct FzL {
     using C = FzCfg<S>;
-    static constexpr int RING_F = (C::fpos(RRC + C::R) + 3) & ~3;
-    static constexpr int OFF_RAW = RING_F * 4;                             // float2 raw[32*S]  cp.async landing of the next chunk
-    static constexpr int OFF_GL = OFF_RAW + 32 * S * 8;                    // float2 gland[32]  cp.async landing of the gathered samples
-    static constexpr int OFF_CW = OFF_GL + 32 * 8;                         // double cwl[32]    per-lane carried window sum
-    static constexpr int OFF_TH = OFF_CW + 32 * 8;                         // float  th[FZ_BUF]
+    static constexpr int BLK = C::CHS * 8;                                 // one staged block of raw samples
+    static constexpr int OFF_L = 0;                                        // float2 lead[32*S]
+    static constexpr int OFF_T = BLK;                                      // float2 trail[32*S]
+    static constexpr int OFF_CW = 2 * BLK;                                 // double cw[16]     carried window sum per phase
+    static constexpr int OFF_TH = OFF_CW + 16 * 8;                         // float  th[FZ_BUF]
     static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                    // float2 selb[FZ_BUF + 2]; [1] = previous sample
     static constexpr int OFF_YH = fz_align16(OFF_SEL + (FZ_BUF + 2) * 8);  // float  yh[PC]   y history, logical order
     static constexpr int OFF_CTX = fz_align16(OFF_YH + PC * 4);
     static constexpr int OFF_CZ = fz_align16(OFF_CTX + (int)sizeof(FzCtx));// double cz[PC + 1], ends where ALIAS starts
     static constexpr int OFF_ALIAS = OFF_CZ + fz_align16((PC + 1) * 8);
-    static constexpr int E_BYTES = 32 * C::ES * 8;                         // ingest phase: window sums [32][ES]
-    static constexpr int C_BYTES = FZ_B * 8 + FZ_B * 4 + (FZ_B + 4) * 4;   // chain phase: prefix block, y block, est block
+    static constexpr int E_BYTES = 32 * C::ES * 8;                         // front stage: window sums [32][ES]
+    static constexpr int C_BYTES = FZ_B * 8 + FZ_B * 4 + (FZ_B + 4) * 4;   // chain stage: prefix block, y block, est block
     static constexpr int BYTES = OFF_ALIAS + fz_align16(E_BYTES > C_BYTES ? E_BYTES : C_BYTES);
 };
 
@@ -361,24 +365,294 @@ __device__ __forceinline__ unsigned fz_back4(const float2 (&sv)[4], float2 sprev
 }
 
 // ---------------------------------------------------------------------------------------------
-// fz_drain: consume buffered symbols: chain blocks of FZ_B (shorter at a packet end) followed by
-// the output stage; runs the packet epilogue / next prologue whenever a packet is exhausted.
+// The chain + back stage runs as three non-inlined functions (own register allocations, compact
+// code): fz_drain (packet bookkeeping, block sizing, buffer compaction) calls, per block of up to
+// FZ_B buffered symbols, fz_chain_fast (scan / verify / repair; the estimates land in th[], which
+// doubles as the staging of phase_dataFloat_out) and fz_back_block (derotate / slice / stores).
 // ---------------------------------------------------------------------------------------------
-template <int S, int RRC, int PC>
-static __device__ __noinline__ void fz_drain(const unsigned wofs)
+
+// phase chain of one block of m symbols at buffer offset 0 (full history window, cx.st.fit.pts == P):
+// cpp/psk_soft.cpp:476-482 with LinearFit::next (:48-87).  Returns false if the counts did not settle
+// within FZ_MAX_ITERS passes (the caller then runs the literal recursion); on success the state, the
+// history (yh, cz) and th[0..m) = est are updated.
+template <int S, int PC>
+static __device__ __noinline__ bool fz_chain_fast(const unsigned wofs, const int m)
 {
-    using L = FzL<S, RRC, PC>;
+    using L = FzL<S, PC>;
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     double* czblk = reinterpret_cast<double*>(wb + L::OFF_ALIAS);                    // cz[P+1 ...]
     float*  yblk = reinterpret_cast<float*>(wb + L::OFF_ALIAS + FZ_B * 8);
     float*  estv = yblk + FZ_B;
     const int lane = fz_lane();
-    const int P = cx.P, M = cx.M, bpb = cx.bpb;
+    const int P = cx.P;
     double* cz = czblk - (P + 1);
+    const int i0 = lane * 4;
+
+    if (cx.st.fit.head != 0) { fz_normalize_ring(yh, estv, cx.st.fit, P, lane); if (lane == 0) cx.cz_valid = 0; __syncwarp(); }
+    if (!cx.cz_valid) { fz_rebuild_cz(yh, cz, P, lane); if (lane == 0) cx.cz_valid = 1; __syncwarp(); }
+
+    const float4 t4 = *reinterpret_cast<const float4*>(th + i0);
+    const float tl[4] = {t4.x, t4.y, t4.z, t4.w};
+    const float xdelta = cx.st.fit.xdelta;
+    const float fP1 = cx.fP1;
+    const double xd = (double)xdelta;
+    const double HPP = cz[P];
+    // classic-unwrap prediction of n (integer scan), first symbol by the reference's rule
+    int nloc[4];
+    {
+        const float tprev = __shfl_up_sync(0xffffffffu, t4.w, 1);
+        int run = 0;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const float pv = (v == 0) ? tprev : tl[v - 1];
+            int dn = -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
+            if (v == 0 && lane == 0) dn = fz_unwrap_count_slow(cx.st.est, tl[0]);
+            run += dn; nloc[v] = run;
+        }
+        const int off = warp_scan_int(run, lane) - run;
+#pragma unroll
+        for (int v = 0; v < 4; v++) nloc[v] += off;
+    }
+    const int last = m - 1;
+    int iter = 0;
+    bool done = false;
+    float yl[4], el[4];
+    double Yv = 0.0, Xv = 0.0;                       // sums after the block's last symbol (owner lane)
+    while (true) {
+        double Cl[4], hi0;
+        {
+            double run = 0.0;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const float y = __double2float_rn(daddr((double)tl[v], dmulr((double)nloc[v], PSKD_M_2PI)));   // :478,481
+                yl[v] = y; run = daddr(run, (double)y); Cl[v] = run;
+            }
+            hi0 = daddr(HPP, dsubr(warp_scan_dbl(run, lane), run));          // cz[P+i0]
+#pragma unroll
+            for (int v = 0; v < 4; v++) Cl[v] = daddr(hi0, Cl[v]);           // cz[P+1+i0+v]
+        }
+        *reinterpret_cast<float4*>(yblk + i0) = make_float4(yl[0], yl[1], yl[2], yl[3]);
+        *reinterpret_cast<double2*>(czblk + i0) = make_double2(Cl[0], Cl[1]);
+        *reinterpret_cast<double2*>(czblk + i0 + 2) = make_double2(Cl[2], Cl[3]);
+        __syncwarp();
+        double Ys[4], Xl[4];
+        double trun = 0.0;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const double hi = (v == 0) ? hi0 : Cl[v - 1];                    // cz[P+i]
+            const double W = dsubr(hi, cz[i0 + v + 1]);                      // ySum after :70
+            const double a = dmulr(xd, W);                                   // :72
+            const double T = (double)fmulr(fmulr(yl[v], fP1), xdelta);       // :78
+            trun = daddr(trun, dsubr(T, a)); Xl[v] = trun;
+            Ys[v] = daddr(W, (double)yl[v]);                                 // :75
+        }
+        const double xoff = daddr(cx.st.fit.xySum, dsubr(warp_scan_dbl(trun, lane), trun));
+        {
+            const FitConst fc = cx.fc;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                Xl[v] = daddr(xoff, Xl[v]);
+                el[v] = fit_eval_fast(fc, Ys[v], Xl[v], nullptr, nullptr);   // :135-162
+            }
+        }
+        Yv = Ys[0]; Xv = Xl[0];
+#pragma unroll
+        for (int v = 1; v < 4; v++) if (v == (last & 3)) { Yv = Ys[v]; Xv = Xl[v]; }
+        // verify every predicted n against the reference's rule (:477) with est_{i-1}
+        const float eprev = __shfl_up_sync(0xffffffffu, el[3], 1);
+        int mymis = 0x7fffffff, mydelta = 0;
+        {
+            int nt[4];
+            bool knife = false;
+#pragma unroll
+            for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count((v == 0) ? eprev : el[v - 1], tl[v], knife);
+            if (__any_sync(0xffffffffu, knife)) {           // rare: a quotient next to a half-integer
+#pragma unroll
+                for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count_slow((v == 0) ? eprev : el[v - 1], tl[v]);
+            }
+#pragma unroll
+            for (int v = 3; v >= 0; v--) {
+                const int i = i0 + v;
+                if (i >= 1 && i < m && nt[v] != nloc[v]) { mymis = i; mydelta = nt[v] - nloc[v]; }
+            }
+        }
+        const int mis = (int)__reduce_min_sync(0xffffffffu, (unsigned)mymis);
+        if (mis == 0x7fffffff) { done = true; break; }
+        if (++iter > FZ_MAX_ITERS) break;
+        const int delta = __shfl_sync(0xffffffffu, mydelta, mis >> 2);
+#pragma unroll
+        for (int v = 0; v < 4; v++) if (i0 + v >= mis) nloc[v] += delta;
+        __syncwarp();
+    }
+    if (iter && lane == 0) cx.passes += (unsigned)iter;
+    if (!done) {
+        if (lane == 0) { cx.seq_blocks++; cx.cz_valid = 0; }
+        __syncwarp();
+        return false;
+    }
+    if ((last >> 2) == lane) {
+        const FitConst fc = cx.fc;
+        FitState& f = cx.st.fit;
+        float mm, bb;
+        cx.st.est = fit_eval_fast(fc, Yv, Xv, &mm, &bb);
+        f.ySum = Yv; f.xySum = Xv; f.m = mm; f.b = bb; f.count += m;
+    }
+    // phase_dataFloat_out (:482) is staged in th[0..m): the angles are consumed
+    if (i0 + 3 < m) *reinterpret_cast<float4*>(th + i0) = make_float4(el[0], el[1], el[2], el[3]);
+    else if (i0 < m) {
+#pragma unroll
+        for (int v = 0; v < 3; v++) if (i0 + v < m) th[i0 + v] = el[v];
+    }
+    __syncwarp();
+    // new history = last P of (history ++ block): shift the prefix and the values by m
+    const double czm = cz[m];
+    for (int base = 0; base <= P; base += 32) {
+        const int j = base + lane;
+        double pv = 0.0; float yv = 0.0f;
+        if (j <= P) pv = dsubr(cz[m + j], czm);
+        if (j < P) yv = (m + j < P) ? yh[m + j] : yblk[m + j - P];
+        __syncwarp();
+        if (j <= P) cz[j] = pv;
+        if (j < P) yh[j] = yv;
+        __syncwarp();
+    }
+    return true;
+}
+
+// back stage of one block of m symbols at buffer offset 0: derotate / differential decode / slice
+// (cpp/psk_soft.cpp:484-566) from selb[] (samples) and th[] (estimates), then the coalesced stores
+// of phase / soft / bits for symbols [kchain, kchain + m).
+template <int S, int PC>
+static __device__ __noinline__ void fz_back_block(const unsigned wofs, const int m)
+{
+    using L = FzL<S, PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    short* bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS);            // chain buffers are dead now
+    const int lane = fz_lane();
+    const int M = cx.M, bpb = cx.bpb, kchain = cx.kchain;
+    const bool diff = cx.diff != 0;
+    const int i0 = lane * 4;
+    float2 sv[4];
+    float el[4];
+    {
+        const float4 a = *reinterpret_cast<const float4*>(selb + 2 + i0);
+        const float4 b = *reinterpret_cast<const float4*>(selb + 4 + i0);
+        const float4 e4 = *reinterpret_cast<const float4*>(th + i0);
+        sv[0] = make_float2(a.x, a.y); sv[1] = make_float2(a.z, a.w);
+        sv[2] = make_float2(b.x, b.y); sv[3] = make_float2(b.z, b.w);
+        el[0] = e4.x; el[1] = e4.y; el[2] = e4.z; el[3] = e4.w;
+    }
+    const float2 sprev = selb[1 + i0];
+    __syncwarp();
+    unsigned bsym[4];
+    unsigned fixmask = 0;
+    {
+        float2 cv[4];
+        unsigned badmask;
+        switch (bpb * 2 + (diff ? 1 : 0)) {
+            case 6: badmask = fz_back4<3, false>(sv, sprev, el, M, cv, bsym); break;
+            case 7: badmask = fz_back4<3, true>(sv, sprev, el, M, cv, bsym); break;
+            case 4: badmask = fz_back4<2, false>(sv, sprev, el, M, cv, bsym); break;
+            case 5: badmask = fz_back4<2, true>(sv, sprev, el, M, cv, bsym); break;
+            case 2: badmask = fz_back4<1, false>(sv, sprev, el, M, cv, bsym); break;
+            case 3: badmask = fz_back4<1, true>(sv, sprev, el, M, cv, bsym); break;
+            case 0: badmask = fz_back4<0, false>(sv, sprev, el, M, cv, bsym); break;
+            default: badmask = fz_back4<0, true>(sv, sprev, el, M, cv, bsym); break;
+        }
+        if (i0 + 3 < m) {
+            *reinterpret_cast<float4*>(selb + 2 + i0) = make_float4(cv[0].x, cv[0].y, cv[1].x, cv[1].y);
+            *reinterpret_cast<float4*>(selb + 4 + i0) = make_float4(cv[2].x, cv[2].y, cv[3].x, cv[3].y);
+        } else if (i0 < m) {
+#pragma unroll
+            for (int v = 0; v < 3; v++) if (i0 + v < m) selb[2 + i0 + v] = cv[v];
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) if (i0 + v >= m) badmask &= ~(1u << v);
+        fixmask = badmask;
+    }
+    int16_t* o_bits = cx.o_bits;
+    if (bpb > 0 && o_bits) {
+        unsigned* dst = reinterpret_cast<unsigned*>(bstage) + lane * 2 * bpb;
+        if (bpb == 3) fz_store_bits<3>(dst, bsym);
+        else if (bpb == 2) fz_store_bits<2>(dst, bsym);
+        else fz_store_bits<1>(dst, bsym);
+    }
+    if (__any_sync(0xffffffffu, fixmask != 0)) {            // rare: literal evaluation of the flagged symbols
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            if ((fixmask >> v) & 1u)
+                fz_back_literal(sv[v], (v == 0) ? sprev : sv[(v + 3) & 3], el[v], M, bpb, diff ? 1 : 0,
+                                selb + 2 + i0 + v, bstage + (i0 + v) * bpb);
+        }
+    }
+    __syncwarp();
+    {
+        float* o_phase = cx.o_phase;
+        if (o_phase) {
+            float* o = o_phase + kchain;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, th[i]); }
+        }
+        float2* o_soft = cx.o_soft;
+        if (o_soft) {
+            float2* o = o_soft + kchain;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, selb[2 + i]); }
+        }
+        if (bpb > 0 && o_bits) {
+            int16_t* o = o_bits + (long long)kchain * bpb;
+            const int nsh = m * bpb;
+            if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+                const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage) + lane;
+                unsigned* o32 = reinterpret_cast<unsigned*>(o) + lane;
+                const int nw = nsh >> 1;                  // <= 192 words
+#pragma unroll
+                for (int q = 0; q < 6; q++) if (lane + 32 * q < nw) __stcs(o32 + 32 * q, s32[32 * q]);
+                if ((nsh & 1) && lane == 0) o[nsh - 1] = bstage[nsh - 1];
+            } else {
+                for (int t = lane; t < nsh; t += 32) o[t] = bstage[t];
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// literal recursion for one block (lane 0) and its estimates into th[0..m)
+template <int S, int PC>
+static __device__ __noinline__ void fz_chain_slow(const unsigned wofs, const int m)
+{
+    using L = FzL<S, PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    float*  estv = reinterpret_cast<float*>(wb + L::OFF_ALIAS + FZ_B * 8) + FZ_B;
+    const int lane = fz_lane();
+    __syncwarp();
+    if (lane == 0) { fz_block_sequential(cx, yh, th, estv, m); cx.cz_valid = 0; }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) th[i] = estv[i];
+    __syncwarp();
+}
+
+// fz_drain: consume buffered symbols: chain blocks of FZ_B (shorter at a packet end) followed by
+// the output stage; runs the packet epilogue / next prologue whenever a packet is exhausted.
+template <int S, int PC>
+static __device__ __noinline__ void fz_drain(const unsigned wofs)
+{
+    using L = FzL<S, PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    const int lane = fz_lane();
 
     while (!cx.unit_done) {
         const int kchain = cx.kchain;
@@ -403,8 +677,9 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
 
         // ---- one sub-block of m symbols at buffer offset 0 ----------------------------------------
         int m = want;
+        const int P = cx.P;
         const int pts = cx.st.fit.pts, cnt = cx.st.fit.count;
-        bool fast = (pts == P) && (P > 1);
+        const bool fast = (pts == P) && (P > 1);
         if (fast && cnt + m > 1048576) {
             if (cnt == 1048576) {                                                   // :51-52 at a block edge
                 if (lane == 0) { SmemRing r{yh}; fit_resum(cx.st.fit, r); }
@@ -414,227 +689,12 @@ static __device__ __noinline__ void fz_drain(const unsigned wofs)
             m = 1048576 - cnt;                                                      // stop at the re-sum point
         }
         if (!fast) m = min(m, max(1, P - pts));                                     // fill-up runs sequentially
-        const int i0 = lane * 4;
-        const float4 t4 = *reinterpret_cast<const float4*>(th + i0);
-        const float tl[4] = {t4.x, t4.y, t4.z, t4.w};
-        float el[4];
-        bool done = false;
-        if (fast) {
-            if (cx.st.fit.head != 0) { fz_normalize_ring(yh, estv, cx.st.fit, P, lane); cx.cz_valid = 0; __syncwarp(); }
-            if (!cx.cz_valid) { fz_rebuild_cz(yh, cz, P, lane); if (lane == 0) cx.cz_valid = 1; __syncwarp(); }
-            const FitConst fc = cx.fc;
-            const float xdelta = cx.st.fit.xdelta;
-            const float fP1 = cx.fP1;
-            const double xd = (double)xdelta;
-            const double X0 = cx.st.fit.xySum;
-            const double HPP = cz[P];
-            const float est0 = cx.st.est;
-            // classic-unwrap prediction of n (integer scan), first symbol by the reference's rule
-            int nloc[4];
-            {
-                const float tprev = __shfl_up_sync(0xffffffffu, t4.w, 1);
-                int run = 0;
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    const float pv = (v == 0) ? tprev : tl[v - 1];
-                    int dn = -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
-                    if (v == 0 && lane == 0) dn = fz_unwrap_count_slow(est0, tl[0]);
-                    run += dn; nloc[v] = run;
-                }
-                const int off = warp_scan_int(run, lane) - run;
-#pragma unroll
-                for (int v = 0; v < 4; v++) nloc[v] += off;
-            }
-            int iter = 0;
-            float yl[4]; double Ys[4], Xl[4];
-            while (true) {
-                double Cl[4], hi0;
-                {
-                    double run = 0.0;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        const float y = __double2float_rn(daddr((double)tl[v], dmulr((double)nloc[v], PSKD_M_2PI)));   // :478,481
-                        yl[v] = y; run = daddr(run, (double)y); Cl[v] = run;
-                    }
-                    hi0 = daddr(HPP, dsubr(warp_scan_dbl(run, lane), run));          // cz[P+i0]
-#pragma unroll
-                    for (int v = 0; v < 4; v++) Cl[v] = daddr(hi0, Cl[v]);           // cz[P+1+i0+v]
-                }
-                *reinterpret_cast<float4*>(yblk + i0) = make_float4(yl[0], yl[1], yl[2], yl[3]);
-                *reinterpret_cast<double2*>(czblk + i0) = make_double2(Cl[0], Cl[1]);
-                *reinterpret_cast<double2*>(czblk + i0 + 2) = make_double2(Cl[2], Cl[3]);
-                __syncwarp();
-                double trun = 0.0;
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    const double hi = (v == 0) ? hi0 : Cl[v - 1];                    // cz[P+i]
-                    const double W = dsubr(hi, cz[i0 + v + 1]);                      // ySum after :70
-                    const double a = dmulr(xd, W);                                   // :72
-                    const double T = (double)fmulr(fmulr(yl[v], fP1), xdelta);       // :78
-                    trun = daddr(trun, dsubr(T, a)); Xl[v] = trun;
-                    Ys[v] = daddr(W, (double)yl[v]);                                 // :75
-                }
-                const double xoff = daddr(X0, dsubr(warp_scan_dbl(trun, lane), trun));
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    Xl[v] = daddr(xoff, Xl[v]);
-                    el[v] = fit_eval_fast(fc, Ys[v], Xl[v], nullptr, nullptr);       // :135-162
-                }
-                // verify every predicted n against the reference's rule (:477) with est_{i-1}
-                const float eprev = __shfl_up_sync(0xffffffffu, el[3], 1);
-                int mymis = 0x7fffffff, mydelta = 0;
-                {
-                    int nt[4];
-                    bool knife = false;
-#pragma unroll
-                    for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count((v == 0) ? eprev : el[v - 1], tl[v], knife);
-                    if (__any_sync(0xffffffffu, knife)) {           // rare: a quotient next to a half-integer
-#pragma unroll
-                        for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count_slow((v == 0) ? eprev : el[v - 1], tl[v]);
-                    }
-#pragma unroll
-                    for (int v = 3; v >= 0; v--) {
-                        const int i = i0 + v;
-                        if (i >= 1 && i < m && nt[v] != nloc[v]) { mymis = i; mydelta = nt[v] - nloc[v]; }
-                    }
-                }
-                const int mis = (int)__reduce_min_sync(0xffffffffu, (unsigned)mymis);
-                if (mis == 0x7fffffff) { done = true; break; }
-                if (++iter > FZ_MAX_ITERS) break;
-                const int delta = __shfl_sync(0xffffffffu, mydelta, mis >> 2);
-#pragma unroll
-                for (int v = 0; v < 4; v++) if (i0 + v >= mis) nloc[v] += delta;
-                __syncwarp();
-            }
-            if (iter && lane == 0) cx.passes += (unsigned)iter;
-            if (done) {
-                const int last = m - 1;
-                if ((last >> 2) == lane) {
-                    double Yv = Ys[0], Xv = Xl[0];
-#pragma unroll
-                    for (int v = 1; v < 4; v++) if (v == (last & 3)) { Yv = Ys[v]; Xv = Xl[v]; }
-                    FitState& f = cx.st.fit;
-                    float mm, bb;
-                    cx.st.est = fit_eval_fast(fc, Yv, Xv, &mm, &bb);
-                    f.ySum = Yv; f.xySum = Xv; f.m = mm; f.b = bb; f.count += m;
-                }
-                __syncwarp();
-                // new history = last P of (history ++ block): shift the prefix and the values by m
-                const double czm = cz[m];
-                for (int base = 0; base <= P; base += 32) {
-                    const int j = base + lane;
-                    double pv = 0.0; float yv = 0.0f;
-                    if (j <= P) pv = dsubr(cz[m + j], czm);
-                    if (j < P) yv = (m + j < P) ? yh[m + j] : yblk[m + j - P];
-                    __syncwarp();
-                    if (j <= P) cz[j] = pv;
-                    if (j < P) yh[j] = yv;
-                    __syncwarp();
-                }
-            } else {
-                if (lane == 0) { cx.seq_blocks++; cx.cz_valid = 0; }
-            }
-        }
-        if (!done) {
-            __syncwarp();
-            if (lane == 0) { fz_block_sequential(cx, yh, th, estv, m); cx.cz_valid = 0; }
-            __syncwarp();
-#pragma unroll
-            for (int v = 0; v < 4; v++) el[v] = (i0 + v < m) ? estv[i0 + v] : 0.0f;
-            __syncwarp();
-        }
-        if (lane == 0) cx.blocks++;
-
-        // ---- back: derotate / differential decode / slice (cpp/psk_soft.cpp:484-566) -----------------
-        const bool diff = cx.diff != 0;
         const float2 prev_new = selb[2 + m - 1];
-        float2 sv[4];
-        {
-            const float4 a = *reinterpret_cast<const float4*>(selb + 2 + i0);
-            const float4 b = *reinterpret_cast<const float4*>(selb + 4 + i0);
-            sv[0] = make_float2(a.x, a.y); sv[1] = make_float2(a.z, a.w);
-            sv[2] = make_float2(b.x, b.y); sv[3] = make_float2(b.z, b.w);
-        }
-        const float2 sprev = selb[1 + i0];
-        __syncwarp();
-        // phase_dataFloat_out (:482): staged in th[0..m), i.e. over consumed entries only
-        if (i0 + 3 < m) *reinterpret_cast<float4*>(th + i0) = make_float4(el[0], el[1], el[2], el[3]);
-        else if (i0 < m) {
-#pragma unroll
-            for (int v = 0; v < 3; v++) if (i0 + v < m) th[i0 + v] = el[v];
-        }
-        unsigned bsym[4];
-        unsigned fixmask = 0;
-        {
-            float2 cv[4];
-            unsigned badmask;
-            switch (bpb * 2 + (diff ? 1 : 0)) {
-                case 6: badmask = fz_back4<3, false>(sv, sprev, el, M, cv, bsym); break;
-                case 7: badmask = fz_back4<3, true>(sv, sprev, el, M, cv, bsym); break;
-                case 4: badmask = fz_back4<2, false>(sv, sprev, el, M, cv, bsym); break;
-                case 5: badmask = fz_back4<2, true>(sv, sprev, el, M, cv, bsym); break;
-                case 2: badmask = fz_back4<1, false>(sv, sprev, el, M, cv, bsym); break;
-                case 3: badmask = fz_back4<1, true>(sv, sprev, el, M, cv, bsym); break;
-                case 0: badmask = fz_back4<0, false>(sv, sprev, el, M, cv, bsym); break;
-                default: badmask = fz_back4<0, true>(sv, sprev, el, M, cv, bsym); break;
-            }
-            if (i0 + 3 < m) {
-                *reinterpret_cast<float4*>(selb + 2 + i0) = make_float4(cv[0].x, cv[0].y, cv[1].x, cv[1].y);
-                *reinterpret_cast<float4*>(selb + 4 + i0) = make_float4(cv[2].x, cv[2].y, cv[3].x, cv[3].y);
-            } else if (i0 < m) {
-#pragma unroll
-                for (int v = 0; v < 3; v++) if (i0 + v < m) selb[2 + i0 + v] = cv[v];
-            }
-#pragma unroll
-            for (int v = 0; v < 4; v++) if (i0 + v >= m) badmask &= ~(1u << v);
-            fixmask = badmask;
-        }
-        short* bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS);           // chain buffers are dead now
-        int16_t* o_bits = cx.o_bits;
-        if (bpb > 0 && o_bits) {
-            unsigned* dst = reinterpret_cast<unsigned*>(bstage) + lane * 2 * bpb;
-            if (bpb == 3) fz_store_bits<3>(dst, bsym);
-            else if (bpb == 2) fz_store_bits<2>(dst, bsym);
-            else fz_store_bits<1>(dst, bsym);
-        }
-        if (__any_sync(0xffffffffu, fixmask != 0)) {            // rare: literal evaluation of the flagged symbols
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                if ((fixmask >> v) & 1u)
-                    fz_back_literal(sv[v], (v == 0) ? sprev : sv[(v + 3) & 3], el[v], M, bpb, diff ? 1 : 0,
-                                    selb + 2 + i0 + v, bstage + (i0 + v) * bpb);
-            }
-        }
-        __syncwarp();
-        {
-            float* o_phase = cx.o_phase;
-            if (o_phase) {
-                float* o = o_phase + kchain;
-#pragma unroll
-                for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, th[i]); }
-            }
-            float2* o_soft = cx.o_soft;
-            if (o_soft) {
-                float2* o = o_soft + kchain;
-#pragma unroll
-                for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, selb[2 + i]); }
-            }
-            if (bpb > 0 && o_bits) {
-                int16_t* o = o_bits + (long long)kchain * bpb;
-                const int nsh = m * bpb;
-                if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
-                    const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage) + lane;
-                    unsigned* o32 = reinterpret_cast<unsigned*>(o) + lane;
-                    const int nw = nsh >> 1;                  // <= 192 words
-#pragma unroll
-                    for (int q = 0; q < 6; q++) if (lane + 32 * q < nw) __stcs(o32 + 32 * q, s32[32 * q]);
-                    if ((nsh & 1) && lane == 0) o[nsh - 1] = bstage[nsh - 1];
-                } else {
-                    for (int t = lane; t < nsh; t += 32) o[t] = bstage[t];
-                }
-            }
-        }
-        __syncwarp();
+        bool done = false;
+        if (fast) done = fz_chain_fast<S, PC>(wofs, m);
+        if (!done) fz_chain_slow<S, PC>(wofs, m);
+        if (lane == 0) cx.blocks++;
+        fz_back_block<S, PC>(wofs, m);
         // ---- drop the consumed symbols from the buffer ------------------------------------------------
         const int left = nbuf - m;
         for (int base = 0; base < left; base += 32) {
@@ -707,82 +767,74 @@ static __device__ __noinline__ void fz_theta_fixup(float* th, const float2* sel,
     th[i] = atan2f(z.y, z.x);
 }
 
-// timing, part 1: exact sliding window sums of one chunk, lane = (phase wp, row group wg):
-// Eloc_i = sum of this group's rows' leading energies through row i minus the trailing energies
-// before row i (cpp/psk_soft.cpp:451, 576).  TC (padded layouts): rows i >= TC of the trailing
-// run sit behind one more pad.
-template <int S, int TC>
-__device__ __forceinline__ double fz_window_rows(const float* __restrict__ addp, const float* __restrict__ subp,
-                                                 int wg, double (&Eloc)[FzCfg<S>::R]) {
-    using C = FzCfg<S>;
-    constexpr int G = C::G, R = C::R;
-    double x = 0.0;
-#pragma unroll
-    for (int i = 0; i < R; i++) {
-        if (G * R == 32 || R * wg + i < 32) {
-            const float a = addp[i * S];
-            const float sb = subp[i * S + ((C::PADDED && i >= TC) ? C::PAD : 0)];
-            x = daddr(x, (double)a);
-            Eloc[i] = x;
-            x = dsubr(x, (double)sb);
-        } else Eloc[i] = 0.0;
-    }
-    return x;
-}
-template <int S>
-__device__ __forceinline__ double fz_window(const float* addp, const float* subp, int wg, int tc, double (&Eloc)[FzCfg<S>::R]) {
-    using C = FzCfg<S>;
-    if (!C::PADDED) return fz_window_rows<S, C::R>(addp, subp, wg, Eloc);
-    if (S == 8) {
-        switch (tc) {
-            case 1: return fz_window_rows<S, 1>(addp, subp, wg, Eloc);
-            case 2: return fz_window_rows<S, 2>(addp, subp, wg, Eloc);
-            case 3: return fz_window_rows<S, 3>(addp, subp, wg, Eloc);
-            case 4: return fz_window_rows<S, 4>(addp, subp, wg, Eloc);
-            case 5: return fz_window_rows<S, 5>(addp, subp, wg, Eloc);
-            case 6: return fz_window_rows<S, 6>(addp, subp, wg, Eloc);
-            case 7: return fz_window_rows<S, 7>(addp, subp, wg, Eloc);
-            default: return fz_window_rows<S, 8>(addp, subp, wg, Eloc);
-        }
-    }
-    // other padded layouts (S = 16): run-time carry
-    constexpr int G = C::G, R = C::R;
-    double x = 0.0;
-#pragma unroll
-    for (int i = 0; i < R; i++) {
-        if (G * R == 32 || R * wg + i < 32) {
-            const float a = addp[i * S];
-            const float sb = subp[i * S + ((i >= tc) ? C::PAD : 0)];
-            x = daddr(x, (double)a);
-            Eloc[i] = x;
-            x = dsubr(x, (double)sb);
-        } else Eloc[i] = 0.0;
-    }
-    return x;
-}
-
 __device__ __forceinline__ void fz_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------
+// staged blocks: 32 rows of raw samples in shared memory, sample n (= row*S + phase) at
+// FzCfg<S>::phys(n).  fz_issue copies a block that lies wholly inside this call's input with
+// cp.async (16-byte pieces when the block's global address allows it, else 8-byte pieces);
+// fz_fill_slow assembles a block that touches the carried tail or the end of the stream.
+// ---------------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void fz_issue(float2* st, const float2* src, int lane, bool a16) {
+    using C = FzCfg<S>;
+    if (a16) {
+        const float4* g4 = reinterpret_cast<const float4*>(src) + lane;
+        float4* d4 = reinterpret_cast<float4*>(st);
+#pragma unroll
+        for (int q = 0; q < C::NQ16; q++) {
+            const int f = lane + 32 * q;
+            if ((S * 16) % 32 == 0 || f < S * 16) {
+                const int fp = (S == 8) ? ((lane ^ ((q & 1) << 2)) + 32 * q) : f;      // phys() on 16-byte pieces
+                fz_cp_async16(d4 + fp, g4 + 32 * q);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < S; q++) {
+            const int n = lane + 32 * q;
+            const int np = (S == 8) ? ((lane ^ (((q >> 1) & 1) << 3)) + 32 * q) : n;
+            fz_cp_async8(st + np, src + n);
+        }
+    }
+}
+template <int S>
+__device__ __forceinline__ void fz_fill_slow(float2* st, long long s0, const FzCtx& cx, int lane) {
+    using C = FzCfg<S>;
+    const long long V = cx.V, tail_len = cx.tail_len;
+    const float2* tailp = cx.tail;
+    const float2* in_mt = cx.in_mt;
+#pragma unroll 2
+    for (int q = 0; q < S; q++) {
+        const int n = lane + 32 * q;
+        const long long v = s0 + n;
+        float2 x = make_float2(0.f, 0.f);
+        if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
+        st[C::phys(n)] = x;
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
-// fz_unit_begin: claim-independent set-up of one unit: geometry, wait for the predecessor unit,
-// carried state into shared memory, first packet prologue, ring priming.  Returns the number of
-// chunks (< 0: nothing to do for this ticket); the lane's carried window sum goes through ebuf[lane].
+// fz_unit_begin: set-up of one unit: geometry, wait for the predecessor unit, carried state into
+// shared memory, first packet prologue, the carried window sums.  Returns the number of chunks
+// (< 0: nothing to do for this ticket).
 // ---------------------------------------------------------------------------------------------
-template <int S, int RRC, int PC>
+template <int S, int PC>
 static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const unsigned wofs, const int u)
 {
     using C = FzCfg<S>;
-    using L = FzL<S, RRC, PC>;
-    constexpr int G = C::G, R = C::R, ES = C::ES;
-    constexpr int CHS = FZ_CH * S;
+    using L = FzL<S, PC>;
+    constexpr int G = C::G, ES = C::ES;
+    constexpr int CHS = C::CHS;
     unsigned char* wb = fz_smem + wofs;
-    float*  ring = reinterpret_cast<float*>(wb);
+    float2* Lst  = reinterpret_cast<float2*>(wb + L::OFF_L);
+    float2* Tst  = reinterpret_cast<float2*>(wb + L::OFF_T);
     float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
     double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);
     const int lane = threadIdx.x & 31;
     const bool wact = lane < G * S;
@@ -799,25 +851,31 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
     const long long tail_len = dgp->tail_len, pkt_len = dgp->pkt_len;
     const int K = (int)dgp->K;
     const long long V = tail_len + dgp->n_in;
-    const int lag = A - 1, RR = C::ring_rows(A);
+    const int lag = A - 1;
     const int kA = (int)first_symbol_at((long long)pk0 * pkt_len, tail_len, S, A, K);
     const int kB = (pk1 == n_pkts) ? K : (int)first_symbol_at((long long)pk1 * pkt_len, tail_len, S, A, K);
     const int nchunks = (kB - kA + FZ_CH - 1) / FZ_CH;
     const float2* in_mt = dgp->in - tail_len;
     const float2* tailp = dgp->tail;
-    // chunks [c_lo, c_hi) lie wholly inside `in` at a 16-byte aligned address: 128-bit loads
-    int c_lo = 0, c_hi = 0;
+    // chunks [c_lo, c_hi): trail block (rows kA+32c ..) and lead block (rows kA+32c+lag ..) both lie
+    // wholly inside `in` -> cp.async copies; 16-byte pieces if both blocks start 16-byte aligned
+    int c_lo = 0, c_hi = 0, a16 = 0;
     {
-        const long long sA0 = (long long)(kA + lag) * S;
-        if ((reinterpret_cast<uintptr_t>(in_mt + sA0) & 15) == 0) {
-            long long lo = (tail_len - sA0 + CHS - 1) / CHS;
-            if (lo < 0) lo = 0;
-            long long hi = (V - sA0) / CHS;                               // chunks fully below V
-            if (hi > nchunks) hi = nchunks;
-            if (lo < hi) { c_lo = (int)lo; c_hi = (int)hi; }
-        }
-        // start the stream: chunks 0 and 1 towards L2
-        if (lane == 0 && c_lo == 0 && c_hi > 0) fz_prefetch_l2(in_mt + sA0, (unsigned)min(2, c_hi) * CHS * 8);
+        const long long sT0 = (long long)kA * S, sL0 = (long long)(kA + lag) * S;
+        long long lo = (tail_len - sT0 + CHS - 1) / CHS;
+        if (lo < 0) lo = 0;
+        long long hi = (V - sL0) / CHS;                                   // lead blocks fully below V
+        if (hi > nchunks) hi = nchunks;
+        if (lo < hi) { c_lo = (int)lo; c_hi = (int)hi; }
+        a16 = (((reinterpret_cast<uintptr_t>(in_mt + sT0) | reinterpret_cast<uintptr_t>(in_mt + sL0)) & 15) == 0) ? 1 : 0;
+        // start the stream: the first two lead blocks towards L2
+        if (lane == 0 && c_lo < c_hi && a16)
+            fz_prefetch_l2(in_mt + sL0 + (long long)c_lo * CHS, (unsigned)min(2, c_hi - c_lo) * CHS * 8);
+    }
+    const bool pre0 = nchunks > 0 && c_lo == 0 && c_hi > 0;
+    if (pre0) {                                                           // chunk 0's blocks: input only, no dependence on the predecessor
+        fz_issue<S>(Tst, in_mt + (long long)kA * S, lane, a16 != 0);
+        fz_issue<S>(Lst, in_mt + (long long)(kA + lag) * S, lane, a16 != 0);
     }
     // ---- wait for the previous unit of this channel, then load its carried state ------------------
     if (ug > 0) {
@@ -844,50 +902,46 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
         cx.pkt = pk0; cx.kchain = kA; cx.nbuf = 0; cx.cz_valid = 0; cx.unit_done = 0;
         cx.fP1 = (float)(P - 1);
         cx.pk_hi = (pk0 + 1 == n_pkts) ? K : (int)first_symbol_at((long long)(pk0 + 1) * pkt_len, tail_len, S, A, K);
-        cx.kA = kA; cx.kB = kB; cx.lag = lag; cx.RR = RR; cx.NS = RR / 32;
-        cx.tc = C::PADDED ? ((lag % R) ? (lag % R) : R) : R;              // R - ((-lag) mod R)
-        cx.c_lo = c_lo; cx.c_hi = c_hi; cx.nchunks = nchunks;
-        cx.gather_in = ((long long)kA * S >= tail_len) ? 1 : 0;           // every gather of this unit falls into `in`
+        cx.kA = kA; cx.kB = kB; cx.lag = lag;
+        cx.c_lo = c_lo; cx.c_hi = c_hi; cx.nchunks = nchunks; cx.a16 = a16;
         cx.ch = ch; cx.ug = ug; cx.V = V;
+        cx.c = 0; cx.inflight = pre0 ? 1 : 0;
     }
     for (int j = lane; j < P; j += 32) yh[j] = __ldcg(gring + j);
     __syncwarp();
     if (lane == 0) { cx.wraps0 = cx.st.wraps; selb[1] = cx.st.last; fz_prologue(cx, yh); }
     __syncwarp();
 
-    // ---- prime the energy ring with rows [kA, kA+lag) and the carried window sum -------------------
-    double Cw = 0.0;               // lane (p, g): sum over the window of output k0 WITHOUT its newest row
+    // ---- carried window sums: rows [kA, kA+lag) per phase, exact double sums ------------------------
     if (nchunks > 0) {
         const long long s0 = (long long)kA * S;
-        for (int s = lane; s < lag * S; s += 32) {
-            const long long v = s0 + s;
-            float2 x = make_float2(0.f, 0.f);
-            if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
-            const int row = s / S, p = s - row * S;
-            ring[C::fpos(RR - lag + row) + p] = energy_f32(x.x, x.y);
+        double acc = 0.0;
+        if (wact) {
+            for (int i = wg; i < lag; i += G) {
+                const long long v = s0 + (long long)i * S + wp;
+                float2 x = make_float2(0.f, 0.f);
+                if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
+                acc = daddr(acc, (double)energy_f32(x.x, x.y));
+            }
+            ebuf[wg * ES + wp] = acc;
         }
         __syncwarp();
-        {
-            double acc = 0.0;
-            for (int i = wg; i < lag; i += G) acc = daddr(acc, (double)ring[C::fpos(RR - lag + i) + wp]);
-            if (wact) ebuf[wg * ES + wp] = acc;
-        }
-        __syncwarp();
+        if (lane < S) {
+            double Cw = 0.0;
 #pragma unroll
-        for (int g2 = 0; g2 < G; g2++) Cw = daddr(Cw, ebuf[g2 * ES + wp]);
+            for (int g2 = 0; g2 < G; g2++) Cw = daddr(Cw, ebuf[g2 * ES + lane]);
+            cwp[lane] = Cw;                    // sum over the window of output kA WITHOUT its newest row
+        }
         __syncwarp();
     }
-    reinterpret_cast<double*>(wb + L::OFF_CW)[lane] = Cw;
-    if (lane == 0) { cx.c = 0; cx.krow = kA; cx.slot = 0; cx.nprev = 0; }
-    __syncwarp();
     return nchunks;
 }
 
 // fz_unit_end: hand the channel's state to the next unit / the next call
-template <int S, int RRC, int PC>
+template <int S, int PC>
 static __device__ __noinline__ void fz_unit_end(const FusedParams& prm, const unsigned wofs)
 {
-    using L = FzL<S, RRC, PC>;
+    using L = FzL<S, PC>;
     unsigned char* wb = fz_smem + wofs;
     float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
@@ -916,102 +970,93 @@ static __device__ __noinline__ void fz_unit_end(const FusedParams& prm, const un
 }
 
 // ---------------------------------------------------------------------------------------------
-// fz_chunk: one iteration of the front stage (its own register allocation; all state in FzCtx):
-//   wait for the asynchronous copies; M-th power angle of the PREVIOUS chunk's gathered samples
-//   (appended to the block buffer); energies of this chunk's 32 newest rows into the ring; issue
-//   the next chunk's copy; exact sliding window sums; first maximum per row; issue the gather.
-// Global loads are cp.async copies into shared memory, so nothing is held in registers between
-// the stages: chunk c+1's samples are issued once chunk c's have been consumed, the gathered
-// samples of chunk c at its end; both are waited for at the top of iteration c+1.
+// fz_chunk: the front stage (its own register allocation; state in FzCtx between calls).  Runs
+// chunks until the block buffer holds what the chain stage wants (or the unit's chunks are
+// exhausted).  One chunk:
+//   wait for the two staged blocks; window sums (lane = phase x row group) from the energies of
+//   the lead and trail samples; scan over the row groups; transpose; issue the next lead block;
+//   first maximum per row (lane = row); pick the selected sample out of the trail block; issue the
+//   next trail block; M-th power angle; append (theta, sample) to the block buffer.
 // ---------------------------------------------------------------------------------------------
-template <int S, int RRC, int PC>
+template <int S, int PC>
 static __device__ __noinline__ void fz_chunk(const unsigned wofs)
 {
     using C = FzCfg<S>;
-    using L = FzL<S, RRC, PC>;
-    constexpr int G = C::G, R = C::R, ES = C::ES, NQ = C::NQ;
-    constexpr int CHS = FZ_CH * S;                       // samples per chunk
+    using L = FzL<S, PC>;
+    constexpr int G = C::G, R = C::R, ES = C::ES;
+    constexpr int CHS = C::CHS;
     unsigned char* wb = fz_smem + wofs;
-    float*  ring = reinterpret_cast<float*>(wb);
+    float2* Lst  = reinterpret_cast<float2*>(wb + L::OFF_L);
+    float2* Tst  = reinterpret_cast<float2*>(wb + L::OFF_T);
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
     float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
     double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);       // [32][ES] window sums
     const int lane = threadIdx.x & 31;
-    float4* rawq = reinterpret_cast<float4*>(wb + L::OFF_RAW) + lane;
-    float2* gland = reinterpret_cast<float2*>(wb + L::OFF_GL) + lane;
-    double* cwl = reinterpret_cast<double*>(wb + L::OFF_CW) + lane;
+    const bool wact = lane < G * S;
+    const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
 
-    const int c = cx.c, krow = cx.krow, slot = cx.slot, nprev = cx.nprev;
-    const int c_lo = cx.c_lo, c_hi = cx.c_hi, lag = cx.lag;
+    int c = cx.c, nbuf = cx.nbuf;
+    bool inflight = cx.inflight != 0;
+    const int nchunks = cx.nchunks, c_lo = cx.c_lo, c_hi = cx.c_hi, lag = cx.lag;
+    const int kA = cx.kA, kB = cx.kB, M = cx.M;
+    const int want = min(FZ_B, cx.pk_hi - cx.kchain);
+    const bool a16 = cx.a16 != 0;
+    const bool m_ok = (M == 2 || M == 4 || M == 8);
     const float2* in_mt = cx.in_mt;
-    const int M = cx.M;
-    const bool have = c < cx.nchunks;
-    const bool fastc = have && c >= c_lo && c < c_hi;
+    int16_t* o_sidx = cx.o_sidx;
+    double Cw = cwp[wp];
+    // lane = (phase, group): where this lane's rows sit in a staged block (even / odd rows, see phys())
+    const int od = (S == 8) ? (wg & 1) : 0;
+    const int ofs_e = (R * wg + od) * S + wp, ofs_o = (R * wg - od) * S + wp;
+    // lane = row: where this lane's row sits in the trail block
+    const int rowp = (S == 8) ? (lane ^ ((lane >> 3) & 1)) * S : lane * S;
 
-    fz_cp_async_wait_all();
-#ifndef PSKD_FZ_NO_STEADY
-    // ---- steady state: full previous chunk, full fast chunk, M in {2,4,8}.  Same work as the general
-    // path below, without lane predicates, so that the angle computation, the energies and the shared-
-    // memory traffic of the stages sit in few large basic blocks and overlap in the instruction stream.
-    if (fastc && nprev == FZ_CH && cx.kB - krow >= FZ_CH && (M == 2 || M == 4 || M == 8)) {
-        const int RR = cx.RR;
-        float* slotp = ring + C::fpos(32 * slot);
-        const int nb0 = cx.nbuf;
-        const float2 gx = *gland;
-        float4 xr[NQ];
-#pragma unroll
-        for (int q = 0; q < NQ; q++)
-            if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) xr[q] = rawq[32 * q];
-        bool bad = false;
-        const float thv = fz_theta(gx, M, bad);
-#pragma unroll
-        for (int q = 0; q < NQ; q++) {
-            const int f = lane + 32 * q;
-            if ((S * 16) % 32 == 0 || f < S * 16) {
-                const int s = 2 * f;
-                const int off = s + (C::PADDED ? ((s / S) / R) * C::PAD : 0);
-                const float2 e = make_float2(energy_f32(xr[q].x, xr[q].y), energy_f32(xr[q].z, xr[q].w));
-                if (S % 2 == 0) {
-                    *reinterpret_cast<float2*>(slotp + off) = e;
-                    if (slot == 0 && s < R * S) *reinterpret_cast<float2*>(ring + C::fpos(RR) + s) = e;
-                } else {
-                    slotp[s] = e.x; slotp[s + 1] = e.y;
-                    if (slot == 0) {
-                        if (s < R * S) ring[C::fpos(RR) + s] = e.x;
-                        if (s + 1 < R * S) ring[C::fpos(RR) + s + 1] = e.y;
-                    }
-                }
+    do {
+        const int krow = kA + FZ_CH * c;
+        if (!inflight) {
+            if (c >= c_lo && c < c_hi) {
+                fz_issue<S>(Tst, in_mt + (long long)krow * S, lane, a16);
+                fz_issue<S>(Lst, in_mt + (long long)(krow + lag) * S, lane, a16);
+            } else {
+                fz_fill_slow<S>(Tst, (long long)krow * S, cx, lane);
+                fz_fill_slow<S>(Lst, (long long)(krow + lag) * S, cx, lane);
             }
         }
-        th[nb0 + lane] = thv;
-        selb[2 + nb0 + lane] = gx;
+        fz_cp_async_wait_all();
         __syncwarp();
-        if (c + 1 < c_hi) {                            // next chunk -> raw staging (own words only: no hazard)
-            const float4* g4 = reinterpret_cast<const float4*>(in_mt + (long long)(krow + FZ_CH + lag) * S) + lane;
+
+        // ---- timing, part 1: exact sliding window sums (:451, :576), lane = (phase wp, row group wg);
+        // lanes beyond G*S (S = 9, 10) run along on (0, 0) and store nothing
+        double Eloc[R];
+        double x = 0.0;
+        {
+            const float2* le = Lst + ofs_e; const float2* lo = Lst + ofs_o;
+            const float2* te = Tst + ofs_e; const float2* to = Tst + ofs_o;
 #pragma unroll
-            for (int q = 0; q < NQ; q++)
-                if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) fz_cp_async16(rawq + 32 * q, g4 + 32 * q);
-            if (c + 2 < c_hi && lane * 8 < CHS / 2) fz_prefetch_line(g4 - lane + (CHS / 2) + lane * 8);
+            for (int i = 0; i < R; i++) {
+                if (G * R == 32 || R * wg + i < 32) {
+                    const float2 a = (i & 1) ? lo[i * S] : le[i * S];
+                    const float2 b = (i & 1) ? to[i * S] : te[i * S];
+                    x = daddr(x, (double)energy_f32(a.x, a.y));          // :448-451
+                    Eloc[i] = x;
+                    x = dsubr(x, (double)energy_f32(b.x, b.y));          // :576
+                } else Eloc[i] = 0.0;
+            }
         }
         {
-            const bool wact = lane < G * S;
-            const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
-            const float* addp = slotp + (C::PADDED ? wg * (R * S + C::PAD) : wg * R * S) + wp;
-            int P0 = 32 * slot + R * wg - lag;
-            if (P0 < 0) P0 += RR;
-            const float* subp = ring + C::fpos(P0) + wp;
-            double Eloc[R];
-            const double x = fz_window<S>(addp, subp, wg, cx.tc, Eloc);
-            const double Cw = *cwl;
-            double off = Cw, tot = 0.0;
+            // scan of the group totals over the row groups (all partial sums exact)
+            double incl = x;
 #pragma unroll
-            for (int g2 = 0; g2 < G; g2++) {
-                const double tg = __shfl_sync(0xffffffffu, x, g2 * S + wp, 32);
-                if (g2 < wg) off = daddr(off, tg);
-                tot = daddr(tot, tg);
+            for (int d = 1; d < G; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, incl, d * S, 32);
+                if (wg >= d) incl = daddr(incl, t);
             }
-            *cwl = daddr(Cw, tot);
+            const double ex = __shfl_up_sync(0xffffffffu, incl, S, 32);
+            const double tot = __shfl_sync(0xffffffffu, incl, (G - 1) * S + wp, 32);
+            const double off = (wg >= 1) ? daddr(Cw, ex) : Cw;
+            Cw = daddr(Cw, tot);
             if (wact) {
                 double* eo = ebuf + (R * wg) * ES + wp;
 #pragma unroll
@@ -1020,143 +1065,13 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
             }
         }
         __syncwarp();
-        {
-            const double* er = ebuf + lane * ES;
-            double e[S];
-#pragma unroll
-            for (int q = 0; q < S; q++) e[q] = er[q];
-            int ix[S];
-#pragma unroll
-            for (int q = 0; q < S; q++) ix[q] = q;
-#pragma unroll
-            for (int lv = 0; lv < 5; lv++) {
-                const int w = 1 << lv;
-#pragma unroll
-                for (int q = 0; q < S; q++) {
-                    if (w < S && (q % (2 * w)) == 0 && q + w < S) {
-                        if (e[q] < e[q + w]) { e[q] = e[q + w]; ix[q] = ix[q + w]; }
-                    }
-                }
-            }
-            const int idx = ix[0];
-            int16_t* o_sidx = cx.o_sidx;
-            if (o_sidx) __stcs(o_sidx + krow + lane, (int16_t)idx);                        // :466
-            const long long v = (long long)(krow + lane) * S + idx;
-            const float2* src = (cx.gather_in || v >= cx.tail_len) ? in_mt + v : cx.tail + v;
-            fz_cp_async8(gland, src);
-        }
-        if (lane == 0) {
-            int ns = slot + 1;
-            if (ns == cx.NS) ns = 0;
-            cx.nbuf = nb0 + FZ_CH;
-            cx.c = c + 1; cx.krow = krow + FZ_CH; cx.slot = ns;       // nprev stays FZ_CH
-        }
-        __syncwarp();
-        if (__any_sync(0xffffffffu, bad)) {            // rare: literal angle for odd inputs
-            if (bad) fz_theta_fixup(th, selb + 2, nb0 + lane, (unsigned)M);
-            __syncwarp();
-        }
-        return;
-    }
-#endif
-    // M-th power angle (:474) of the PREVIOUS chunk's samples
-    bool th_bad = false;
-    int th_at = 0;
-    if (nprev > 0) {
-        const int nb0 = cx.nbuf;
-        th_at = nb0 + lane;
-        if (lane < nprev) {
-            const float2 gx = *gland;
-            th[th_at] = fz_theta(gx, M, th_bad);
-            th_bad = th_bad || !(M == 2 || M == 4 || M == 8);          // other M: literal angle path
-            selb[2 + th_at] = gx;
-        }
-        __syncwarp();
-        if (lane == 0) cx.nbuf = nb0 + nprev;
-    }
-    int nrows = 0;
-    if (have) {
-        const int RR = cx.RR;
-        float* slotp = ring + C::fpos(32 * slot);
-        // ingest: energies of the chunk's 32 newest rows (the windows' leading edge, :448-451)
-        if (fastc) {
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                const int f = lane + 32 * q;
-                if ((S * 16) % 32 == 0 || f < S * 16) {
-                    const float4 x = rawq[32 * q];
-                    const int s = 2 * f;
-                    const int off = s + (C::PADDED ? ((s / S) / R) * C::PAD : 0);
-                    const float2 e = make_float2(energy_f32(x.x, x.y), energy_f32(x.z, x.w));
-                    if (S % 2 == 0) {
-                        *reinterpret_cast<float2*>(slotp + off) = e;
-                        if (slot == 0 && s < R * S) *reinterpret_cast<float2*>(ring + C::fpos(RR) + s) = e;
-                    } else {
-                        slotp[s] = e.x; slotp[s + 1] = e.y;
-                        if (slot == 0) {
-                            if (s < R * S) ring[C::fpos(RR) + s] = e.x;
-                            if (s + 1 < R * S) ring[C::fpos(RR) + s + 1] = e.y;
-                        }
-                    }
-                }
-            }
-        } else {
-            const long long sA = (long long)(krow + lag) * S;
-            const long long V = cx.V, tail_len = cx.tail_len;
-            const float2* tailp = cx.tail;
-            for (int s = lane; s < CHS; s += 32) {
-                const long long v = sA + s;
-                float2 x = make_float2(0.f, 0.f);
-                if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
-                const int row = s / S, p = s - row * S;
-                const float e = energy_f32(x.x, x.y);
-                ring[C::fpos(32 * slot + row) + p] = e;
-                if (slot == 0 && row < R) ring[C::fpos(RR + row) + p] = e;
-            }
-        }
-        __syncwarp();
-        if (c + 1 >= c_lo && c + 1 < c_hi) {           // next chunk -> raw staging (own words only: no hazard)
-            const float4* g4 = reinterpret_cast<const float4*>(in_mt + (long long)(krow + FZ_CH + lag) * S) + lane;
-#pragma unroll
-            for (int q = 0; q < NQ; q++)
-                if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) fz_cp_async16(rawq + 32 * q, g4 + 32 * q);
-            // and the chunk after it towards L2, one 128-byte line per lane
-            if (c + 2 < c_hi && lane * 8 < CHS / 2) fz_prefetch_line(g4 - lane + (CHS / 2) + lane * 8);
-        }
+        const bool nfast = (c + 1 >= c_lo) && (c + 1 < c_hi);
+        if (nfast) fz_issue<S>(Lst, in_mt + (long long)(krow + FZ_CH + lag) * S, lane, a16);
 
-        // timing, part 1: exact sliding window sums, lane = (phase wp, row group wg); lanes beyond
-        // G*S (S = 9, 10) run along on (0, 0) and store nothing
+        // ---- timing, part 2: lane = row: first maximum (:462), the selected sample (:465) ------------
+        const int nrows = min(FZ_CH, kB - krow);
+        float2 gx;
         {
-            const bool wact = lane < G * S;
-            const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
-            const float* addp = slotp + (C::PADDED ? wg * (R * S + C::PAD) : wg * R * S) + wp;
-            int P0 = 32 * slot + R * wg - lag;
-            if (P0 < 0) P0 += RR;
-            const float* subp = ring + C::fpos(P0) + wp;
-            double Eloc[R];
-            const double x = fz_window<S>(addp, subp, wg, cx.tc, Eloc);
-            // exclusive scan of the group totals over the row groups
-            const double Cw = *cwl;
-            double off = Cw, tot = 0.0;
-#pragma unroll
-            for (int g2 = 0; g2 < G; g2++) {
-                const double tg = __shfl_sync(0xffffffffu, x, g2 * S + wp, 32);
-                if (g2 < wg) off = daddr(off, tg);
-                tot = daddr(tot, tg);
-            }
-            *cwl = daddr(Cw, tot);
-            if (wact) {
-                double* eo = ebuf + (R * wg) * ES + wp;
-#pragma unroll
-                for (int i = 0; i < R; i++)
-                    if (G * R == 32 || R * wg + i < 32) eo[i * ES] = daddr(off, Eloc[i]);
-            }
-        }
-        __syncwarp();
-
-        // timing, part 2: lane = row: first maximum (:462), issue the gather (:465)
-        nrows = min(FZ_CH, cx.kB - krow);
-        if (lane < nrows) {
             const double* er = ebuf + lane * ES;
             double e[S];
 #pragma unroll
@@ -1176,33 +1091,45 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
                 }
             }
             const int idx = ix[0];
-            int16_t* o_sidx = cx.o_sidx;
-            if (o_sidx) __stcs(o_sidx + krow + lane, (int16_t)idx);                    // :466
-            const long long v = (long long)(krow + lane) * S + idx;
-            const float2* src = (cx.gather_in || v >= cx.tail_len) ? in_mt + v : cx.tail + v;
-            fz_cp_async8(gland, src);
+            if (o_sidx && lane < nrows) __stcs(o_sidx + krow + lane, (int16_t)idx);        // :466
+            gx = Tst[rowp + idx];
         }
-    }
-    if (lane == 0) {
-        int ns = slot + (have ? 1 : 0);
-        if (ns == cx.NS) ns = 0;
-        cx.c = c + 1; cx.krow = krow + FZ_CH; cx.slot = ns; cx.nprev = nrows;
-    }
-    __syncwarp();
-    if (__any_sync(0xffffffffu, th_bad)) {          // rare: literal angle for odd inputs
-        if (th_bad) fz_theta_fixup(th, selb + 2, th_at, (unsigned)M);
         __syncwarp();
-    }
+        if (nfast) {
+            fz_issue<S>(Tst, in_mt + (long long)(krow + FZ_CH) * S, lane, a16);
+            // and the lead block after the next towards L2, one 128-byte line per lane
+            if (c + 2 < c_hi && lane * 16 < CHS)
+                fz_prefetch_line(in_mt + (long long)(krow + 2 * FZ_CH + lag) * S + lane * 16);
+        }
+        inflight = nfast;
+
+        // ---- M-th power angle (:474), append to the block buffer ---------------------------------------
+        bool bad = false;
+        const float thv = fz_theta(gx, M, bad);
+        bad = (bad || !m_ok) && lane < nrows;
+        if (lane < nrows) {
+            th[nbuf + lane] = thv;
+            selb[2 + nbuf + lane] = gx;
+        }
+        if (__any_sync(0xffffffffu, bad)) {            // rare: literal angle for odd inputs / other M
+            __syncwarp();
+            if (bad) fz_theta_fixup(th, selb + 2, nbuf + lane, (unsigned)M);
+        }
+        nbuf += nrows;
+        c++;
+    } while (c < nchunks && nbuf < want);
+    __syncwarp();
+    if (lane == 0) { cx.c = c; cx.nbuf = nbuf; cx.inflight = inflight ? 1 : 0; }
+    if (lane < S) cwp[lane] = Cw;
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int S, int RRC, int PC>
+template <int S, int PC>
 __global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZ_MIN_CTAS)
 k_fused(const FusedParams prm)
 {
-    using C = FzCfg<S>;
-    using L = FzL<S, RRC, PC>;
-    constexpr int NQ = C::NQ;
+    using L = FzL<S, PC>;
     const int lane = threadIdx.x & 31;
     const unsigned wofs = (threadIdx.x >> 5) * (unsigned)L::BYTES;
     FzCtx& cx = *reinterpret_cast<FzCtx*>(fz_smem + wofs + L::OFF_CTX);
@@ -1212,30 +1139,23 @@ k_fused(const FusedParams prm)
         if (lane == 0) u = atomicAdd(prm.ticket, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= prm.n_units) break;
-        const int nchunks = fz_unit_begin<S, RRC, PC>(prm, wofs, u);
+        const int nchunks = fz_unit_begin<S, PC>(prm, wofs, u);
         if (nchunks < 0) continue;
-        fz_drain<S, RRC, PC>(wofs);    // packets without symbols before the first chunk (and units without any symbol)
-        if (nchunks > 0 && cx.c_lo == 0 && cx.c_hi > 0) {              // chunk 0 -> raw staging
-            float4* rawq = reinterpret_cast<float4*>(fz_smem + wofs + L::OFF_RAW) + lane;
-            const float4* g4 = reinterpret_cast<const float4*>(cx.in_mt + (long long)(cx.kA + cx.lag) * S) + lane;
-#pragma unroll
-            for (int q = 0; q < NQ; q++)
-                if ((S * 16) % 32 == 0 || lane + 32 * q < S * 16) fz_cp_async16(rawq + 32 * q, g4 + 32 * q);
+        fz_drain<S, PC>(wofs);         // packets without symbols before the first chunk (and units without any symbol)
+        while (cx.c < nchunks) {
+            fz_chunk<S, PC>(wofs);
+            fz_drain<S, PC>(wofs);
         }
-        for (int c = 0; c <= nchunks; c++) {
-            fz_chunk<S, RRC, PC>(wofs);
-            if (cx.nbuf >= min(FZ_B, cx.pk_hi - cx.kchain)) fz_drain<S, RRC, PC>(wofs);
-        }
-        fz_unit_end<S, RRC, PC>(prm, wofs);
+        fz_unit_end<S, PC>(prm, wofs);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int S, int RRC, int PC>
+template <int S, int PC>
 static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
-    using L = FzL<S, RRC, PC>;
+    using L = FzL<S, PC>;
     FusedParams p{};
     p.desc = c.d_desc; p.state = c.d_state; p.ring_base = c.d_ring;
     p.list = f.d_list; p.n_list = f.n_list;
@@ -1250,11 +1170,11 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     static int ctas_per_sm = 0, n_sm = 0;
     cudaError_t e;
     if (ctas_per_sm == 0) {
-        e = cudaFuncSetAttribute(k_fused<S, RRC, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_fused<S, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_fused<S, RRC, PC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(k_fused<S, PC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fused<S, RRC, PC>, FZ_WARPS * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fused<S, PC>, FZ_WARPS * 32, smem);
         if (e != cudaSuccess) return e;
         if (ctas_per_sm < 1) { ctas_per_sm = 0; return cudaErrorInvalidConfiguration; }
         int dev = 0;
@@ -1266,7 +1186,7 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     c.prof->begin(KID_FUSED, c.stream);
-    k_fused<S, RRC, PC><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
+    k_fused<S, PC><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
     c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
@@ -1279,16 +1199,17 @@ bool fused_supports(int S, int A, int P) {
     return true;
 }
 
-// two shared-memory size classes: the component's defaults and below (numAvg <= 129, phaseAvg <= 52:
-// 5 CTAs of 4 warps per SM at S = 8) and everything up to FUSED_AMAX / FUSED_PMAX
+// two shared-memory size classes: phaseAvg <= 52 (the component's default and below: 9.3 KB per warp at
+// S = 8, six CTAs of four warps per SM) and everything up to FUSED_PMAX.  numAvg does not enter: the
+// kernel keeps no energy ring (FUSED_AMAX only bounds how far behind the trail block is re-read).
 cudaError_t launch_fused(const LaunchCtx& c, const FusedLaunch& f) {
     if (f.n_list == 0) return cudaSuccess;
-    const bool small = f.Amax <= 129 && f.Pmax <= 52;
+    const bool small = f.Pmax <= 52;
     switch (f.S) {
-        case 8:  return small ? launch_fused_t<8, 160, 52>(c, f) : launch_fused_t<8, 288, 128>(c, f);
-        case 9:  return small ? launch_fused_t<9, 160, 52>(c, f) : launch_fused_t<9, 288, 128>(c, f);
-        case 10: return small ? launch_fused_t<10, 160, 52>(c, f) : launch_fused_t<10, 288, 128>(c, f);
-        case 16: return launch_fused_t<16, 288, 128>(c, f);
+        case 8:  return small ? launch_fused_t<8, 52>(c, f) : launch_fused_t<8, 128>(c, f);
+        case 9:  return small ? launch_fused_t<9, 52>(c, f) : launch_fused_t<9, 128>(c, f);
+        case 10: return small ? launch_fused_t<10, 52>(c, f) : launch_fused_t<10, 128>(c, f);
+        case 16: return launch_fused_t<16, 128>(c, f);
     }
     return cudaErrorInvalidValue;
 }
