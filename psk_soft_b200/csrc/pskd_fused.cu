@@ -364,6 +364,42 @@ __device__ __forceinline__ unsigned fz_back4(const float2 (&sv)[4], float2 sprev
     return badmask;
 }
 
+// The same stage as a ROLLED loop over the lane's four symbols (inputs and outputs go through shared
+// memory, the bits through a packed accumulator).  The block's code is executed once per 128 symbols,
+// so its cost is dominated by instruction fetch (the L0 instruction cache holds ~380 instructions and is
+// shared by the warps of a scheduler): four trips through ~70 instructions beat one trip through ~250.
+template <int BPB, bool DIFF>
+__device__ __forceinline__ unsigned fz_back_rolled(const float2* selb, const float* th, float2* cst, int i0, int M, unsigned& bits) {
+    const float inv_m = 1.0f / (float)M;
+    unsigned badmask = (BPB == 0 && (M & (M - 1)) != 0) ? 0xfu : 0u;       // -est/M not an exact multiply
+    unsigned acc = 0;
+#pragma unroll 1
+    for (int v = 0; v < 4; v++) {
+        const int i = i0 + v;
+        bool bad = false;
+        float2 s = selb[2 + i];
+        float pc = 0.0f;
+        if (DIFF) s = fz_cdiv_fast(s, selb[1 + i], bad);                                          // :488
+        else pc = fmulr(-th[i], inv_m);                                                           // :494 (exact for M = 2^n)
+        if (BPB == 2) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                     // :497-498
+        float sn, cs;
+        fz_sincos(pc, sn, cs, bad);                                                               // :499
+        const float x = fsubr(fmulr(s.x, cs), fmulr(s.y, sn));                                    // :500-501, unfused
+        const float y = faddr(fmulr(s.x, sn), fmulr(s.y, cs));
+        bad = bad || (isnan(x) && isnan(y));                                                      // __mulsc3 recovery
+        const float2 c = make_float2(x, y);
+        cst[i] = c;
+        unsigned b = 0;
+        if (BPB == 3) b = fz_slice8_flag(c, bad);
+        else if (BPB == 1) b = (x < 0.0f) ? 1u : 0u;
+        else if (BPB == 2) b = ((x != 0.0f) != (y != 0.0f) ? 1u : 0u) | ((y != 0.0f) ? 0u : 2u);   // :523-526 (float -> bool, sic)
+        acc |= b << (4 * v);
+        badmask |= bad ? (1u << v) : 0u;
+    }
+    bits = acc;
+    return badmask;
+}
+
 // ---------------------------------------------------------------------------------------------
 // The chain + back stage runs as three non-inlined functions (own register allocations, compact
 // code): fz_drain (packet bookkeeping, block sizing, buffer compaction) calls, per block of up to
@@ -523,8 +559,9 @@ static __device__ __noinline__ bool fz_chain_fast(const unsigned wofs, const int
 }
 
 // back stage of one block of m symbols at buffer offset 0: derotate / differential decode / slice
-// (cpp/psk_soft.cpp:484-566) from selb[] (samples) and th[] (estimates), then the coalesced stores
-// of phase / soft / bits for symbols [kchain, kchain + m).
+// (cpp/psk_soft.cpp:484-566) from selb[] (samples) and th[] (estimates) into the staging buffers
+// (soft, bits: the chain's buffers are dead by now), then the coalesced stores of phase / soft /
+// bits for symbols [kchain, kchain + m).
 template <int S, int PC>
 static __device__ __noinline__ void fz_back_block(const unsigned wofs, const int m)
 {
@@ -533,77 +570,55 @@ static __device__ __noinline__ void fz_back_block(const unsigned wofs, const int
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
     float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
-    short* bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS);            // chain buffers are dead now
+    float2* cst  = reinterpret_cast<float2*>(wb + L::OFF_ALIAS);              // soft staging [FZ_B]
+    short* bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS + FZ_B * 8);   // bits staging [FZ_B * 3]
     const int lane = fz_lane();
     const int M = cx.M, bpb = cx.bpb, kchain = cx.kchain;
     const bool diff = cx.diff != 0;
     const int i0 = lane * 4;
-    float2 sv[4];
-    float el[4];
-    {
-        const float4 a = *reinterpret_cast<const float4*>(selb + 2 + i0);
-        const float4 b = *reinterpret_cast<const float4*>(selb + 4 + i0);
-        const float4 e4 = *reinterpret_cast<const float4*>(th + i0);
-        sv[0] = make_float2(a.x, a.y); sv[1] = make_float2(a.z, a.w);
-        sv[2] = make_float2(b.x, b.y); sv[3] = make_float2(b.z, b.w);
-        el[0] = e4.x; el[1] = e4.y; el[2] = e4.z; el[3] = e4.w;
+    unsigned bits = 0, fixmask;
+    switch (bpb * 2 + (diff ? 1 : 0)) {
+        case 6: fixmask = fz_back_rolled<3, false>(selb, th, cst, i0, M, bits); break;
+        case 7: fixmask = fz_back_rolled<3, true>(selb, th, cst, i0, M, bits); break;
+        case 4: fixmask = fz_back_rolled<2, false>(selb, th, cst, i0, M, bits); break;
+        case 5: fixmask = fz_back_rolled<2, true>(selb, th, cst, i0, M, bits); break;
+        case 2: fixmask = fz_back_rolled<1, false>(selb, th, cst, i0, M, bits); break;
+        case 3: fixmask = fz_back_rolled<1, true>(selb, th, cst, i0, M, bits); break;
+        case 0: fixmask = fz_back_rolled<0, false>(selb, th, cst, i0, M, bits); break;
+        default: fixmask = fz_back_rolled<0, true>(selb, th, cst, i0, M, bits); break;
     }
-    const float2 sprev = selb[1 + i0];
-    __syncwarp();
-    unsigned bsym[4];
-    unsigned fixmask = 0;
-    {
-        float2 cv[4];
-        unsigned badmask;
-        switch (bpb * 2 + (diff ? 1 : 0)) {
-            case 6: badmask = fz_back4<3, false>(sv, sprev, el, M, cv, bsym); break;
-            case 7: badmask = fz_back4<3, true>(sv, sprev, el, M, cv, bsym); break;
-            case 4: badmask = fz_back4<2, false>(sv, sprev, el, M, cv, bsym); break;
-            case 5: badmask = fz_back4<2, true>(sv, sprev, el, M, cv, bsym); break;
-            case 2: badmask = fz_back4<1, false>(sv, sprev, el, M, cv, bsym); break;
-            case 3: badmask = fz_back4<1, true>(sv, sprev, el, M, cv, bsym); break;
-            case 0: badmask = fz_back4<0, false>(sv, sprev, el, M, cv, bsym); break;
-            default: badmask = fz_back4<0, true>(sv, sprev, el, M, cv, bsym); break;
-        }
-        if (i0 + 3 < m) {
-            *reinterpret_cast<float4*>(selb + 2 + i0) = make_float4(cv[0].x, cv[0].y, cv[1].x, cv[1].y);
-            *reinterpret_cast<float4*>(selb + 4 + i0) = make_float4(cv[2].x, cv[2].y, cv[3].x, cv[3].y);
-        } else if (i0 < m) {
 #pragma unroll
-            for (int v = 0; v < 3; v++) if (i0 + v < m) selb[2 + i0 + v] = cv[v];
-        }
-#pragma unroll
-        for (int v = 0; v < 4; v++) if (i0 + v >= m) badmask &= ~(1u << v);
-        fixmask = badmask;
-    }
+    for (int v = 0; v < 4; v++) if (i0 + v >= m) fixmask &= ~(1u << v);
     int16_t* o_bits = cx.o_bits;
     if (bpb > 0 && o_bits) {
+        const unsigned bsym[4] = {bits & 7u, (bits >> 4) & 7u, (bits >> 8) & 7u, (bits >> 12) & 7u};
         unsigned* dst = reinterpret_cast<unsigned*>(bstage) + lane * 2 * bpb;
         if (bpb == 3) fz_store_bits<3>(dst, bsym);
         else if (bpb == 2) fz_store_bits<2>(dst, bsym);
         else fz_store_bits<1>(dst, bsym);
     }
     if (__any_sync(0xffffffffu, fixmask != 0)) {            // rare: literal evaluation of the flagged symbols
-#pragma unroll
         for (int v = 0; v < 4; v++) {
             if ((fixmask >> v) & 1u)
-                fz_back_literal(sv[v], (v == 0) ? sprev : sv[(v + 3) & 3], el[v], M, bpb, diff ? 1 : 0,
-                                selb + 2 + i0 + v, bstage + (i0 + v) * bpb);
+                fz_back_literal(selb[2 + i0 + v], selb[1 + i0 + v], th[i0 + v], M, bpb, diff ? 1 : 0,
+                                cst + i0 + v, bstage + (i0 + v) * bpb);
         }
     }
     __syncwarp();
     {
         float* o_phase = cx.o_phase;
         if (o_phase) {
-            float* o = o_phase + kchain;
-#pragma unroll
-            for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, th[i]); }
+            float* o = o_phase + kchain + lane;
+            const float* si = th + lane;
+#pragma unroll 1
+            for (int i = lane; i < m; i += 32, o += 32, si += 32) __stcs(o, *si);
         }
         float2* o_soft = cx.o_soft;
         if (o_soft) {
-            float2* o = o_soft + kchain;
-#pragma unroll
-            for (int q = 0; q < 4; q++) { const int i = lane + 32 * q; if (i < m) __stcs(o + i, selb[2 + i]); }
+            float2* o = o_soft + kchain + lane;
+            const float2* si = cst + lane;
+#pragma unroll 1
+            for (int i = lane; i < m; i += 32, o += 32, si += 32) __stcs(o, *si);
         }
         if (bpb > 0 && o_bits) {
             int16_t* o = o_bits + (long long)kchain * bpb;
@@ -612,8 +627,8 @@ static __device__ __noinline__ void fz_back_block(const unsigned wofs, const int
                 const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage) + lane;
                 unsigned* o32 = reinterpret_cast<unsigned*>(o) + lane;
                 const int nw = nsh >> 1;                  // <= 192 words
-#pragma unroll
-                for (int q = 0; q < 6; q++) if (lane + 32 * q < nw) __stcs(o32 + 32 * q, s32[32 * q]);
+#pragma unroll 1
+                for (int i = lane; i < nw; i += 32, o32 += 32, s32 += 32) __stcs(o32, *s32);
                 if ((nsh & 1) && lane == 0) o[nsh - 1] = bstage[nsh - 1];
             } else {
                 for (int t = lane; t < nsh; t += 32) o[t] = bstage[t];
