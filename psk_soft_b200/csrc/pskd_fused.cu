@@ -445,7 +445,11 @@ static __device__ __noinline__ bool fz_chain_fast(const unsigned wofs, const int
         for (int v = 0; v < 4; v++) {
             const float pv = (v == 0) ? tprev : tl[v - 1];
             int dn = -__float2int_rn((tl[v] - pv) * 0.15915494309189535f);
-            if (v == 0 && lane == 0) dn = fz_unwrap_count_slow(cx.st.est, tl[0]);
+            if (v == 0 && lane == 0) {                                         // :477 against the carried estimate
+                bool knife = false;
+                dn = fz_unwrap_count(cx.st.est, tl[0], knife);
+                if (knife) dn = fz_unwrap_count_slow(cx.st.est, tl[0]);
+            }
             run += dn; nloc[v] = run;
         }
         const int off = warp_scan_int(run, lane) - run;
@@ -792,10 +796,10 @@ __device__ __forceinline__ void fz_prefetch_l2(const void* p, unsigned bytes) {
 // cp.async (16-byte pieces when the block's global address allows it, else 8-byte pieces);
 // fz_fill_slow assembles a block that touches the carried tail or the end of the stream.
 // ---------------------------------------------------------------------------------------------
-template <int S>
-__device__ __forceinline__ void fz_issue(float2* st, const float2* src, int lane, bool a16) {
+template <int S, bool A16>
+__device__ __forceinline__ void fz_issue(float2* st, const float2* src, int lane) {
     using C = FzCfg<S>;
-    if (a16) {
+    if (A16) {
         const float4* g4 = reinterpret_cast<const float4*>(src) + lane;
         float4* d4 = reinterpret_cast<float4*>(st);
 #pragma unroll
@@ -889,8 +893,13 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
     }
     const bool pre0 = nchunks > 0 && c_lo == 0 && c_hi > 0;
     if (pre0) {                                                           // chunk 0's blocks: input only, no dependence on the predecessor
-        fz_issue<S>(Tst, in_mt + (long long)kA * S, lane, a16 != 0);
-        fz_issue<S>(Lst, in_mt + (long long)(kA + lag) * S, lane, a16 != 0);
+        if (a16) {
+            fz_issue<S, true>(Tst, in_mt + (long long)kA * S, lane);
+            fz_issue<S, true>(Lst, in_mt + (long long)(kA + lag) * S, lane);
+        } else {
+            fz_issue<S, false>(Tst, in_mt + (long long)kA * S, lane);
+            fz_issue<S, false>(Lst, in_mt + (long long)(kA + lag) * S, lane);
+        }
     }
     // ---- wait for the previous unit of this channel, then load its carried state ------------------
     if (ug > 0) {
@@ -993,7 +1002,7 @@ static __device__ __noinline__ void fz_unit_end(const FusedParams& prm, const un
 //   first maximum per row (lane = row); pick the selected sample out of the trail block; issue the
 //   next trail block; M-th power angle; append (theta, sample) to the block buffer.
 // ---------------------------------------------------------------------------------------------
-template <int S, int PC>
+template <int S, int PC, bool A16>
 static __device__ __noinline__ void fz_chunk(const unsigned wofs)
 {
     using C = FzCfg<S>;
@@ -1017,7 +1026,6 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
     const int nchunks = cx.nchunks, c_lo = cx.c_lo, c_hi = cx.c_hi, lag = cx.lag;
     const int kA = cx.kA, kB = cx.kB, M = cx.M;
     const int want = min(FZ_B, cx.pk_hi - cx.kchain);
-    const bool a16 = cx.a16 != 0;
     const bool m_ok = (M == 2 || M == 4 || M == 8);
     const float2* in_mt = cx.in_mt;
     int16_t* o_sidx = cx.o_sidx;
@@ -1032,8 +1040,8 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
         const int krow = kA + FZ_CH * c;
         if (!inflight) {
             if (c >= c_lo && c < c_hi) {
-                fz_issue<S>(Tst, in_mt + (long long)krow * S, lane, a16);
-                fz_issue<S>(Lst, in_mt + (long long)(krow + lag) * S, lane, a16);
+                fz_issue<S, A16>(Tst, in_mt + (long long)krow * S, lane);
+                fz_issue<S, A16>(Lst, in_mt + (long long)(krow + lag) * S, lane);
             } else {
                 fz_fill_slow<S>(Tst, (long long)krow * S, cx, lane);
                 fz_fill_slow<S>(Lst, (long long)(krow + lag) * S, cx, lane);
@@ -1081,7 +1089,7 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
         }
         __syncwarp();
         const bool nfast = (c + 1 >= c_lo) && (c + 1 < c_hi);
-        if (nfast) fz_issue<S>(Lst, in_mt + (long long)(krow + FZ_CH + lag) * S, lane, a16);
+        if (nfast) fz_issue<S, A16>(Lst, in_mt + (long long)(krow + FZ_CH + lag) * S, lane);
 
         // ---- timing, part 2: lane = row: first maximum (:462), the selected sample (:465) ------------
         const int nrows = min(FZ_CH, kB - krow);
@@ -1111,10 +1119,13 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
         }
         __syncwarp();
         if (nfast) {
-            fz_issue<S>(Tst, in_mt + (long long)(krow + FZ_CH) * S, lane, a16);
+            fz_issue<S, A16>(Tst, in_mt + (long long)(krow + FZ_CH) * S, lane);
             // and the lead block after the next towards L2, one 128-byte line per lane
-            if (c + 2 < c_hi && lane * 16 < CHS)
-                fz_prefetch_line(in_mt + (long long)(krow + 2 * FZ_CH + lag) * S + lane * 16);
+            if (c + 2 < c_hi) {
+                const float2* nx = in_mt + (long long)(krow + 2 * FZ_CH + lag) * S;
+                if (A16) { if (lane == 0) fz_prefetch_l2(nx, (unsigned)CHS * 8u); }
+                else if (lane * 16 < CHS) fz_prefetch_line(nx + lane * 16);
+            }
         }
         inflight = nfast;
 
@@ -1157,9 +1168,10 @@ k_fused(const FusedParams prm)
         const int nchunks = fz_unit_begin<S, PC>(prm, wofs, u);
         if (nchunks < 0) continue;
         fz_drain<S, PC>(wofs);         // packets without symbols before the first chunk (and units without any symbol)
-        while (cx.c < nchunks) {
-            fz_chunk<S, PC>(wofs);
-            fz_drain<S, PC>(wofs);
+        if (cx.a16) {
+            while (cx.c < nchunks) { fz_chunk<S, PC, true>(wofs); fz_drain<S, PC>(wofs); }
+        } else {
+            while (cx.c < nchunks) { fz_chunk<S, PC, false>(wofs); fz_drain<S, PC>(wofs); }
         }
         fz_unit_end<S, PC>(prm, wofs);
     }
