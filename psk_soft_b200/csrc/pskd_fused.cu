@@ -141,6 +141,15 @@ __device__ __forceinline__ void fz_cp_async8(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void fz_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// e = f32(f32(re*re) + f32(im*im)) (std::norm<float>, cpp/psk_soft.cpp:448) with the two products in one
+// packed instruction (FMUL2: both halves rounded to nearest like the scalar multiply)
+__device__ __forceinline__ float fz_energy(float2 v) {
+    float px, py;
+    asm("{\n\t.reg .b64 a, r;\n\tmov.b64 a, {%2, %3};\n\tmul.rn.f32x2 r, a, a;\n\tmov.b64 {%0, %1}, r;\n\t}"
+        : "=f"(px), "=f"(py) : "f"(v.x), "f"(v.y));
+    return faddr(px, py);
+}
+
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -240,29 +249,6 @@ __device__ __forceinline__ unsigned fz_slice8(float2 c) {
 
 static __device__ __noinline__ float2 fz_cdiv(float2 n, float2 d) { return cdiv_f32(n, d); }
 
-// four symbols' bits as shorts (LSB first, cpp/psk_soft.cpp:512,525-526,559-563) packed into words
-template <int BPB>
-__device__ __forceinline__ void fz_store_bits(unsigned* dst, const unsigned b[4]) {
-    if (BPB == 1) {
-        *reinterpret_cast<uint2*>(dst) = make_uint2(b[0] | (b[1] << 16), b[2] | (b[3] << 16));
-    } else if (BPB == 2) {
-        uint4 w;
-        w.x = (b[0] & 1u) | ((b[0] >> 1) << 16); w.y = (b[1] & 1u) | ((b[1] >> 1) << 16);
-        w.z = (b[2] & 1u) | ((b[2] >> 1) << 16); w.w = (b[3] & 1u) | ((b[3] >> 1) << 16);
-        *reinterpret_cast<uint4*>(dst) = w;
-    } else {
-        // shorts: b0.0 b0.1 | b0.2 b1.0 | b1.1 b1.2 | b2.0 b2.1 | b2.2 b3.0 | b3.1 b3.2
-        uint2 w0, w1, w2;
-        w0.x = (b[0] & 1u) | (((b[0] >> 1) & 1u) << 16);
-        w0.y = ((b[0] >> 2) & 1u) | ((b[1] & 1u) << 16);
-        w1.x = ((b[1] >> 1) & 1u) | (((b[1] >> 2) & 1u) << 16);
-        w1.y = (b[2] & 1u) | (((b[2] >> 1) & 1u) << 16);
-        w2.x = ((b[2] >> 2) & 1u) | ((b[3] & 1u) << 16);
-        w2.y = ((b[3] >> 1) & 1u) | (((b[3] >> 2) & 1u) << 16);
-        reinterpret_cast<uint2*>(dst)[0] = w0; reinterpret_cast<uint2*>(dst)[1] = w1; reinterpret_cast<uint2*>(dst)[2] = w2;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // sincosf for the derotation phasor (cpp/psk_soft.cpp:499, std::polar(1.0f, pc)).  Three-term
 // Cody-Waite reduction by pi/2 and the Cephes single-precision kernels: |error| <= 1e-7 for
@@ -331,52 +317,20 @@ static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float
     for (int j = 0; j < bpb; j++) b_stage[j] = (short)((b >> j) & 1u);
 }
 
-// derotate / differential decode / slice of a lane's four symbols (cpp/psk_soft.cpp:484-566),
-// specialised on bits per symbol and on differential decoding so that the four symbols form one
-// branch-free, call-free instruction stream.  QPSK <=> BPB == 2 (constelationSize 4).  Returns
-// the mask of symbols that need fz_back_literal.
+// derotate / differential decode / slice (cpp/psk_soft.cpp:484-566), specialised on bits per symbol and on
+// differential decoding.  QPSK <=> BPB == 2 (constelationSize 4).  Flagged symbols take fz_back_literal.
+// A ROLLED loop: trip t handles symbol 32*t + lane (inputs and outputs go through shared memory,
+// conflict-free).  The block's code is executed once per 128 symbols, so its cost is
+// dominated by instruction fetch (the L0 instruction cache holds ~380 instructions and is shared by the
+// warps of a scheduler): four trips through ~70 instructions beat one trip through ~250.
 template <int BPB, bool DIFF>
-__device__ __forceinline__ unsigned fz_back4(const float2 (&sv)[4], float2 sprev, const float (&el)[4], int M,
-                                             float2 (&cv)[4], unsigned (&bsym)[4]) {
+__device__ __forceinline__ void fz_back_rolled(const float2* selb, const float* th, float2* cst, short* bstage,
+                                               int lane, int M, int m) {
     const float inv_m = 1.0f / (float)M;
-    unsigned badmask = (BPB == 0 && (M & (M - 1)) != 0) ? 0xfu : 0u;       // -est/M not an exact multiply
-#pragma unroll
-    for (int v = 0; v < 4; v++) {
-        bool bad = false;
-        float2 s = sv[v];
-        float pc = 0.0f;
-        if (DIFF) s = fz_cdiv_fast(s, (v == 0) ? sprev : sv[v - 1], bad);                         // :488
-        else pc = fmulr(-el[v], inv_m);                                                           // :494 (exact for M = 2^n)
-        if (BPB == 2) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                     // :497-498
-        float sn, cs;
-        fz_sincos(pc, sn, cs, bad);                                                               // :499
-        const float x = fsubr(fmulr(s.x, cs), fmulr(s.y, sn));                                    // :500-501, unfused
-        const float y = faddr(fmulr(s.x, sn), fmulr(s.y, cs));
-        bad = bad || (isnan(x) && isnan(y));                                                      // __mulsc3 recovery
-        cv[v] = make_float2(x, y);
-        unsigned b = 0;
-        if (BPB == 3) b = fz_slice8_flag(cv[v], bad);
-        else if (BPB == 1) b = (x < 0.0f) ? 1u : 0u;
-        else if (BPB == 2) b = ((x != 0.0f) != (y != 0.0f) ? 1u : 0u) | ((y != 0.0f) ? 0u : 2u);   // :523-526 (float -> bool, sic)
-        bsym[v] = b;
-        badmask |= bad ? (1u << v) : 0u;
-    }
-    return badmask;
-}
-
-// The same stage as a ROLLED loop over the lane's four symbols (inputs and outputs go through shared
-// memory, the bits through a packed accumulator).  The block's code is executed once per 128 symbols,
-// so its cost is dominated by instruction fetch (the L0 instruction cache holds ~380 instructions and is
-// shared by the warps of a scheduler): four trips through ~70 instructions beat one trip through ~250.
-template <int BPB, bool DIFF>
-__device__ __forceinline__ unsigned fz_back_rolled(const float2* selb, const float* th, float2* cst, int i0, int M, unsigned& bits) {
-    const float inv_m = 1.0f / (float)M;
-    unsigned badmask = (BPB == 0 && (M & (M - 1)) != 0) ? 0xfu : 0u;       // -est/M not an exact multiply
-    unsigned acc = 0;
+    const bool inexact = (BPB == 0 && (M & (M - 1)) != 0);                 // -est/M not an exact multiply
 #pragma unroll 1
-    for (int v = 0; v < 4; v++) {
-        const int i = i0 + v;
-        bool bad = false;
+    for (int i = lane; i < ((m + 31) & ~31); i += 32) {
+        bool bad = inexact;
         float2 s = selb[2 + i];
         float pc = 0.0f;
         if (DIFF) s = fz_cdiv_fast(s, selb[1 + i], bad);                                          // :488
@@ -389,15 +343,19 @@ __device__ __forceinline__ unsigned fz_back_rolled(const float2* selb, const flo
         bad = bad || (isnan(x) && isnan(y));                                                      // __mulsc3 recovery
         const float2 c = make_float2(x, y);
         cst[i] = c;
-        unsigned b = 0;
-        if (BPB == 3) b = fz_slice8_flag(c, bad);
-        else if (BPB == 1) b = (x < 0.0f) ? 1u : 0u;
-        else if (BPB == 2) b = ((x != 0.0f) != (y != 0.0f) ? 1u : 0u) | ((y != 0.0f) ? 0u : 2u);   // :523-526 (float -> bool, sic)
-        acc |= b << (4 * v);
-        badmask |= bad ? (1u << v) : 0u;
+        if (BPB == 3) {
+            const unsigned b = fz_slice8_flag(c, bad);
+            bstage[3 * i] = (short)(b & 1u); bstage[3 * i + 1] = (short)((b >> 1) & 1u); bstage[3 * i + 2] = (short)(b >> 2);   // :559-563
+        } else if (BPB == 1) {
+            bstage[i] = (x < 0.0f) ? 1 : 0;                                                       // :512
+        } else if (BPB == 2) {                                                                    // :523-526 (float -> bool, sic)
+            reinterpret_cast<unsigned*>(bstage)[i] = ((x != 0.0f) != (y != 0.0f) ? 1u : 0u) | ((y != 0.0f) ? 0u : 0x10000u);
+        }
+        bad = bad && i < m;
+        if (__any_sync(0xffffffffu, bad)) {             // rare: literal evaluation of the flagged symbols
+            if (bad) fz_back_literal(selb[2 + i], selb[1 + i], th[i], M, BPB, DIFF ? 1 : 0, cst + i, bstage + i * BPB);
+        }
     }
-    bits = acc;
-    return badmask;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -579,35 +537,17 @@ static __device__ __noinline__ void fz_back_block(const unsigned wofs, const int
     const int lane = fz_lane();
     const int M = cx.M, bpb = cx.bpb, kchain = cx.kchain;
     const bool diff = cx.diff != 0;
-    const int i0 = lane * 4;
-    unsigned bits = 0, fixmask;
     switch (bpb * 2 + (diff ? 1 : 0)) {
-        case 6: fixmask = fz_back_rolled<3, false>(selb, th, cst, i0, M, bits); break;
-        case 7: fixmask = fz_back_rolled<3, true>(selb, th, cst, i0, M, bits); break;
-        case 4: fixmask = fz_back_rolled<2, false>(selb, th, cst, i0, M, bits); break;
-        case 5: fixmask = fz_back_rolled<2, true>(selb, th, cst, i0, M, bits); break;
-        case 2: fixmask = fz_back_rolled<1, false>(selb, th, cst, i0, M, bits); break;
-        case 3: fixmask = fz_back_rolled<1, true>(selb, th, cst, i0, M, bits); break;
-        case 0: fixmask = fz_back_rolled<0, false>(selb, th, cst, i0, M, bits); break;
-        default: fixmask = fz_back_rolled<0, true>(selb, th, cst, i0, M, bits); break;
+        case 6: fz_back_rolled<3, false>(selb, th, cst, bstage, lane, M, m); break;
+        case 7: fz_back_rolled<3, true>(selb, th, cst, bstage, lane, M, m); break;
+        case 4: fz_back_rolled<2, false>(selb, th, cst, bstage, lane, M, m); break;
+        case 5: fz_back_rolled<2, true>(selb, th, cst, bstage, lane, M, m); break;
+        case 2: fz_back_rolled<1, false>(selb, th, cst, bstage, lane, M, m); break;
+        case 3: fz_back_rolled<1, true>(selb, th, cst, bstage, lane, M, m); break;
+        case 0: fz_back_rolled<0, false>(selb, th, cst, bstage, lane, M, m); break;
+        default: fz_back_rolled<0, true>(selb, th, cst, bstage, lane, M, m); break;
     }
-#pragma unroll
-    for (int v = 0; v < 4; v++) if (i0 + v >= m) fixmask &= ~(1u << v);
     int16_t* o_bits = cx.o_bits;
-    if (bpb > 0 && o_bits) {
-        const unsigned bsym[4] = {bits & 7u, (bits >> 4) & 7u, (bits >> 8) & 7u, (bits >> 12) & 7u};
-        unsigned* dst = reinterpret_cast<unsigned*>(bstage) + lane * 2 * bpb;
-        if (bpb == 3) fz_store_bits<3>(dst, bsym);
-        else if (bpb == 2) fz_store_bits<2>(dst, bsym);
-        else fz_store_bits<1>(dst, bsym);
-    }
-    if (__any_sync(0xffffffffu, fixmask != 0)) {            // rare: literal evaluation of the flagged symbols
-        for (int v = 0; v < 4; v++) {
-            if ((fixmask >> v) & 1u)
-                fz_back_literal(selb[2 + i0 + v], selb[1 + i0 + v], th[i0 + v], M, bpb, diff ? 1 : 0,
-                                cst + i0 + v, bstage + (i0 + v) * bpb);
-        }
-    }
     __syncwarp();
     {
         float* o_phase = cx.o_phase;
@@ -1062,9 +1002,9 @@ static __device__ __noinline__ void fz_chunk(const unsigned wofs)
                 if (G * R == 32 || R * wg + i < 32) {
                     const float2 a = (i & 1) ? lo[i * S] : le[i * S];
                     const float2 b = (i & 1) ? to[i * S] : te[i * S];
-                    x = daddr(x, (double)energy_f32(a.x, a.y));          // :448-451
+                    x = daddr(x, (double)fz_energy(a));                       // :448-451
                     Eloc[i] = x;
-                    x = dsubr(x, (double)energy_f32(b.x, b.y));          // :576
+                    x = dsubr(x, (double)fz_energy(b));                       // :576
                 } else Eloc[i] = 0.0;
             }
         }
