@@ -549,25 +549,45 @@ static __device__ __noinline__ void fz_back_block(const unsigned wofs, const int
     }
     int16_t* o_bits = cx.o_bits;
     __syncwarp();
+    // coalesced stores; a full block at a 16-byte aligned position goes out in 128-bit pieces
     {
+        const bool full = (m == FZ_B);
         float* o_phase = cx.o_phase;
         if (o_phase) {
-            float* o = o_phase + kchain + lane;
-            const float* si = th + lane;
+            float* o = o_phase + kchain;
+            if (full && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                __stcs(reinterpret_cast<float4*>(o) + lane, reinterpret_cast<const float4*>(th)[lane]);
+            } else {
+                o += lane;
+                const float* si = th + lane;
 #pragma unroll 1
-            for (int i = lane; i < m; i += 32, o += 32, si += 32) __stcs(o, *si);
+                for (int i = lane; i < m; i += 32, o += 32, si += 32) __stcs(o, *si);
+            }
         }
         float2* o_soft = cx.o_soft;
         if (o_soft) {
-            float2* o = o_soft + kchain + lane;
-            const float2* si = cst + lane;
+            float2* o = o_soft + kchain;
+            if (full && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(cst) + lane;
+                float4* o4 = reinterpret_cast<float4*>(o) + lane;
+                const float4 v0 = s4[0], v1 = s4[32];
+                __stcs(o4, v0); __stcs(o4 + 32, v1);
+            } else {
+                o += lane;
+                const float2* si = cst + lane;
 #pragma unroll 1
-            for (int i = lane; i < m; i += 32, o += 32, si += 32) __stcs(o, *si);
+                for (int i = lane; i < m; i += 32, o += 32, si += 32) __stcs(o, *si);
+            }
         }
         if (bpb > 0 && o_bits) {
             int16_t* o = o_bits + (long long)kchain * bpb;
             const int nsh = m * bpb;
-            if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
+            if (full && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+                const uint2* s2 = reinterpret_cast<const uint2*>(bstage) + lane;
+                uint2* o2 = reinterpret_cast<uint2*>(o) + lane;
+#pragma unroll
+                for (int q = 0; q < 3; q++) if (q < bpb) __stcs(o2 + 32 * q, s2[32 * q]);
+            } else if ((reinterpret_cast<uintptr_t>(o) & 3) == 0) {
                 const unsigned* s32 = reinterpret_cast<const unsigned*>(bstage) + lane;
                 unsigned* o32 = reinterpret_cast<unsigned*>(o) + lane;
                 const int nw = nsh >> 1;                  // <= 192 words
