@@ -81,3 +81,38 @@ def test_bank_differential_qpsk_vs_oracle(oracle_built):
         got = dict(soft=out["soft"][c, :K].cpu().numpy().view(np.complex64).reshape(-1), phase=out["phase"][c, :K].cpu().numpy(),
                    sidx=out["sidx"][c, :K].cpu().numpy(), bits=out["bits"][c, :2 * K].cpu().numpy())
         assert_parity(got, ref, differential=True, tag=f"channel {c}")
+
+
+@pytest.mark.parametrize("S,M,D", [(8, 8, 0), (9, 4, 1), (10, 2, 0)])
+def test_bank_unaligned_rows_vs_oracle(oracle_built, S, M, D):
+    """odd row lengths and an odd first sample: the input rows of odd channels and every output row start
+    8-byte (not 16-byte) aligned -> the 8-byte copy path of the fused kernel's staged blocks and the
+    element-wise output stores instead of the 128-bit ones"""
+    import torch
+    import psk_soft_b200 as pk
+    props = dict(samplesPerBaud=S, constelationSize=M, numAvg=60, phaseAvg=30, differentialDecoding=D)
+    nch, n = 48, 90001
+    cap = n // S + 9                                          # odd for every S used here -> odd output rows
+    cap += (cap + 1) % 2
+    iq = torch.empty((nch, n, 2), dtype=torch.float32, device="cuda")
+    pk.synth_fill(iq.data_ptr(), n, 0, nch, n, seed=31 + S, samplesPerBaud=S, constelationSize=M,
+                  sigma=0.02, freq_max=2e-5, pn_sigma=0.01)
+    torch.cuda.synchronize()
+    bank = pk.Bank(nch, props)
+    bpb = {2: 1, 4: 2, 8: 3}[M]
+    soft = torch.zeros((nch, cap, 2), dtype=torch.float32, device="cuda")
+    phase = torch.zeros((nch, cap), dtype=torch.float32, device="cuda")
+    sidx = torch.zeros((nch, cap), dtype=torch.int16, device="cuda")
+    bits = torch.zeros((nch, cap * 3), dtype=torch.int16, device="cuda")
+    skip = 3                                                  # start at an odd sample of every row
+    rc, ns, nb = bank.process_raw(iq.data_ptr() + skip * 8, n, n - skip, soft.data_ptr(), bits.data_ptr(), phase.data_ptr(),
+                                  sidx.data_ptr(), cap, cap * 3, xdelta=0.01, packet_len=7000)
+    assert rc == 0 and (ns == ns[0]).all()
+    K = int(ns[0])
+    torch.cuda.synchronize()
+    iq_h = iq.cpu().numpy().view(np.complex64).reshape(nch, n)
+    for c in (0, 1, 22, 47):
+        ref = oracle_built.OracleComponent(**props).demod(iq_h[c, skip:], packet_len=7000, xdelta=0.01)
+        got = dict(soft=soft[c, :K].cpu().numpy().view(np.complex64).reshape(-1), phase=phase[c, :K].cpu().numpy(),
+                   sidx=sidx[c, :K].cpu().numpy(), bits=bits[c, :bpb * K].cpu().numpy())
+        assert_parity(got, ref, differential=bool(D), tag=f"S={S} channel {c}")
