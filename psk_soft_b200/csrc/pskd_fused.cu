@@ -995,7 +995,7 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
     double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);       // [32][ES] window sums
-    const int lane = threadIdx.x & 31;
+    const int lane = fz_lane();
     const bool wact = lane < G * S;
     const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
 

@@ -13,4 +13,4 @@ for r in rows:
         o = a - base
         if lo <= o <= hi:
             g = lambda k: int(r[hdr.index(k)] or 0)
-            print(f'{o:6x} {g("Instructions Executed")/per:6.2f} {g("# Samples"):6d} ni{g("stall_no_inst"):5d}  {r[1].strip()[:90]}')
+            print(f'{o:6x} {g("Instructions Executed")/per:6.2f} {g("# Samples"):6d} ni{g("stall_no_inst"):5d} w{g("stall_wait"):5d} ss{g("stall_short_sb"):5d} ls{g("stall_long_sb"):5d}  {r[1].strip()[:90]}')
