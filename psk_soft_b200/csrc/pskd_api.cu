@@ -91,7 +91,7 @@ struct pskd_bank {
     cudaEvent_t slab_in[16] = {nullptr}, slab_done[16] = {nullptr};
     int chain_mode = 0;        // 0 auto (scan-based where possible), 1 force the sequential chain (PSKD_CHAIN=seq)
     int fused_mode = -1;       // -1 auto (large banks), 0 never, 1 whenever a channel qualifies (PSKD_FUSED)
-    int fused_min_channels = 1024;   // auto: channels per launch from which the fused kernel fills the GPU (PSKD_FUSED_MIN)
+    int fused_min_channels = 1152;   // auto: channels per launch from which the fused kernel beats the staged ones (measured crossover ~1120 for 1M-sample 8-PSK calls; PSKD_FUSED_MIN)
     int* d_list = nullptr;     // fused launch lists (channel indices), one segment per (slab, samplesPerBaud)
     int* h_list_slot[2] = {nullptr, nullptr};
     int* d_done = nullptr;     // [n_channels] units completed per channel in the current call
