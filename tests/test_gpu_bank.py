@@ -116,3 +116,56 @@ def test_bank_unaligned_rows_vs_oracle(oracle_built, S, M, D):
         got = dict(soft=soft[c, :K].cpu().numpy().view(np.complex64).reshape(-1), phase=phase[c, :K].cpu().numpy(),
                    sidx=sidx[c, :K].cpu().numpy(), bits=bits[c, :bpb * K].cpu().numpy())
         assert_parity(got, ref, differential=bool(D), tag=f"S={S} channel {c}")
+
+
+def test_full_size_bank_properties(oracle_built, fused_mode):
+    """BASELINE.json configs[3] at FULL size (QPSK, S=8, 4096 channels x 1M samples, packets 64000) through
+    size-independent properties: symbol counts, value ranges, one call == two calls cut at a packet boundary,
+    a 64-channel sub-bank processed alone (other launch geometry / kernel choice) == the same channels inside the
+    bank, and sampled channels against the oracle over their full length."""
+    import torch
+    import psk_soft_b200 as pk
+    if torch.cuda.mem_get_info()[0] < 70e9:
+        pytest.skip("needs ~60 GB of free device memory")
+    props = dict(samplesPerBaud=8, constelationSize=4, numAvg=100, phaseAvg=50, differentialDecoding=0)
+    nch, n, pkt = 4096, 1_000_000, 64000
+    iq, one, K, bank = _run_bank(pk, torch, props, nch, n, [0, n], seed=4, packet_len=pkt)
+    assert K == n // 8 - 99
+    st = bank.stats()
+    assert st["symbols_out"] == nch * K
+    sidx = one["sidx"][:, :K]
+    assert int(sidx.min()) >= 0 and int(sidx.max()) < 8
+    bits = one["bits"][:, :2 * K]
+    assert int(bits.min()) >= 0 and int(bits.max()) <= 1
+    assert bool(torch.isfinite(one["phase"][:, :K]).all()) and bool(torch.isfinite(one["soft"][:, :K]).all())
+    del bank
+    # two calls cut at a packet boundary: identical packets -> identical integers, floats within the parity tolerance
+    _, two, K2, _ = _run_bank(pk, torch, props, nch, n, [0, 7 * pkt, n], seed=4, packet_len=pkt)
+    assert K2 == K
+    assert torch.equal(one["sidx"], two["sidx"]) and torch.equal(one["bits"], two["bits"])
+    for k in ("phase", "soft"):
+        a, b = one[k][:, :K].float(), two[k][:, :K].float()
+        assert bool(((a - b).abs() <= 1e-4 * torch.clamp(a.abs(), min=1.0)).all()), k
+    del two
+    # a sub-bank processed alone
+    lo, hi = 1000, 1064
+    sub = pk.Bank(hi - lo, props)
+    cap = n // 8 + 8
+    s_soft = torch.zeros((hi - lo, cap, 2), dtype=torch.float32, device="cuda")
+    s_phase = torch.zeros((hi - lo, cap), dtype=torch.float32, device="cuda")
+    s_sidx = torch.zeros((hi - lo, cap), dtype=torch.int16, device="cuda")
+    s_bits = torch.zeros((hi - lo, cap * 3), dtype=torch.int16, device="cuda")
+    rc, ns, nb = sub.process_raw(iq[lo:hi].data_ptr(), n, n, s_soft.data_ptr(), s_bits.data_ptr(), s_phase.data_ptr(),
+                                 s_sidx.data_ptr(), cap, cap * 3, xdelta=0.01, packet_len=pkt)
+    torch.cuda.synchronize()
+    assert rc == 0 and int(ns[0]) == K
+    assert torch.equal(s_sidx[:, :K], one["sidx"][lo:hi, :K]) and torch.equal(s_bits[:, :2 * K], one["bits"][lo:hi, :2 * K])
+    a, b = s_phase[:, :K], one["phase"][lo:hi, :K]
+    assert bool(((a - b).abs() <= 1e-4 * torch.clamp(a.abs(), min=1.0)).all())
+    # sampled channels against the oracle, full length
+    for c in (0, 1777, 4095):
+        iq_h = iq[c].cpu().numpy().view(np.complex64).reshape(n)
+        ref = oracle_built.OracleComponent(**props).demod(iq_h, packet_len=pkt, xdelta=0.01)
+        got = dict(soft=one["soft"][c, :K].cpu().numpy().view(np.complex64).reshape(-1), phase=one["phase"][c, :K].cpu().numpy(),
+                   sidx=one["sidx"][c, :K].cpu().numpy(), bits=one["bits"][c, :2 * K].cpu().numpy())
+        assert_parity(got, ref, tag=f"full-size channel {c}")
