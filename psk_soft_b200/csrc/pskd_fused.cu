@@ -48,6 +48,10 @@ constexpr int FZ_CH = 32;              // rows per chunk
 constexpr int FZ_B = 128;              // symbols per chain block (4 per lane)
 constexpr int FZ_BUF = 160;            // capacity of the (theta, sample) block buffer
 constexpr int FZ_MAX_ITERS = 16;
+#ifndef PSKD_FZ_PF
+#define PSKD_FZ_PF 2
+#endif
+constexpr int FZ_PF = PSKD_FZ_PF;      // lead blocks are prefetched into L2 this many chunks ahead of their cp.async
 // The hot stage functions are inlined into ONE loop body, every rare path is a separate non-inlined
 // function: the hot code (~19 KB) then sits in a few contiguous runs, which is what the 32 KB L1.5
 // instruction cache needs (measured: stage functions as separate calls 14.1 ms per launch, inlined 13.4;
@@ -872,7 +876,7 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
         a16 = (((reinterpret_cast<uintptr_t>(in_mt + sT0) | reinterpret_cast<uintptr_t>(in_mt + sL0)) & 15) == 0) ? 1 : 0;
         // start the stream: the first two lead blocks towards L2
         if (lane == 0 && c_lo < c_hi && a16)
-            fz_prefetch_l2(in_mt + sL0 + (long long)c_lo * CHS, (unsigned)min(2, c_hi - c_lo) * CHS * 8);
+            fz_prefetch_l2(in_mt + sL0 + (long long)c_lo * CHS, (unsigned)min(FZ_PF, c_hi - c_lo) * CHS * 8);
     }
     const bool pre0 = nchunks > 0 && c_lo == 0 && c_hi > 0;
     if (pre0) {                                                           // chunk 0's blocks: input only, no dependence on the predecessor
@@ -1104,8 +1108,8 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
         if (nfast) {
             fz_issue<S, A16>(Tst, in_mt + (long long)(krow + FZ_CH) * S, lane);
             // and the lead block after the next towards L2, one 128-byte line per lane
-            if (c + 2 < c_hi) {
-                const float2* nx = in_mt + (long long)(krow + 2 * FZ_CH + lag) * S;
+            if (c + FZ_PF < c_hi) {
+                const float2* nx = in_mt + (long long)(krow + FZ_PF * FZ_CH + lag) * S;
                 if (A16) { if (lane == 0) fz_prefetch_l2(nx, (unsigned)CHS * 8u); }
                 else if (lane * 16 < CHS) fz_prefetch_line(nx + lane * 16);
             }
