@@ -12,6 +12,11 @@ FLOAT_RTOL = 1e-4
 
 
 def float_close(a, b, rtol=FLOAT_RTOL):
+    with np.errstate(invalid="ignore", over="ignore"):
+        return _float_close(a, b, rtol)
+
+
+def _float_close(a, b, rtol):
     a = np.asarray(a); b = np.asarray(b)
     if np.iscomplexobj(a):
         mag = np.maximum(1.0, np.abs(b))
@@ -20,7 +25,21 @@ def float_close(a, b, rtol=FLOAT_RTOL):
         mag = np.maximum(1.0, np.abs(b))
         err = np.abs(a - b)
     bad = ~(err <= rtol * mag)
-    return bad, (err / mag)
+    # non-finite values (division by a zero sample in differential mode, cpp/psk_soft.cpp:488) must agree
+    # component by component: NaN with NaN, +/-inf with the same infinity
+    def same_nonfinite(x, y):
+        return (np.isnan(x) & np.isnan(y)) | (np.isinf(x) & np.isinf(y) & (np.sign(x) == np.sign(y)))
+    if np.iscomplexobj(a):
+        fin = np.isfinite(b.real) & np.isfinite(b.imag)
+        agree = (same_nonfinite(a.real, b.real) | (np.isfinite(b.real) & (np.abs(a.real - b.real) <= rtol * mag))) & \
+                (same_nonfinite(a.imag, b.imag) | (np.isfinite(b.imag) & (np.abs(a.imag - b.imag) <= rtol * mag)))
+    else:
+        fin = np.isfinite(b)
+        agree = same_nonfinite(a, b)
+    with np.errstate(invalid="ignore"):
+        bad = np.where(fin, bad, ~agree)
+        rel = np.where(fin, err / mag, 0.0)
+    return bad, rel
 
 
 def assert_parity(got, ref, differential=False, tag="", check_first_bits=True):

@@ -155,3 +155,38 @@ def test_time_parallel_chain_long_single_channel(oracle_built, monkeypatch):
     r2 = ref2.demod(iq[640000:], packet_len=64000, xdelta=0.01)
     assert_parity(a, r1, tag="first call")
     assert_parity(got2, r2, tag="second call, time-parallel from carried state")
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_fused_randomized_configurations(seed, oracle_built, monkeypatch):
+    """Randomized sweep of the fused kernel's whole domain (samplesPerBaud 8/9/10/16, numAvg 1..256, phaseAvg
+    2..128 -- both shared-memory classes --, any constellation, differential on/off, arbitrary packet lengths,
+    amplitudes over six decades, silent stretches, several calls with carried state) against the oracle."""
+    import psk_soft_b200 as pk
+    monkeypatch.setenv("PSKD_FUSED", "1")
+    monkeypatch.setenv("PSKD_TP", "0")
+    rs = np.random.RandomState(1000 + seed)
+    nch = 5
+    props, iqs = [], []
+    n = int(rs.randint(30000, 70000))
+    for c in range(nch):
+        S = int(rs.choice([8, 9, 10, 16])); M = int(rs.choice([2, 4, 8, 8])); D = int(rs.randint(0, 2))
+        A = int(rs.choice([1, 2, 7, 31, 32, 33, 100, 129, 130, 200, 256])); P = int(rs.choice([2, 3, 25, 50, 52, 53, 100, 128]))
+        props.append(dict(samplesPerBaud=S, constelationSize=M, numAvg=A, phaseAvg=P, differentialDecoding=D))
+        amp = float(10.0 ** rs.uniform(-3, 3))
+        x = siggen.gen_shaped(n, S, M, seed=int(rs.randint(1 << 30)), sigma=0.02 * amp, freq=float(rs.uniform(-3e-5, 3e-5)),
+                              phase0=float(rs.uniform(0, 6.28)), timing_shift=int(rs.randint(0, S)), amp=amp)
+        if rs.rand() < 0.4:                                   # a silent stretch (all-zero samples)
+            a0 = int(rs.randint(0, n - 3000)); x[a0:a0 + int(rs.randint(10, 3000))] = 0
+        iqs.append(x)
+    iqs = np.stack(iqs)
+    pkt = int(rs.choice([97, 640, 1000, 4096, 16000, 64000]))
+    cuts = sorted(set([0, n] + [int(v) for v in rs.randint(1, n, size=int(rs.randint(0, 3)))]))
+    bank = pk.Bank(nch, props)
+    orcs = [oracle_built.OracleComponent(**p) for p in props]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        got = bank.process_host(iqs[:, a:b].copy(), xdelta=0.01, packet_len=pkt)
+        for c in range(nch):
+            ref = orcs[c].demod(iqs[c, a:b], packet_len=pkt, xdelta=0.01)
+            assert_parity(got[c], ref, differential=bool(props[c]["differentialDecoding"]),
+                          tag=f"seed {seed} ch{c} {props[c]} pkt {pkt} call {a}:{b}", check_first_bits=(a == 0))
