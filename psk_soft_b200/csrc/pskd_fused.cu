@@ -407,7 +407,13 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
     if (cx.st.fit.head != 0) { fz_normalize_ring(yh, estv, cx.st.fit, P, lane); if (lane == 0) cx.cz_valid = 0; __syncwarp(); }
     if (!cx.cz_valid) { fz_rebuild_cz(yh, cz, P, lane); if (lane == 0) cx.cz_valid = 1; __syncwarp(); }
 
-    const float4 t4 = *reinterpret_cast<const float4*>(th + i0);
+    float4 t4 = *reinterpret_cast<const float4*>(th + i0);
+    if (m < FZ_B) {                    // a short block: what lies behind it in the buffer may be anything (never written,
+        if (i0 + 0 >= m) t4.x = 0.0f;  // NaN, huge) and would poison the scans below (exclusive = inclusive - own)
+        if (i0 + 1 >= m) t4.y = 0.0f;
+        if (i0 + 2 >= m) t4.z = 0.0f;
+        if (i0 + 3 >= m) t4.w = 0.0f;
+    }
     const float tl[4] = {t4.x, t4.y, t4.z, t4.w};
     const float xdelta = cx.st.fit.xdelta;
     const float fP1 = cx.fP1;
@@ -1146,6 +1152,10 @@ k_fused(const FusedParams prm)
     const int lane = threadIdx.x & 31;
     const unsigned wofs = (threadIdx.x >> 5) * (unsigned)L::BYTES;
     FzCtx& cx = *reinterpret_cast<FzCtx*>(fz_smem + wofs + L::OFF_CTX);
+#ifdef PSKD_FZ_FILL_SMEM            // debugging aid: start from a known pattern instead of whatever the last kernel left
+    for (int i = lane; i < L::BYTES / 4; i += 32) reinterpret_cast<unsigned*>(fz_smem + wofs)[i] = PSKD_FZ_FILL_SMEM;
+    __syncwarp();
+#endif
 
     for (;;) {
         int u = 0;
