@@ -151,3 +151,50 @@ def test_tiny_and_ragged_calls(oracle_built):
     ref = oracle_built.OracleComponent(**props).demod(iq[:6000], packet_len=3, xdelta=0.01)
     got = pk.PskSoft(**props).demod(iq[:6000], packet_len=3, xdelta=0.01)
     assert_parity(got, ref, tag="3-sample packets")
+
+
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("PSKD_FUZZ_SEEDS", "12")))))
+def test_randomized_reconfiguration_scripts(seed, oracle_built):
+    """random sequences of packets with property changes in between (any constellation / phaseAvg / differential
+    toggle, resetState, queue flush, SRI rate changes, window growth) against the oracle, state carried across every
+    call (reference: cpp/psk_soft.cpp:353-426, 619-651).  Window shrinks are left out: the reference stalls there
+    (:457 never true again) and the C ABI reports them as unsupported."""
+    import psk_soft_b200 as pk
+    rs = np.random.RandomState(7000 + seed)
+    S, A = int(rs.choice([8, 9, 10, 16])), int(rs.choice([3, 20, 64, 100]))
+    props = dict(samplesPerBaud=S, numAvg=A, constelationSize=int(rs.choice([2, 4, 8])), phaseAvg=int(rs.choice([2, 10, 50, 64])),
+                 differentialDecoding=int(rs.randint(0, 2)))
+    orc = oracle_built.OracleComponent(**props)
+    dev = pk.PskSoft(**props)
+    xdelta = 0.01
+    for step in range(14):
+        ch = {}
+        r = rs.rand()
+        if r < 0.15:
+            ch["constelationSize"] = int(rs.choice([2, 4, 8]))
+        elif r < 0.30:
+            ch["phaseAvg"] = int(rs.choice([2, 5, 25, 50, 100, 128]))
+        elif r < 0.42:
+            ch["differentialDecoding"] = int(rs.randint(0, 2))
+        elif r < 0.50:
+            ch["resetState"] = 1
+        elif r < 0.62:                                         # window growth only
+            S2, A2 = int(rs.choice([8, 9, 10, 16])), int(rs.choice([3, 20, 64, 100, 150]))
+            if S2 * A2 >= S * A:
+                if S2 != S: ch["samplesPerBaud"] = S2
+                if A2 != A: ch["numAvg"] = A2
+                S, A = S2, A2
+        if rs.rand() < 0.15:
+            xdelta = float(rs.choice([0.01, 0.02, 1.0, 0.5]))
+        flushed = bool(rs.rand() < 0.1)
+        n = int(rs.choice([1, 7, S * A // 2 + 1, 2000, 9000, 30000, 70000]))
+        M = int(dev.constelationSize if "constelationSize" not in ch else ch["constelationSize"])
+        iq = siggen.gen_shaped(n, S, max(M, 2), seed=int(rs.randint(1 << 30)), sigma=0.03, freq=float(rs.uniform(-3e-5, 3e-5)),
+                               phase0=float(rs.uniform(0, 6.28)), timing_shift=int(rs.randint(0, S)))
+        orc.configure(**ch)
+        dev.configure(**ch)
+        ref = orc.push(iq, xdelta=xdelta, flushed=flushed)
+        got = dev.push(iq, xdelta=xdelta, flushed=flushed)
+        diff = bool(dev.differentialDecoding)
+        assert_parity(got, ref, differential=False if np.isfinite(ref["soft"]).all() else diff,
+                      tag=f"seed {seed} step {step} n {n} {ch} xdelta {xdelta} flushed {flushed}")
