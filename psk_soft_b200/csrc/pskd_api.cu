@@ -91,6 +91,7 @@ struct pskd_bank {
     cudaEvent_t slab_in[16] = {nullptr}, slab_done[16] = {nullptr};
     int chain_mode = 0;        // 0 auto (scan-based where possible), 1 force the sequential chain (PSKD_CHAIN=seq)
     int fused_mode = -1;       // -1 auto (large banks), 0 never, 1 whenever a channel qualifies (PSKD_FUSED)
+    int host_slabs = 16;       // host-buffer mode: channel slabs the H2D / kernels / D2H pipeline works through (PSKD_SLABS, 1..16)
     int fused_min_channels = 1152;   // auto: channels per launch from which the fused kernel beats the staged ones (measured crossover ~1120 for 1M-sample 8-PSK calls; PSKD_FUSED_MIN)
     int* d_list = nullptr;     // fused launch lists (channel indices), one segment per (slab, samplesPerBaud)
     int* h_list_slot[2] = {nullptr, nullptr};
@@ -201,6 +202,7 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     if (const char* e = getenv("PSKD_CHAIN")) b->chain_mode = (strcmp(e, "seq") == 0) ? 1 : 0;
     if (const char* e = getenv("PSKD_FUSED")) b->fused_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
     if (const char* e = getenv("PSKD_FUSED_MIN")) b->fused_min_channels = std::max(1, atoi(e));
+    if (const char* e = getenv("PSKD_SLABS")) b->host_slabs = std::min(16, std::max(1, atoi(e)));
     if (const char* e = getenv("PSKD_TP")) b->tp_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
     cudaError_t e;
 #define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
@@ -498,7 +500,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     if (host_bufs) {
         long long nm = 0;
         for (int i = 0; i < nch; i++) nm = std::max(nm, (long long)(in->n_complex ? in->n_complex[i] : in->n_complex_all));
-        n_slabs = std::min(nch, nm * (long long)nch >= (1 << 22) ? 8 : 1);
+        n_slabs = std::min(nch, nm * (long long)nch >= (1 << 22) ? b->host_slabs : 1);
     }
     std::vector<unsigned char> fusable(nch, 0);
     for (int i = 0; i < nch; i++) {
