@@ -99,6 +99,31 @@ class ClockSampler(threading.Thread):
                 "samples": len(rows), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(torch, dev):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function), so that the pinned
+    host buffers of the e2e leg are first-touched on the GPU's own NUMA node.  Best effort: returns what it did."""
+    try:
+        p = torch.cuda.get_device_properties(dev)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        cpulist = open(f"{base}/local_cpulist").read().strip()
+        node = open(f"{base}/numa_node").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return {"gpu_pci": bdf, "numa_node": node, "cpus": len(cpus), "bound": True}
+        return {"gpu_pci": bdf, "numa_node": node, "cpus": len(allowed), "bound": False}
+    except Exception as e:  # no sysfs entry, not permitted, old torch ...
+        return {"bound": False, "why": type(e).__name__}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -228,6 +253,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the demod path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.cuda.current_device()
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
 
@@ -363,6 +390,7 @@ def main():
     # ---- cpu_baseline: the reference CPU demod on a bounded sample, rank 0, N=1 only --------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, full_affinity)       # the reference gets every host core again
         cores = os.cpu_count() or 1
         cch = min(nch, 512)                      # ~20-30 core-seconds of reference CPU work
         cn = n if nch > 1 else min(n, 16_000_000)
@@ -382,7 +410,7 @@ def main():
                            "samplesPerBaud": S, "constelationSize": w["M"], "numAvg": w["A"], "phaseAvg": w["P"],
                            "differentialDecoding": w["D"], "packet_len": PACKET_LEN, "xdelta": XDELTA,
                            "l2": f"inputs ({nch * n * 8 / 1e9:.1f} GB per GPU) far larger than the 126 MB L2; no flush needed",
-                           "parallelism": f"channels sharded over {world} GPU(s), no collective"},
+                           "parallelism": f"channels sharded over {world} GPU(s), no collective", "host_affinity": numa},
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "chain": {k: stats[k] for k in ("spec_chunks", "spec_misses", "seq_channels", "wraps")}}
         print(json.dumps(line), flush=True)
