@@ -691,7 +691,16 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             // a unit = enough consecutive packets for >= ~4096 symbols
             const long long ppu = std::max<long long>(1, (4096LL * g.S + g.pkt_len_min - 1) / g.pkt_len_min);
             f.pkts_per_unit = (int)std::min<long long>(ppu, 1 << 20);
-            f.units_per_channel = (g.max_pkts + f.pkts_per_unit - 1) / f.pkts_per_unit;
+            // ONE long packet per channel and call (the packet-by-packet use behind serviceFunction): the packet is
+            // cut into parts of >= ~2048 symbols, so that a 4096-channel bank is not 4096 units over 2960 resident
+            // warps (measured: 64000-sample calls 1.05 -> 1.00 ms; with two packets per call the extra unit
+            // start-ups already cost 5 %, on 1M-sample calls 8 %, hence the limit).  PSKD_FUSED_PARTS=1 switches it off.
+            f.parts_per_pkt = 1;
+            if (f.pkts_per_unit == 1 && g.max_pkts <= 1) {
+                static const int max_parts = getenv("PSKD_FUSED_PARTS") ? std::max(1, atoi(getenv("PSKD_FUSED_PARTS"))) : 8;
+                f.parts_per_pkt = (int)std::min<long long>(max_parts, std::max<long long>(1, g.pkt_len_min / (2048LL * g.S)));
+            }
+            f.units_per_channel = f.parts_per_pkt * ((g.max_pkts + f.pkts_per_unit - 1) / f.pkts_per_unit);
             if ((long long)f.units_per_channel * g.count > 0x7fffffffLL) return fail(PSKD_ERR_ARG, "too many packets");
             f.Amax = g.Amax; f.Pmax = g.Pmax;
             f.d_ticket = b->d_ticket + (slab * 4 + (g.S == 8 ? 0 : g.S == 9 ? 1 : g.S == 10 ? 2 : 3));

@@ -83,6 +83,7 @@ struct FzCtx {                         // one per warp, shared memory
     // front-stage constants of the unit and its loop state (fz_chunk)
     int kA, kB, lag, c_lo, c_hi, nchunks, ch, ug;
     int a16;                           // staged blocks are copied in 16-byte pieces (else 8-byte)
+    int end_mid;                       // the unit ends inside its packet: no epilogue, the next unit carries on
     int c;                             // next chunk
     int inflight;                      // chunk c's blocks are already on their way (cp.async)
 };
@@ -124,6 +125,7 @@ struct FusedParams {
     const int* list; int n_list;       // channels served by this launch
     int n_units;                       // n_list * max units per channel
     int pkts_per_unit;
+    int parts_per_pkt;                 // > 1: a unit is one of these parts of ONE packet (pkts_per_unit == 1)
     int* ticket;                       // unit ticket counter (zeroed before the launch)
     int* done;                         // [n_channels] units completed per channel (zeroed before the launch)
     float2* out_soft; int16_t* out_bits; float* out_phase; int16_t* out_sidx;
@@ -649,6 +651,7 @@ static __device__ __noinline__ void fz_chain_slow(const unsigned wofs, const int
 // next packet's prologue (:393-426).  Returns true when the unit is done.
 template <int S>
 static __device__ __noinline__ bool fz_next_packet(FzCtx& cx, float* yh, const int lane) {
+    if (cx.end_mid) { if (lane == 0) cx.unit_done = 1; __syncwarp(); return true; }    // the packet goes on in the next unit
     if (lane == 0) fz_epilogue(cx, yh);
     __syncwarp();
     const int pkt = cx.pkt + 1;
@@ -856,16 +859,26 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
     const int ch = __ldg(prm.list + (u - ug * prm.n_list));
     const ChanDesc* dgp = prm.desc + ch;
     const int n_pkts = dgp->n_pkts;
-    const int pk0 = ug * prm.pkts_per_unit;
+    const int parts = prm.parts_per_pkt;
+    const int part = (parts > 1) ? ug % parts : 0;
+    const int pk0 = (parts > 1) ? ug / parts : ug * prm.pkts_per_unit;
     if (pk0 >= n_pkts) return -1;
-    const int pk1 = min(pk0 + prm.pkts_per_unit, n_pkts);
+    const int pk1 = (parts > 1) ? pk0 + 1 : min(pk0 + prm.pkts_per_unit, n_pkts);
     const int A = dgp->A, P = dgp->P;
     const long long tail_len = dgp->tail_len, pkt_len = dgp->pkt_len;
     const int K = (int)dgp->K;
     const long long V = tail_len + dgp->n_in;
     const int lag = A - 1;
-    const int kA = (int)first_symbol_at((long long)pk0 * pkt_len, tail_len, S, A, K);
-    const int kB = (pk1 == n_pkts) ? K : (int)first_symbol_at((long long)pk1 * pkt_len, tail_len, S, A, K);
+    int kA = (int)first_symbol_at((long long)pk0 * pkt_len, tail_len, S, A, K);
+    int kB = (pk1 == n_pkts) ? K : (int)first_symbol_at((long long)pk1 * pkt_len, tail_len, S, A, K);
+    if (parts > 1) {                   // this unit: part `part` of the packet's symbols (cuts at multiples of 32 symbols)
+        const int per = (((kB - kA + parts - 1) / parts) + 31) & ~31;
+        const int a = min(kB, kA + part * per);
+        kB = (part == parts - 1) ? kB : min(kB, a + per);
+        kA = a;
+    }
+    const bool start_mid = part > 0;                  // the packet's prologue ran in part 0
+    const bool end_mid = part < parts - 1;            // the packet's epilogue runs in its last part
     const int nchunks = (kB - kA + FZ_CH - 1) / FZ_CH;
     const float2* in_mt = dgp->in - tail_len;
     const float2* tailp = dgp->tail;
@@ -918,7 +931,9 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
         cx.n_pkts = n_pkts; cx.pk1 = pk1; cx.K = K; cx.A = A; cx.M = dgp->M; cx.P = P; cx.bpb = dgp->bpb; cx.diff = dgp->D;
         cx.pkt = pk0; cx.kchain = kA; cx.nbuf = 0; cx.cz_valid = 0; cx.unit_done = 0;
         cx.fP1 = (float)(P - 1);
-        cx.pk_hi = (pk0 + 1 == n_pkts) ? K : (int)first_symbol_at((long long)(pk0 + 1) * pkt_len, tail_len, S, A, K);
+        cx.pk_hi = (parts > 1) ? kB
+                   : (pk0 + 1 == n_pkts) ? K : (int)first_symbol_at((long long)(pk0 + 1) * pkt_len, tail_len, S, A, K);
+        cx.end_mid = end_mid ? 1 : 0;
         cx.kA = kA; cx.kB = kB; cx.lag = lag;
         cx.c_lo = c_lo; cx.c_hi = c_hi; cx.nchunks = nchunks; cx.a16 = a16;
         cx.ch = ch; cx.ug = ug; cx.V = V;
@@ -926,7 +941,11 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
     }
     for (int j = lane; j < P; j += 32) yh[j] = __ldcg(gring + j);
     __syncwarp();
-    if (lane == 0) { cx.wraps0 = cx.st.wraps; selb[1] = cx.st.last; fz_prologue(cx, yh); }
+    if (lane == 0) {
+        cx.wraps0 = cx.st.wraps; selb[1] = cx.st.last;
+        if (!start_mid) fz_prologue(cx, yh);
+        else if (cx.st.fit.pts == cx.st.fit.n && cx.st.fit.pts > 1) cx.fc = fit_const(cx.st.fit);
+    }
     __syncwarp();
 
     // ---- carried window sums: rows [kA, kA+lag) per phase, exact double sums ------------------------
@@ -1183,7 +1202,7 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     FusedParams p{};
     p.desc = c.d_desc; p.state = c.d_state; p.ring_base = c.d_ring;
     p.list = f.d_list; p.n_list = f.n_list;
-    p.pkts_per_unit = f.pkts_per_unit;
+    p.pkts_per_unit = f.pkts_per_unit; p.parts_per_pkt = f.parts_per_pkt;
     p.n_units = f.n_list * f.units_per_channel;
     p.ticket = f.d_ticket; p.done = f.d_done;
     p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_sidx = c.out_sidx;

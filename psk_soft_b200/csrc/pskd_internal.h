@@ -159,6 +159,7 @@ struct FusedLaunch {
     const int* d_list; int n_list;     // channel indices (relative to LaunchCtx::d_desc)
     int units_per_channel;             // ceil(max n_pkts / pkts_per_unit)
     int pkts_per_unit;
+    int parts_per_pkt;                 // > 1 (only with pkts_per_unit == 1): every packet is cut into this many units
     int Amax, Pmax;                    // over the listed channels (sizes the shared-memory regions)
     int* d_ticket;                     // one int, zero before the launch
     int* d_done;                       // [n_channels] zero before the launch (indexed like d_desc)
