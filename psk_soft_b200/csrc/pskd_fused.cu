@@ -1215,7 +1215,8 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     if (ctas_per_sm == 0) {
         e = cudaFuncSetAttribute(k_fused<S, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_fused<S, PC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        static const int carve = getenv("PSKD_FZ_CARVEOUT") ? atoi(getenv("PSKD_FZ_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;   // tuning: % of the maximum
+        e = cudaFuncSetAttribute(k_fused<S, PC>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fused<S, PC>, FZ_WARPS * 32, smem);
         if (e != cudaSuccess) return e;
