@@ -46,7 +46,11 @@ namespace pskd {
 constexpr int FZ_WARPS = PSKD_FZ_WARPS; // warps (= concurrent units) per CTA
 constexpr int FZ_CH = 32;              // rows per chunk
 constexpr int FZ_B = 128;              // symbols per chain block (4 per lane)
-constexpr int FZ_BUF = 160;            // capacity of the (theta, sample) block buffer
+#ifndef PSKD_FZ_BLOCKS
+#define PSKD_FZ_BLOCKS 1
+#endif
+constexpr int FZ_BLOCKS = PSKD_FZ_BLOCKS;               // chain blocks the front stage collects before the chain/back stage runs
+constexpr int FZ_BUF = FZ_BLOCKS * FZ_B + 32;          // capacity of the (theta, sample) block buffer
 constexpr int FZ_MAX_ITERS = 16;
 #ifndef PSKD_FZ_PF
 #define PSKD_FZ_PF 2
@@ -1037,7 +1041,7 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
     bool inflight = cx.inflight != 0;
     const int nchunks = cx.nchunks, c_lo = cx.c_lo, c_hi = cx.c_hi, lag = cx.lag;
     const int kA = cx.kA, kB = cx.kB, M = cx.M;
-    const int want = min(FZ_B, cx.pk_hi - cx.kchain);
+    const int want = min(FZ_BLOCKS * FZ_B, cx.pk_hi - cx.kchain);
     const bool m_ok = (M == 2 || M == 4 || M == 8);
     const float2* in_mt = cx.in_mt;
     int16_t* o_sidx = cx.o_sidx;
