@@ -689,7 +689,8 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             FusedLaunch f{};
             f.S = g.S; f.d_list = b->d_list + g.first; f.n_list = g.count;
             // a unit = enough consecutive packets for >= ~4096 symbols
-            const long long ppu = std::max<long long>(1, (4096LL * g.S + g.pkt_len_min - 1) / g.pkt_len_min);
+            static const long long unit_syms = getenv("PSKD_FUSED_UNIT") ? std::max(256, atoi(getenv("PSKD_FUSED_UNIT"))) : 4096;
+            const long long ppu = std::max<long long>(1, (unit_syms * g.S + g.pkt_len_min - 1) / g.pkt_len_min);
             f.pkts_per_unit = (int)std::min<long long>(ppu, 1 << 20);
             // ONE long packet per channel and call (the packet-by-packet use behind serviceFunction): the packet is
             // cut into parts of >= ~2048 symbols, so that a 4096-channel bank is not 4096 units over 2960 resident
