@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSKD_ABI_VERSION 1
+#define PSKD_ABI_VERSION 2
 
 /* ---- return codes.  Mirrors the reference's conventions: serviceFunction returns NORMAL for
  * every packet it consumed, including ones it ignores (cpp/psk_soft.cpp:359-363,617); problems
@@ -166,6 +166,8 @@ typedef struct pskd_kernel_time {
     char     name[32];
     double   ms_total;     /* summed event-to-event time of this kernel's launches */
     uint64_t launches;
+    double   alg_bytes;    /* algorithmic bytes (8 N in + per symbol 8 soft + 4 phase + 2 sampleIndex + 2 b bits, split per
+                              stage) of the channels those launches served: alg_bytes / ms_total is the kernel's roofline rate */
 } pskd_kernel_time;
 int pskd_profile_enable(pskd_handle h, int on);
 /* waits for the stream, then copies up to cap entries; *n = entries available; reset != 0 zeroes them */
@@ -187,6 +189,9 @@ typedef struct pskd_synth {
     float    freq_max;     /* per-channel carrier offset drawn uniformly in +-freq_max cycles/sample */
     float    pn_sigma;     /* phase-noise amplitude (rad), slow pseudo-random wander */
     float    shaped;       /* 1: envelope 0.6+0.4*sin(pi*(p+.5)/S), 0: rectangular pulses */
+    uint32_t period;       /* > 0: the carrier offset of every channel is rounded to a multiple of 1/(constelationSize*period)
+                              cycles/sample, so that the M-th power phase of a buffer of `period` samples continues seamlessly
+                              when the buffer is replayed (bench.py replays one resident buffer with carried state) */
 } pskd_synth;
 
 /* fills iq_dev[c][0..n_complex) (device memory, stride in complex samples) for channels

@@ -81,9 +81,11 @@ class Bank:
 
     # -- property surface ------------------------------------------------------------------
     def set_props(self, ch: int = -1, **props):
-        cur = self.get_props(0 if ch < 0 else ch)
-        cur.update({k: int(v) for k, v in props.items()})
-        self._check(self.lib.pskd_set_props(self._h, int(ch), C.byref(_to_props(cur))))
+        """Change the named properties of channel `ch` (-1: of every channel, each keeping its other properties)."""
+        for c in (range(self.n_channels) if ch < 0 else (ch,)):
+            cur = self.get_props(c)
+            cur.update({k: int(v) for k, v in props.items()})
+            self._check(self.lib.pskd_set_props(self._h, int(c), C.byref(_to_props(cur))))
 
     def get_props(self, ch: int = 0) -> dict:
         p = B.Props()
@@ -107,11 +109,11 @@ class Bank:
         self._check(self.lib.pskd_profile_enable(self._h, int(on)))
 
     def profile_read(self, reset: bool = True) -> dict:
-        """{kernel name: (total ms, launches)} measured with CUDA events on the bank's stream."""
-        arr = (B.KernelTime * 16)()
+        """{kernel name: (total ms, launches, algorithmic bytes)} measured with CUDA events on the bank's stream."""
+        arr = (B.KernelTime * 24)()
         n = C.c_int(0)
-        self._check(self.lib.pskd_profile_read(self._h, arr, 16, C.byref(n), int(reset)))
-        return {arr[i].name.decode(): (arr[i].ms_total, int(arr[i].launches)) for i in range(min(n.value, 16))}
+        self._check(self.lib.pskd_profile_read(self._h, arr, 24, C.byref(n), int(reset)))
+        return {arr[i].name.decode(): (arr[i].ms_total, int(arr[i].launches), float(arr[i].alg_bytes)) for i in range(min(n.value, 24))}
 
     # -- checkpoint / resume -----------------------------------------------------------------
     def export_state(self) -> bytes:
@@ -222,10 +224,11 @@ class PskSoft:
 
 def synth_fill(iq_dev_ptr: int, iq_stride: int, ch0: int, n_channels: int, n_complex: int, *, seed: int,
                samplesPerBaud: int, constelationSize: int, sigma: float = 0.02, freq_max: float = 2e-5,
-               pn_sigma: float = 0.0, shaped: bool = True, device: int = 0, stream: int = 0):
-    """Fill a device buffer with a synthetic PSK channel bank (see include/pskd.h: pskd_synth_fill)."""
+               pn_sigma: float = 0.0, shaped: bool = True, device: int = 0, stream: int = 0, period: int = 0):
+    """Fill a device buffer with a synthetic PSK channel bank (see include/pskd.h: pskd_synth_fill).
+    period > 0: carrier offsets quantised so that a buffer of `period` samples can be replayed as one continuous stream."""
     lib = B.load()
-    cfg = B.Synth(seed, samplesPerBaud, constelationSize, sigma, freq_max, pn_sigma, 1.0 if shaped else 0.0)
+    cfg = B.Synth(seed, samplesPerBaud, constelationSize, sigma, freq_max, pn_sigma, 1.0 if shaped else 0.0, int(period))
     rc = lib.pskd_synth_fill(device, iq_dev_ptr, int(iq_stride), int(ch0), int(n_channels), int(n_complex),
                              C.byref(cfg), stream or None)
     if rc != 0:

@@ -51,12 +51,13 @@ class Stats(C.Structure):
 
 
 class KernelTime(C.Structure):
-    _fields_ = [("name", C.c_char * 32), ("ms_total", C.c_double), ("launches", C.c_uint64)]
+    _fields_ = [("name", C.c_char * 32), ("ms_total", C.c_double), ("launches", C.c_uint64), ("alg_bytes", C.c_double)]
 
 
 class Synth(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("samplesPerBaud", C.c_uint16), ("constelationSize", C.c_uint16),
-                ("sigma", C.c_float), ("freq_max", C.c_float), ("pn_sigma", C.c_float), ("shaped", C.c_float)]
+                ("sigma", C.c_float), ("freq_max", C.c_float), ("pn_sigma", C.c_float), ("shaped", C.c_float),
+                ("period", C.c_uint32)]
 
 
 _lib = None

@@ -19,6 +19,10 @@
 
 using namespace pskd;
 
+static constexpr int MAX_SLABS = 64, RING = 3;
+static constexpr int FUSED_TICKETS = 4 * MAX_SLABS, FZS_TICKETS = 16 * MAX_SLABS;
+static constexpr long long STALL_CAP = 32768;    // samples kept of a stalled (over-full) timing window; > every admissible numAvg*samplesPerBaud
+
 static thread_local std::string g_last_error;
 
 static int fail(int code, const char* fmt, ...) {
@@ -57,7 +61,8 @@ struct DevBuf {
 struct ChanHost {
     pskd_props props;          // as configured (live)
     pskd_props latched;        // as used by the last process call
-    long long tail_len = 0;    // samples.size() between calls
+    long long tail_len = 0;    // samples of the window held on the device between calls (= samples.size() unless stalled)
+    long long win_size = 0;    // samples.size() between calls (grows without bound while the component is stalled)
     bool resetNumSymbols = true, resetPhaseAvg = true, resetSamplesPerBaud = true;   // cpp/psk_soft.cpp:191-193
     size_t symbolEnergySize = 10;   // symbolEnergy.size() (cpp/psk_soft.cpp:189), for the listener at :640
     bool first_packet = true;
@@ -65,6 +70,9 @@ struct ChanHost {
     long long tail_off = 0;    // element offset of this channel's tail region
     long long tail_cap = 0;
     pskd_sri_out sri{};
+    // what the host knows about the device-side LinearFit history (time-parallel plan without a sequential head)
+    long long hist_syms = 0;   // symbols pushed into the history since it was last cleared
+    double last_xdelta = 0.0;  // SRI.xdelta of the previous call (a change clears the history, cpp/psk_soft.cpp:91-102)
 };
 
 struct pskd_bank {
@@ -88,18 +96,24 @@ struct pskd_bank {
     unsigned long long launches = 0;
     pskd_stats stats{};
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host-buffer mode: H2D / D2H overlap the kernels slab by slab
-    cudaEvent_t slab_in[16] = {nullptr}, slab_done[16] = {nullptr};
+    // ring of staging slots (host-buffer mode): slot r was filled (ev_h2d), consumed by the kernels (ev_kern), emptied (ev_d2h)
+    cudaEvent_t ev_h2d[RING] = {nullptr}, ev_kern[RING] = {nullptr}, ev_d2h[RING] = {nullptr};
+    unsigned long long slab_seq = 0;     // slabs issued so far (ring position continues across calls)
+    long long slab_bytes = 256LL << 20;  // host-buffer mode: staging per slab (PSKD_SLAB_MB)
+    int tp_max_channels = 2048;          // auto: time-parallel chain for launches of at most this many scan-chain channels (PSKD_TP_MAX)
     int chain_mode = 0;        // 0 auto (scan-based where possible), 1 force the sequential chain (PSKD_CHAIN=seq)
     int fused_mode = -1;       // -1 auto (large banks), 0 never, 1 whenever a channel qualifies (PSKD_FUSED)
-    int host_slabs = 16;       // host-buffer mode: channel slabs the H2D / kernels / D2H pipeline works through (PSKD_SLABS, 1..16)
+    int host_slabs = MAX_SLABS; // host-buffer mode: most channel slabs one call is cut into (PSKD_SLABS, 1..MAX_SLABS)
     int fused_min_channels = 1152;   // auto: channels per launch from which the fused kernel beats the staged ones (measured crossover ~1120 for 1M-sample 8-PSK calls; PSKD_FUSED_MIN)
     int* d_list = nullptr;     // fused launch lists (channel indices), one segment per (slab, samplesPerBaud)
     int* h_list_slot[2] = {nullptr, nullptr};
     int* d_done = nullptr;     // [n_channels] units completed per channel in the current call
-    int* d_ticket = nullptr;   // [16 slabs x 4 samplesPerBaud values] unit ticket counters
+    int* d_ticket = nullptr;   // [16 slabs x 4 samplesPerBaud values] unit ticket counters of k_fused, then FZS_TICKETS for the k_fzs_* launches
+    int fzs_ticket_next = 0;
+    int fzs_mode = 1;          // staged path through the fused kernel's stages (k_fzs_front + k_fzs_cb) where a channel qualifies (PSKD_FZS=0: legacy staged kernels)
     int tp_mode = -1;          // time-parallel chain of the staged path: -1 auto (few channels, many packets), 0 never, 1 whenever possible (PSKD_TP)
     DevBuf<TpItem> tp_items; DevBuf<TpChan> tp_chans; DevBuf<TpPacket> tp_pkts; DevBuf<TpEnd> tp_ends;
-    DevBuf<float> tp_end_ring, tp_start_ring; DevBuf<int> tp_fail;
+    DevBuf<float> tp_end_ring, tp_start_ring; DevBuf<int> tp_fail, tp_slot_flags;
     Profiler prof;
 };
 
@@ -123,10 +137,12 @@ static int check_props(const pskd_props& p) {
 static int bpb_of(int M) { return M == 2 ? 1 : M == 4 ? 2 : M == 8 ? 3 : 0; }
 
 // (re)allocate the carried-tail regions so every channel can hold S*A samples (+ one symbol of slack)
-static int ensure_tails(pskd_bank* b) {
+static int ensure_tails(pskd_bank* b, const std::vector<long long>* min_cap = nullptr) {
     bool grow = false;
-    for (auto& c : b->ch) {
+    for (int i = 0; i < b->n_channels; i++) {
+        auto& c = b->ch[i];
         long long need = (long long)c.props.samplesPerBaud * c.props.numAvg + c.props.samplesPerBaud;
+        if (min_cap) need = std::max(need, (*min_cap)[i]);
         if (need > c.tail_cap) grow = true;
     }
     if (!grow) return PSKD_OK;
@@ -135,21 +151,27 @@ static int ensure_tails(pskd_bank* b) {
     for (int i = 0; i < b->n_channels; i++) {
         auto& c = b->ch[i];
         long long need = (long long)c.props.samplesPerBaud * c.props.numAvg + c.props.samplesPerBaud;
+        if (min_cap) need = std::max(need, (*min_cap)[i]);
         new_cap[i] = std::max(need, c.tail_cap);
         new_off[i] = total;
         total += (new_cap[i] + 1) & ~1LL;     // keep 16-byte alignment of every region
     }
     float2* nt[2] = {nullptr, nullptr};
     CUDA_TRY(cudaMalloc((void**)&nt[0], std::max<long long>(total, 1) * sizeof(float2)));
-    CUDA_TRY(cudaMalloc((void**)&nt[1], std::max<long long>(total, 1) * sizeof(float2)));
+    {
+        cudaError_t e1 = cudaMalloc((void**)&nt[1], std::max<long long>(total, 1) * sizeof(float2));
+        if (e1 != cudaSuccess) { cudaFree(nt[0]); CUDA_TRY(e1); }
+    }
     if (b->d_tail[0]) {
-        for (int i = 0; i < b->n_channels; i++) {
+        cudaError_t e1 = cudaSuccess;
+        for (int i = 0; i < b->n_channels && e1 == cudaSuccess; i++) {
             auto& c = b->ch[i];
             if (c.tail_len > 0)
-                CUDA_TRY(cudaMemcpyAsync(nt[b->tail_cur] + new_off[i], b->d_tail[b->tail_cur] + c.tail_off,
-                                         c.tail_len * sizeof(float2), cudaMemcpyDeviceToDevice, b->stream));
+                e1 = cudaMemcpyAsync(nt[b->tail_cur] + new_off[i], b->d_tail[b->tail_cur] + c.tail_off,
+                                     c.tail_len * sizeof(float2), cudaMemcpyDeviceToDevice, b->stream);
         }
-        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(b->stream);
+        if (e1 != cudaSuccess) { cudaFree(nt[0]); cudaFree(nt[1]); CUDA_TRY(e1); }
         cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]);
     }
     b->d_tail[0] = nt[0]; b->d_tail[1] = nt[1]; b->tail_total = total;
@@ -162,6 +184,8 @@ static int ensure_rings(pskd_bank* b) {
     for (auto& c : b->ch) maxP = std::max<int>(maxP, c.props.phaseAvg);
     int need = 2 * maxP;                       // second half is the repack spare (GlobalRing::repack)
     if (need <= b->ring_cap) return PSKD_OK;
+    if ((long long)need * b->n_channels > 0x7fffffffLL)     // ChanDesc::ring_off and the kernels index the rings with 32-bit offsets
+        return fail(PSKD_ERR_UNSUPPORTED, "phaseAvg=%d x %d channels: the history rings exceed 2^31 floats", maxP, b->n_channels);
     float* nr = nullptr;
     CUDA_TRY(cudaMalloc((void**)&nr, (size_t)need * b->n_channels * sizeof(float)));
     CUDA_TRY(cudaMemsetAsync(nr, 0, (size_t)need * b->n_channels * sizeof(float), b->stream));
@@ -202,16 +226,20 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     if (const char* e = getenv("PSKD_CHAIN")) b->chain_mode = (strcmp(e, "seq") == 0) ? 1 : 0;
     if (const char* e = getenv("PSKD_FUSED")) b->fused_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
     if (const char* e = getenv("PSKD_FUSED_MIN")) b->fused_min_channels = std::max(1, atoi(e));
-    if (const char* e = getenv("PSKD_SLABS")) b->host_slabs = std::min(16, std::max(1, atoi(e)));
+    if (const char* e = getenv("PSKD_SLABS")) b->host_slabs = std::min(MAX_SLABS, std::max(1, atoi(e)));
+    if (const char* e = getenv("PSKD_SLAB_MB")) b->slab_bytes = (long long)std::max(1, atoi(e)) << 20;
+    if (const char* e = getenv("PSKD_TP_MAX")) b->tp_max_channels = std::max(1, atoi(e));
     if (const char* e = getenv("PSKD_TP")) b->tp_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
+    if (const char* e = getenv("PSKD_FZS")) b->fzs_mode = atoi(e) != 0;
     cudaError_t e;
 #define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
     CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CT(cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
     CT(cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 16; i++) {
-        CT(cudaEventCreateWithFlags(&b->slab_in[i], cudaEventDisableTiming));
-        CT(cudaEventCreateWithFlags(&b->slab_done[i], cudaEventDisableTiming));
+    for (int i = 0; i < RING; i++) {
+        CT(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming));
+        CT(cudaEventCreateWithFlags(&b->ev_kern[i], cudaEventDisableTiming));
+        CT(cudaEventCreateWithFlags(&b->ev_d2h[i], cudaEventDisableTiming));
     }
     CT(cudaMalloc((void**)&b->d_desc, sizeof(ChanDesc) * n_channels));
     for (int i = 0; i < 2; i++) {
@@ -221,7 +249,7 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     }
     CT(cudaMalloc((void**)&b->d_list, sizeof(int) * n_channels));
     CT(cudaMalloc((void**)&b->d_done, sizeof(int) * n_channels));
-    CT(cudaMalloc((void**)&b->d_ticket, sizeof(int) * 64));
+    CT(cudaMalloc((void**)&b->d_ticket, sizeof(int) * (FUSED_TICKETS + FZS_TICKETS)));
     b->h_desc = b->h_desc_slot[0];
     CT(cudaMalloc((void**)&b->d_state, sizeof(ChanState) * n_channels));
     CT(cudaMalloc((void**)&b->d_counters, sizeof(DevCounters)));
@@ -249,7 +277,9 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
 int pskd_destroy(pskd_handle b) {
     if (!b) return PSKD_OK;
     cudaSetDevice(b->device);
+    if (b->copy_in) cudaStreamSynchronize(b->copy_in);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    if (b->copy_out) cudaStreamSynchronize(b->copy_out);
     cudaFree(b->d_desc);
     for (int i = 0; i < 2; i++) { if (b->h_desc_slot[i]) cudaFreeHost(b->h_desc_slot[i]); if (b->h_list_slot[i]) cudaFreeHost(b->h_list_slot[i]); if (b->desc_ev[i]) cudaEventDestroy(b->desc_ev[i]); }
     cudaFree(b->d_list); cudaFree(b->d_done); cudaFree(b->d_ticket);
@@ -258,9 +288,9 @@ int pskd_destroy(pskd_handle b) {
     b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
     b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release();
     b->tp_items.release(); b->tp_chans.release(); b->tp_pkts.release(); b->tp_ends.release();
-    b->tp_end_ring.release(); b->tp_start_ring.release(); b->tp_fail.release();
+    b->tp_end_ring.release(); b->tp_start_ring.release(); b->tp_fail.release(); b->tp_slot_flags.release();
     b->prof.destroy();
-    for (int i = 0; i < 16; i++) { if (b->slab_in[i]) cudaEventDestroy(b->slab_in[i]); if (b->slab_done[i]) cudaEventDestroy(b->slab_done[i]); }
+    for (int i = 0; i < RING; i++) for (cudaEvent_t e : {b->ev_h2d[i], b->ev_kern[i], b->ev_d2h[i]}) if (e) cudaEventDestroy(e);
     if (b->copy_in) cudaStreamDestroy(b->copy_in);
     if (b->copy_out) cudaStreamDestroy(b->copy_out);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -303,7 +333,9 @@ uint64_t pskd_launch_count(pskd_handle b) { return b ? b->launches : 0; }
 int pskd_sync(pskd_handle b) {
     if (!b) return fail(PSKD_ERR_ARG, "null handle");
     CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaStreamSynchronize(b->copy_in));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->copy_out));       // host-buffer calls with PSKD_FLAG_NO_SYNC: the outputs are on the host now
     return PSKD_OK;
 }
 
@@ -324,12 +356,12 @@ int pskd_profile_read(pskd_handle b, pskd_kernel_time* out, int cap, int* n, int
         if (out && k < cap) {
             memset(&out[k], 0, sizeof(out[k]));
             strncpy(out[k].name, kernel_name(i), sizeof(out[k].name) - 1);
-            out[k].ms_total = b->prof.ms[i]; out[k].launches = b->prof.launches[i];
+            out[k].ms_total = b->prof.ms[i]; out[k].launches = b->prof.launches[i]; out[k].alg_bytes = b->prof.bytes[i];
         }
         k++;
     }
     *n = k;
-    if (reset) for (int i = 0; i < KID_COUNT; i++) { b->prof.ms[i] = 0; b->prof.launches[i] = 0; }
+    if (reset) for (int i = 0; i < KID_COUNT; i++) { b->prof.ms[i] = 0; b->prof.launches[i] = 0; b->prof.bytes[i] = 0; }
     return PSKD_OK;
 }
 
@@ -409,21 +441,72 @@ int pskd_state_export(pskd_handle b, void* host_buf, size_t cap, size_t* written
 
 int pskd_state_import(pskd_handle b, const void* host_buf, size_t n_bytes) {
     if (!b || !host_buf || n_bytes < sizeof(StateHeader)) return fail(PSKD_ERR_ARG, "pskd_state_import: bad arguments");
-    const unsigned char* p = static_cast<const unsigned char*>(host_buf);
+    const unsigned char* p0 = static_cast<const unsigned char*>(host_buf);
     StateHeader h;
-    memcpy(&h, p, sizeof(h)); p += sizeof(h);
+    memcpy(&h, p0, sizeof(h));
     if (h.magic != STATE_MAGIC || h.version != STATE_VERSION) return fail(PSKD_ERR_ARG, "pskd_state_import: not a pskd state blob (or another version)");
     if (h.n_channels != b->n_channels) return fail(PSKD_ERR_ARG, "pskd_state_import: blob has %d channels, bank has %d", h.n_channels, b->n_channels);
-    if (h.total_bytes > n_bytes || h.ring_cap < 0) return fail(PSKD_ERR_ARG, "pskd_state_import: truncated blob");
+    const int nch = b->n_channels;
+    // ---- validate EVERYTHING against the blob's own size before a single byte reaches the bank ----
+    if (h.ring_cap < 2 || h.ring_cap > 2 * 65535 || (h.ring_cap & 1)) return fail(PSKD_ERR_ARG, "pskd_state_import: corrupt blob (history ring of %d floats)", h.ring_cap);
+    const size_t fixed = sizeof(StateHeader) + (size_t)nch * (sizeof(StateChan) + (size_t)h.ring_cap * sizeof(float));
+    if (h.total_bytes > n_bytes || h.total_bytes < fixed) return fail(PSKD_ERR_ARG, "pskd_state_import: truncated blob");
+    std::vector<StateChan> sc(nch);
+    memcpy(sc.data(), p0 + sizeof(StateHeader), sizeof(StateChan) * nch);
+    size_t expect = fixed;
+    int maxP = 1;
+    for (int i = 0; i < nch; i++) {
+        const StateChan& c = sc[i];
+        int rc = check_props(c.props);
+        if (rc != PSKD_OK) return rc;
+        const long long cap = std::max((long long)c.props.samplesPerBaud * c.props.numAvg + c.props.samplesPerBaud, STALL_CAP);
+        if (c.tail_len < 0 || c.tail_len > cap) return fail(PSKD_ERR_ARG, "pskd_state_import: channel %d: carried window of %lld samples does not fit its properties", i, c.tail_len);
+        const FitState& f = c.dev.fit;
+        if (c.fit_n < 1 || c.fit_n > 65535 || f.n != c.fit_n || 2 * f.n > h.ring_cap || f.pts < 0 || f.pts > f.n || f.head < 0 || f.head >= f.n ||
+            f.count < 0 || f.count > 1048576)
+            return fail(PSKD_ERR_ARG, "pskd_state_import: channel %d: corrupt LinearFit state (n %d pts %d head %d)", i, f.n, f.pts, f.head);
+        maxP = std::max(maxP, std::max<int>(c.props.phaseAvg, f.n));
+        expect += (size_t)c.tail_len * sizeof(float2);
+    }
+    if (expect != h.total_bytes) return fail(PSKD_ERR_ARG, "pskd_state_import: blob is %llu bytes, its contents need %zu", (unsigned long long)h.total_bytes, expect);
+    if ((long long)nch * std::max(2 * maxP, h.ring_cap) > 0x7fffffffLL) return fail(PSKD_ERR_UNSUPPORTED, "pskd_state_import: history rings exceed 2^31 floats");
     CUDA_TRY(cudaSetDevice(b->device));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
-    const int nch = b->n_channels;
-    std::vector<StateChan> sc(nch);
-    memcpy(sc.data(), p, sizeof(StateChan) * nch); p += sizeof(StateChan) * nch;
-    for (int i = 0; i < nch; i++) {
-        int rc = check_props(sc[i].props);
-        if (rc != PSKD_OK) return rc;
-        if (sc[i].tail_len < 0) return fail(PSKD_ERR_ARG, "pskd_state_import: corrupt blob");
+    // ---- make room (capacities only grow; the bank's own state is still untouched and consistent) ----
+    const std::vector<ChanHost> saved = b->ch;
+    for (int i = 0; i < nch; i++) b->ch[i].props = sc[i].props;       // sizes the tail regions and the rings
+    std::vector<long long> tail_need(nch);
+    for (int i = 0; i < nch; i++) tail_need[i] = sc[i].tail_len;
+    int rc = ensure_tails(b, &tail_need);
+    if (rc == PSKD_OK) rc = ensure_rings(b);
+    if (rc == PSKD_OK && h.ring_cap > b->ring_cap) {                  // blob written by a bank with a longer history ring
+        // grow to the blob's ring: ensure_rings sizes from phaseAvg, so ask for it explicitly
+        float* nr = nullptr;
+        if (cudaMalloc((void**)&nr, (size_t)h.ring_cap * nch * sizeof(float)) != cudaSuccess) { (void)cudaGetLastError(); rc = fail(PSKD_ERR_NOMEM, "pskd_state_import: out of device memory"); }
+        else { cudaFree(b->d_ring); b->d_ring = nr; b->ring_cap = h.ring_cap; }
+    }
+    if (rc != PSKD_OK) { for (int i = 0; i < nch; i++) b->ch[i].props = saved[i].props; return rc; }
+    // ---- commit: device state first (stream-ordered copies from the caller's buffer), then the host view ----
+    std::vector<ChanState> dev(nch);
+    for (int i = 0; i < nch; i++) dev[i] = sc[i].dev;
+    const unsigned char* p = p0 + sizeof(StateHeader) + sizeof(StateChan) * nch;
+    cudaError_t e = cudaMemcpy(b->d_state, dev.data(), sizeof(ChanState) * nch, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(b->d_ring, 0, (size_t)b->ring_cap * nch * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMemcpy2D(b->d_ring, (size_t)b->ring_cap * sizeof(float), p, (size_t)h.ring_cap * sizeof(float),
+                         (size_t)h.ring_cap * sizeof(float), nch, cudaMemcpyHostToDevice);
+    p += (size_t)nch * h.ring_cap * sizeof(float);
+    for (int i = 0; i < nch && e == cudaSuccess; i++) {
+        const long long tl = sc[i].tail_len;
+        if (tl > 0) {
+            e = cudaMemcpy(b->d_tail[b->tail_cur] + b->ch[i].tail_off, p, (size_t)tl * sizeof(float2), cudaMemcpyHostToDevice);
+            p += (size_t)tl * sizeof(float2);
+        }
+    }
+    if (e != cudaSuccess) {
+        // a CUDA failure half-way leaves the device state undefined: make the bank say so on its next use
+        for (int i = 0; i < nch; i++) { b->ch[i] = saved[i]; b->ch[i].props.resetState = 1; b->ch[i].tail_len = 0; }
+        return fail(PSKD_ERR_CUDA, "pskd_state_import: %s; the bank was reset", cudaGetErrorString(e));
     }
     for (int i = 0; i < nch; i++) {
         ChanHost& c = b->ch[i];
@@ -431,27 +514,8 @@ int pskd_state_import(pskd_handle b, const void* host_buf, size_t n_bytes) {
         c.resetNumSymbols = sc[i].resetNumSymbols != 0; c.resetPhaseAvg = sc[i].resetPhaseAvg != 0;
         c.resetSamplesPerBaud = sc[i].resetSamplesPerBaud != 0; c.first_packet = sc[i].first_packet != 0;
         c.fit_n = sc[i].fit_n; c.symbolEnergySize = (size_t)sc[i].symbolEnergySize; c.sri = sc[i].sri;
-        c.tail_len = 0;          // set below once the regions are large enough
-    }
-    int rc = ensure_tails(b);
-    if (rc == PSKD_OK) rc = ensure_rings(b);
-    if (rc != PSKD_OK) return rc;
-    if (h.ring_cap > b->ring_cap) return fail(PSKD_ERR_ARG, "pskd_state_import: history ring of the blob does not fit the bank");
-    std::vector<ChanState> dev(nch);
-    for (int i = 0; i < nch; i++) dev[i] = sc[i].dev;
-    CUDA_TRY(cudaMemcpy(b->d_state, dev.data(), sizeof(ChanState) * nch, cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy2D(b->d_ring, (size_t)b->ring_cap * sizeof(float), p, (size_t)h.ring_cap * sizeof(float),
-                          (size_t)h.ring_cap * sizeof(float), nch, cudaMemcpyHostToDevice));
-    p += (size_t)nch * h.ring_cap * sizeof(float);
-    for (int i = 0; i < nch; i++) {
-        ChanHost& c = b->ch[i];
-        const long long tl = sc[i].tail_len;
-        if (tl > c.tail_cap) return fail(PSKD_ERR_ARG, "pskd_state_import: carried window of channel %d does not fit", i);
-        if (tl > 0) {
-            CUDA_TRY(cudaMemcpy(b->d_tail[b->tail_cur] + c.tail_off, p, (size_t)tl * sizeof(float2), cudaMemcpyHostToDevice));
-            p += (size_t)tl * sizeof(float2);
-        }
-        c.tail_len = tl;
+        c.tail_len = sc[i].tail_len; c.win_size = sc[i].tail_len;
+        c.hist_syms = 0; c.last_xdelta = 0.0;       // not part of the blob: the next call plans conservatively
     }
     return PSKD_OK;
 }
@@ -461,7 +525,6 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     if (!in->iq && (in->n_complex || in->n_complex_all)) return fail(PSKD_ERR_ARG, "pskd_process: iq is NULL");
     const int nch = b->n_channels;
     const bool host_bufs = (in->flags & PSKD_FLAG_HOST_BUFFERS) != 0;
-    if (host_bufs && (in->flags & PSKD_FLAG_NO_SYNC)) return fail(PSKD_ERR_ARG, "PSKD_FLAG_NO_SYNC needs device buffers");
     CUDA_TRY(cudaSetDevice(b->device));
 
     // ---- packet prologue, bank-wide (cpp/psk_soft.cpp:353-372) -------------------------------
@@ -479,9 +542,38 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             c.props.resetState = 0;
         }
     }
-    int rc = ensure_tails(b);
-    if (rc != PSKD_OK) return rc;
-    rc = ensure_rings(b);
+    // ---- the timing window at the packet start: resyncEnergy and the stall (cpp/psk_soft.cpp:380-383, 408-412,
+    // 457, 619-636).  resyncEnergy runs when asked for, or whenever the window is not full (every packet in
+    // steady state); its observable effects are the truncation of an over-full window to its OLDEST numDataPts
+    // samples and symbolEnergy.size().  A window that is full or over-full at the packet start (after numAvg *
+    // samplesPerBaud shrank) never emits again -- `samples.size() == numDataPts` (:457) cannot become true while the
+    // deque only grows -- until the window length grows past the deque size: the component keeps consuming packets
+    // and emits nothing.  That stall is emulated: the deque size is tracked, its first STALL_CAP samples are kept
+    // (they are what a later, longer window would contain; a deque beyond every admissible window length can never
+    // recover, so nothing more needs to be stored).
+    std::vector<unsigned char> stalled(nch, 0), resync_asked(nch, 0);
+    {
+        std::vector<long long> cap_need(nch, 0);
+        bool any_stall = false;
+        for (int i = 0; i < nch; i++) {
+            ChanHost& c = b->ch[i];
+            const long long n_in = (long long)(in->n_complex ? in->n_complex[i] : in->n_complex_all);
+            const long long numDataPts = (long long)c.props.samplesPerBaud * c.props.numAvg;
+            resync_asked[i] = c.resetSamplesPerBaud;
+            if (c.resetSamplesPerBaud || numDataPts > c.win_size) {
+                if (c.win_size > numDataPts) { c.win_size = numDataPts; c.tail_len = std::min(c.tail_len, numDataPts); }
+                c.symbolEnergySize = c.props.samplesPerBaud;
+                c.resetSamplesPerBaud = false;
+            }
+            if (c.win_size >= numDataPts && n_in > 0) {
+                stalled[i] = 1; any_stall = true;
+                if (c.tail_len == c.win_size) cap_need[i] = std::min(c.tail_len + n_in, STALL_CAP);
+            }
+        }
+        int rc0 = ensure_tails(b, any_stall ? &cap_need : nullptr);
+        if (rc0 != PSKD_OK) return rc0;
+    }
+    int rc = ensure_rings(b);
     if (rc != PSKD_OK) return rc;
 
     // ---- per-channel geometry ---------------------------------------------------------------
@@ -489,60 +581,49 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     b->h_desc = b->h_desc_slot[b->desc_slot];
     CUDA_TRY(cudaEventSynchronize(b->desc_ev[b->desc_slot]));   // previous upload from this slot is done
     long long Kmax = 0, scr_total = 0, nmax = 0;
-    int Smax = 2, Amax = 1, Pmax_fast = 1, n_fast = 0, n_seq = 0;
-    unsigned long long S_mask = 0, S_mask_fast = 0;
-    int Amax_fast = 1, Amin_fast = 1 << 30;
     bool any_nobits = false;
     const int next_tail = b->tail_cur ^ 1;
-    // host-buffer mode works through slabs of channels (H2D / kernels / D2H overlap); the fused
-    // kernel is chosen per launch, i.e. per slab
-    int n_slabs = 1;
-    if (host_bufs) {
-        long long nm = 0;
-        for (int i = 0; i < nch; i++) nm = std::max(nm, (long long)(in->n_complex ? in->n_complex[i] : in->n_complex_all));
-        n_slabs = std::min(nch, nm * (long long)nch >= (1 << 22) ? b->host_slabs : 1);
-    }
-    std::vector<unsigned char> fusable(nch, 0);
+    std::vector<unsigned char> fusable(nch, 0), fzsable(nch, 0);
     for (int i = 0; i < nch; i++) {
         ChanHost& c = b->ch[i];
         const long long n_in = (long long)(in->n_complex ? in->n_complex[i] : in->n_complex_all);
         if ((size_t)n_in > in->iq_stride && nch > 1) return fail(PSKD_ERR_ARG, "channel %d: n_complex > iq_stride", i);
         const int S = c.props.samplesPerBaud, A = (int)c.props.numAvg, M = c.props.constelationSize, P = c.props.phaseAvg;
-        const long long numDataPts = (long long)S * A;
-        // resyncEnergy (cpp/psk_soft.cpp:619-636): runs when asked for, or whenever the window is not
-        // full (:380-383, i.e. every packet in steady state).  Its only observable effects here are
-        // the truncation of an over-full window and symbolEnergy.size().
-        if (c.resetSamplesPerBaud || numDataPts > c.tail_len) {
-            if (c.tail_len > numDataPts) c.tail_len = numDataPts;
-            c.symbolEnergySize = S;
-            c.resetSamplesPerBaud = false;
-        }
-        if (c.tail_len >= numDataPts && n_in > 0)
-            return fail(PSKD_ERR_UNSUPPORTED, "channel %d: window over-full after a numAvg/samplesPerBaud decrease; the reference stalls "
-                        "forever here (cpp/psk_soft.cpp:457 never true again) -- not carried on the GPU path", i);
-        const long long total = c.tail_len + n_in;
-        long long K = total / S - A + 1;
-        if (K < 0) K = 0;
-        const long long pkt = in->packet_len ? (long long)in->packet_len : std::max<long long>(n_in, 1);
-        const long long npk = n_in > 0 ? (n_in + pkt - 1) / pkt : 0;
-        if (npk > 0x7fffffffLL) return fail(PSKD_ERR_ARG, "too many packets");
         ChanDesc& d = b->h_desc[i];
         d.in = host_bufs ? nullptr : reinterpret_cast<const float2*>(in->iq) + (size_t)i * in->iq_stride;
         d.tail = b->d_tail[b->tail_cur] + c.tail_off;
         d.tail_next = b->d_tail[next_tail] + c.tail_off;
-        d.n_in = n_in; d.tail_len = c.tail_len; d.K = K;
-        d.next_tail_len = total - K * S;
-        if (d.next_tail_len > c.tail_cap) return fail(PSKD_ERR_UNSUPPORTED, "channel %d: carried window exceeds its capacity", i);
-        d.sym_off = (long long)i * (long long)out->sym_stride;
-        d.bits_off = (long long)i * (long long)out->bits_stride;
-        d.pkt_len = pkt; d.n_pkts = (int)npk;
+        d.n_in = n_in; d.tail_len = c.tail_len;
         d.S = S; d.A = A; d.M = M; d.P = P; d.D = c.props.differentialDecoding ? 1 : 0; d.bpb = bpb_of(M);
         d.ring_off = i * b->ring_cap;
         d.flags = (c.resetNumSymbols ? CH_RESET_NUMSYMS : 0) | (c.resetPhaseAvg ? CH_RESET_PHASEAVG : 0);
+        d.sym_off = (long long)i * (long long)out->sym_stride;
+        d.bits_off = (long long)i * (long long)out->bits_stride;
+        long long K = 0;
+        if (stalled[i]) {
+            // consumes the packet(s), emits nothing.  The phase estimator's prologue / epilogue still run, but only
+            // they: one emulated packet when a reset is pending (its SRI block only with sriChanged / resetNumSymbols,
+            // :393), none otherwise (nothing of the carried state changes)
+            d.flags |= CH_STALLED | (((in->flags & PSKD_FLAG_SRI_CHANGED) || resync_asked[i]) ? CH_SRI_CHANGED : 0);
+            const bool pending = (d.flags & (CH_RESET_NUMSYMS | CH_RESET_PHASEAVG | CH_SRI_CHANGED)) != 0;
+            d.K = 0; d.pkt_len = std::max<long long>(n_in, 1); d.n_pkts = pending ? 1 : 0;
+            d.next_tail_len = (c.tail_len == c.win_size) ? std::min(c.tail_len + n_in, STALL_CAP) : c.tail_len;
+        } else {
+            const long long total = c.tail_len + n_in;
+            K = total / S - A + 1;
+            if (K < 0) K = 0;
+            const long long pkt = in->packet_len ? (long long)in->packet_len : std::max<long long>(n_in, 1);
+            const long long npk = n_in > 0 ? (n_in + pkt - 1) / pkt : 0;
+            if (npk > 0x7fffffffLL) return fail(PSKD_ERR_ARG, "too many packets");
+            d.K = K; d.pkt_len = pkt; d.n_pkts = (int)npk;
+            d.next_tail_len = total - K * S;
+        }
+        if (d.next_tail_len > c.tail_cap) return fail(PSKD_ERR_UNSUPPORTED, "channel %d: carried window exceeds its capacity", i);
         // the scan-based chain needs the history staged in shared memory and an unchanged window length
-        const bool fast = b->chain_mode == 0 && P <= CHAIN_PAR_PMAX && c.fit_n == P;
+        const bool fast = b->chain_mode == 0 && P <= CHAIN_PAR_PMAX && c.fit_n == P && !stalled[i];
         if (fast) d.flags |= CH_FAST;
         fusable[i] = fast && b->fused_mode != 0 && fused_supports(S, A, P) && K < (1LL << 30);
+        fzsable[i] = fast && b->fzs_mode != 0 && fzs_supports(S, A, P) && K < (1LL << 30);
         if (d.bpb == 0) any_nobits = true;
         if ((size_t)K > out->sym_stride && (out->soft || out->phase || out->sample_index))
             return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld symbols > sym_stride %zu", i, K, out->sym_stride);
@@ -550,6 +631,26 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld bits > bits_stride %zu", i, K * d.bpb, out->bits_stride);
         Kmax = std::max(Kmax, K); nmax = std::max(nmax, n_in);
     }
+
+    // ---- slabs.  Device buffers: one slab = the whole bank.  Host buffers: slabs of consecutive channels flow
+    // H2D (copy_in) -> kernels (stream) -> D2H (copy_out) through a RING of staging buffers, so the device memory
+    // the call needs is bounded by the slab size, not the bank size, and the transfers of neighbouring slabs (and of
+    // the next call, with PSKD_FLAG_NO_SYNC) overlap the kernels.
+    int n_slabs = 1;
+    size_t sym_stride = out->sym_stride, bits_stride = out->bits_stride, in_stride = 0;
+    if (host_bufs) {
+        sym_stride = (size_t)((Kmax + 7) & ~7LL); bits_stride = sym_stride * 3;
+        in_stride = (size_t)((nmax + 1) & ~1LL);
+        const long long per_ch = std::max<long long>(1, (long long)in_stride * 8 + (long long)sym_stride * 20);
+        long long ch_per_slab = std::max<long long>(1, b->slab_bytes / per_ch);
+        long long ns = (nch + ch_per_slab - 1) / ch_per_slab;
+        ns = std::min<long long>(std::min<long long>(ns, b->host_slabs), nch);
+        n_slabs = (int)std::max<long long>(ns, 1);
+    }
+    auto slab_lo = [&](int s) { return (int)((long long)s * nch / n_slabs); };
+    int slab_ch_max = 0;
+    for (int s = 0; s < n_slabs; s++) slab_ch_max = std::max(slab_ch_max, slab_lo(s + 1) - slab_lo(s));
+
     // ---- which channels take the fused kernel (per slab), which the staged kernels --------------
     struct FusedSeg { int slab, S, first, count, Amax, Pmax, max_pkts; long long pkt_len_min; };
     std::vector<FusedSeg> segs;
@@ -557,7 +658,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     int n_listed = 0;
     static const int fusedS[4] = {8, 9, 10, 16};
     for (int s = 0; s < n_slabs; s++) {
-        const int lo = (int)((long long)s * nch / n_slabs), hi = (int)((long long)(s + 1) * nch / n_slabs);
+        const int lo = slab_lo(s), hi = slab_lo(s + 1);
         int nf = 0;
         for (int i = lo; i < hi; i++) nf += fusable[i];
         const bool use = nf > 0 && (b->fused_mode == 1 || nf >= b->fused_min_channels);
@@ -576,80 +677,127 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             if (g.count) segs.push_back(g);
         }
     }
-    for (int i = 0; i < nch; i++) {
-        ChanDesc& d = b->h_desc[i];
-        if (d.flags & CH_FUSED) { d.scr_off = 0; continue; }
-        if (d.flags & CH_FAST) { n_fast++; Pmax_fast = std::max(Pmax_fast, d.P); } else n_seq++;
-        d.scr_off = scr_total;
-        scr_total += (d.K + 3) & ~3LL;
-        Smax = std::max(Smax, d.S); Amax = std::max(Amax, d.A);
-        if (d.K > 0) {
-            const bool front_fast = (d.S == 8 || d.S == 9 || d.S == 10 || d.S == 16) && d.A <= FRONT_FAST_AMAX;
-            if (front_fast) { d.flags |= CH_FRONT_FAST; S_mask_fast |= 1ull << d.S; Amax_fast = std::max(Amax_fast, d.A); Amin_fast = std::min(Amin_fast, d.A); }
-            else S_mask |= 1ull << d.S;
-        }
-    }
-    const bool any_staged = (n_fast + n_seq) > 0;
-
-    // ---- time-parallel chain plan (staged path): channels with many packets whose chain would otherwise
-    // run packet after packet on one warp.  Heads = packets before the first packet that is certain to start
-    // with a full history; one item per later packet.
+    // ---- per-slab summary of the staged channels + the time-parallel chain plan ---------------------
+    // Time-parallel plan (few channels with many packets, whose chain would otherwise run packet after packet on one
+    // warp): heads = packets before the first packet that is certain to start with a full history; one item per
+    // later packet.  Channel indices in the plan are slab-relative (the kernels of a slab see its channels only);
+    // packet slots and end records are numbered across the whole call.
+    struct SlabInfo {
+        int n_fast = 0, n_seq = 0, n_fzs = 0, Pmax_fast = 1, Pmax_fzs = 1, Smax = 2, Amax = 1, Amax_fast = 1, Amin_fast = 1 << 30;
+        unsigned long long S_mask = 0, S_mask_fast = 0, S_mask_fzs = 0;
+        long long Kmax = 0, Kmax_fzs = 0;
+        int head0 = 0, n_head = 0, item0 = 0, n_item = 0, chan0 = 0, n_chan = 0, n_slot = 0, tp_fzs = 0;
+    };
+    std::vector<SlabInfo> slabs(n_slabs);
     std::vector<TpItem> tp_heads, tp_items;
     std::vector<TpChan> tp_chans;
     int tp_slots = 0, tp_records = 0, tp_Pmax = 1;
-    if (b->tp_mode != 0 && (!host_bufs || n_slabs == 1) && n_fast > 0 && (b->tp_mode == 1 || n_fast <= 2048) && in->sri_xdelta != 1.0) {
-        for (int i = 0; i < nch; i++) {
+    static const bool headless_ok = !(getenv("PSKD_TP_HEADLESS") && atoi(getenv("PSKD_TP_HEADLESS")) == 0);
+    bool any_staged = false;
+    for (int s = 0; s < n_slabs; s++) {
+        const int lo = slab_lo(s), hi = slab_lo(s + 1);
+        SlabInfo& si = slabs[s];
+        long long scr_slab = 0;            // scratch is reused slab after slab (their kernels are ordered on one stream)
+        for (int i = lo; i < hi; i++) {
             ChanDesc& d = b->h_desc[i];
-            if (!(d.flags & CH_FAST) || (d.flags & CH_FUSED) || d.P < 2 || d.K <= 0) continue;
-            if (d.pkt_len / d.S - 1 < d.P + 2) continue;                   // every full packet must hold the whole history
-            int j0 = -1;
-            for (int j = 1; j < d.n_pkts; j++)
-                if (first_symbol_at((long long)j * d.pkt_len, d.tail_len, d.S, d.A, d.K) >= d.P) { j0 = j; break; }
-            if (j0 < 0 || d.n_pkts - j0 < (b->tp_mode == 1 ? 2 : 4)) continue;
-            d.flags |= CH_TP;
-            TpChan tc{i, j0, d.n_pkts, tp_records, tp_slots, 0};
-            tp_chans.push_back(tc);
-            tp_heads.push_back(TpItem{i, 0, j0, 0, -1, tp_records, -1, 0});
-            for (int j = j0; j < d.n_pkts; j++) {
-                const int rec = tp_records + 1 + (j - j0);
-                tp_items.push_back(TpItem{i, j, j + 1, j == j0 ? 2 : 1, tp_records, rec, tp_slots + (j - j0), 0});
+            if (host_bufs) { d.sym_off = (long long)(i - lo) * (long long)sym_stride; d.bits_off = (long long)(i - lo) * (long long)bits_stride; }
+            if (d.flags & CH_FUSED) { d.scr_off = 0; continue; }
+            any_staged = true;
+            if (d.flags & CH_FAST) si.n_fast++; else si.n_seq++;
+            d.scr_off = scr_slab;
+            scr_slab += (d.K + 3) & ~3LL;
+            si.Kmax = std::max(si.Kmax, d.K);
+            if (fzsable[i]) {              // staged, through the fused kernel's stages
+                d.flags |= CH_FZS;
+                si.n_fzs++; si.Pmax_fzs = std::max(si.Pmax_fzs, d.P); si.Kmax_fzs = std::max(si.Kmax_fzs, d.K);
+                if (d.K > 0) si.S_mask_fzs |= 1ull << d.S;
+                continue;
             }
-            tp_records += 1 + (d.n_pkts - j0);
-            tp_slots += d.n_pkts - j0;
-            tp_Pmax = std::max(tp_Pmax, d.P);
+            if (d.flags & CH_FAST) si.Pmax_fast = std::max(si.Pmax_fast, d.P);
+            si.Smax = std::max(si.Smax, d.S); si.Amax = std::max(si.Amax, d.A);
+            if (d.K > 0) {
+                const bool front_fast = (d.S == 8 || d.S == 9 || d.S == 10 || d.S == 16) && d.A <= FRONT_FAST_AMAX;
+                if (front_fast) { d.flags |= CH_FRONT_FAST; si.S_mask_fast |= 1ull << d.S; si.Amax_fast = std::max(si.Amax_fast, d.A); si.Amin_fast = std::min(si.Amin_fast, d.A); }
+                else si.S_mask |= 1ull << d.S;
+            }
         }
+        scr_total = std::max(scr_total, scr_slab);
+        si.head0 = (int)tp_heads.size(); si.item0 = (int)tp_items.size(); si.chan0 = (int)tp_chans.size();
+        if (b->tp_mode != 0 && si.n_fast > 0 && (b->tp_mode == 1 || si.n_fast <= b->tp_max_channels) && in->sri_xdelta != 1.0) {
+            for (int i = lo; i < hi; i++) {
+                ChanDesc& d = b->h_desc[i];
+                const ChanHost& c = b->ch[i];
+                if (!(d.flags & CH_FAST) || (d.flags & CH_FUSED) || d.P < 2 || d.K <= 0) continue;
+                if (d.pkt_len / d.S - 1 < d.P + 2) continue;                   // every full packet must hold the whole history
+                // No sequential head when the carried history is known to be full and nothing clears it at this call's
+                // first packet: packet 0 starts from the carried state, every later packet from a synthesised ring.
+                const bool headless = headless_ok && c.hist_syms >= d.P && c.last_xdelta == in->sri_xdelta &&
+                                      !(d.flags & (CH_RESET_NUMSYMS | CH_RESET_PHASEAVG)) && d.n_pkts >= 2 &&
+                                      first_symbol_at(d.pkt_len, d.tail_len, d.S, d.A, d.K) >= d.P + 1;
+                int j0 = -1;
+                if (headless) j0 = 0;
+                else
+                    for (int j = 1; j < d.n_pkts; j++)
+                        if (first_symbol_at((long long)j * d.pkt_len, d.tail_len, d.S, d.A, d.K) >= d.P) { j0 = j; break; }
+                if (j0 < 0 || d.n_pkts - j0 < (b->tp_mode == 1 ? 2 : 4)) continue;
+                d.flags |= CH_TP;
+                if (d.flags & CH_FZS) si.tp_fzs++;
+                const int has_head = headless ? 0 : 1;
+                const int cr = i - lo;                                         // slab-relative channel
+                tp_chans.push_back(TpChan{cr, j0, d.n_pkts, tp_records, tp_slots, has_head});
+                if (has_head) tp_heads.push_back(TpItem{cr, 0, j0, 0, -1, tp_records, -1, 0});
+                for (int j = j0; j < d.n_pkts; j++) {
+                    const int rec = tp_records + has_head + (j - j0);
+                    const int kind = (j == j0) ? (has_head ? 2 : 0) : 1;
+                    tp_items.push_back(TpItem{cr, j, j + 1, kind, has_head ? tp_records : -1, rec, tp_slots + (j - j0), 0});
+                }
+                tp_records += has_head + (d.n_pkts - j0);
+                tp_slots += d.n_pkts - j0;
+                si.n_slot += d.n_pkts - j0;
+                tp_Pmax = std::max(tp_Pmax, d.P);
+            }
+        }
+        si.n_head = (int)tp_heads.size() - si.head0; si.n_item = (int)tp_items.size() - si.item0; si.n_chan = (int)tp_chans.size() - si.chan0;
     }
 
     // ---- buffers ------------------------------------------------------------------------------
     CUDA_TRY(b->sel.reserve((size_t)scr_total + 4));
     CUDA_TRY(b->theta.reserve((size_t)scr_total + 4));
     float* dev_soft = out->soft; float* dev_phase = out->phase; int16_t* dev_bits = out->bits; int16_t* dev_sidx = out->sample_index;
-    size_t sym_stride = out->sym_stride, bits_stride = out->bits_stride, in_stride = 0;
+    size_t slot_in = 0, slot_sym = 0, slot_bits = 0;          // elements per ring slot
     if (host_bufs) {
-        // stage through device buffers with the caller's strides squeezed to what this call needs
-        sym_stride = (size_t)((Kmax + 7) & ~7LL); bits_stride = sym_stride * 3;
-        in_stride = (size_t)((nmax + 1) & ~1LL);
-        CUDA_TRY(b->st_in.reserve(2 * in_stride * nch + 4));
-        if (out->soft) { CUDA_TRY(b->st_soft.reserve(2 * sym_stride * nch + 4)); dev_soft = b->st_soft.p; }
-        if (out->phase) { CUDA_TRY(b->st_phase.reserve(sym_stride * nch + 4)); dev_phase = b->st_phase.p; }
-        if (out->bits) { CUDA_TRY(b->st_bits.reserve(bits_stride * nch + 4)); dev_bits = b->st_bits.p; }
-        if (out->sample_index) { CUDA_TRY(b->st_sidx.reserve(sym_stride * nch + 4)); dev_sidx = b->st_sidx.p; }
-        for (int i = 0; i < nch; i++) {
-            ChanDesc& d = b->h_desc[i];
-            d.in = reinterpret_cast<const float2*>(b->st_in.p) + (size_t)i * in_stride;
-            d.sym_off = (long long)i * (long long)sym_stride;
-            d.bits_off = (long long)i * (long long)bits_stride;
+        slot_in = 2 * in_stride * slab_ch_max; slot_sym = sym_stride * slab_ch_max; slot_bits = bits_stride * slab_ch_max;
+        // growing a staging buffer frees the old one: let every slab in flight (an earlier NO_SYNC call) drain first
+        const bool grow = RING * slot_in + 4 > b->st_in.cap || (out->soft && RING * 2 * slot_sym + 4 > b->st_soft.cap) ||
+                          (out->phase && RING * slot_sym + 4 > b->st_phase.cap) || (out->bits && RING * slot_bits + 4 > b->st_bits.cap) ||
+                          (out->sample_index && RING * slot_sym + 4 > b->st_sidx.cap);
+        if (grow) { CUDA_TRY(cudaStreamSynchronize(b->copy_in)); CUDA_TRY(cudaStreamSynchronize(b->stream)); CUDA_TRY(cudaStreamSynchronize(b->copy_out)); }
+        CUDA_TRY(b->st_in.reserve(RING * slot_in + 4));
+        if (out->soft) CUDA_TRY(b->st_soft.reserve(RING * 2 * slot_sym + 4));
+        if (out->phase) CUDA_TRY(b->st_phase.reserve(RING * slot_sym + 4));
+        if (out->bits) CUDA_TRY(b->st_bits.reserve(RING * slot_bits + 4));
+        if (out->sample_index) CUDA_TRY(b->st_sidx.reserve(RING * slot_sym + 4));
+    }
+    const size_t ostride_all = host_bufs ? slot_sym : sym_stride * (size_t)nch;     // elements of a whole-call temporary
+    if (!out->phase && any_staged) { CUDA_TRY(b->phase_tmp.reserve(ostride_all + 4)); }
+    if (!out->sample_index) { CUDA_TRY(b->sidx_tmp.reserve(ostride_all + 4)); if (!host_bufs) dev_sidx = b->sidx_tmp.p; }
+
+    // channel descriptors: host mode fills in the ring slot addresses first
+    if (host_bufs) {
+        for (int s = 0; s < n_slabs; s++) {
+            const int lo = slab_lo(s), hi = slab_lo(s + 1);
+            const int r = (int)((b->slab_seq + (unsigned long long)s) % RING);
+            for (int i = lo; i < hi; i++)
+                b->h_desc[i].in = reinterpret_cast<const float2*>(b->st_in.p + (size_t)r * slot_in) + (size_t)(i - lo) * in_stride;
         }
     }
-    if (!dev_phase && any_staged) { CUDA_TRY(b->phase_tmp.reserve(sym_stride * nch + 4)); }
-    if (!dev_sidx) { CUDA_TRY(b->sidx_tmp.reserve(sym_stride * nch + 4)); dev_sidx = b->sidx_tmp.p; }
-
     CUDA_TRY(cudaMemcpyAsync(b->d_desc, b->h_desc, sizeof(ChanDesc) * nch, cudaMemcpyHostToDevice, b->stream));
     if (n_listed > 0) {
         CUDA_TRY(cudaMemcpyAsync(b->d_list, h_list, sizeof(int) * n_listed, cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemsetAsync(b->d_done, 0, sizeof(int) * nch, b->stream));
-        CUDA_TRY(cudaMemsetAsync(b->d_ticket, 0, sizeof(int) * 64, b->stream));
     }
+    CUDA_TRY(cudaMemsetAsync(b->d_ticket, 0, sizeof(int) * (FUSED_TICKETS + FZS_TICKETS), b->stream));
+    b->fzs_ticket_next = 0;
     CUDA_TRY(cudaEventRecord(b->desc_ev[b->desc_slot], b->stream));
     const int tp_stride = (tp_Pmax + 3) & ~3;
     if (!tp_chans.empty()) {
@@ -660,34 +808,41 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         CUDA_TRY(b->tp_end_ring.reserve((size_t)tp_records * tp_stride));
         CUDA_TRY(b->tp_start_ring.reserve((size_t)tp_records * tp_stride));
         CUDA_TRY(b->tp_fail.reserve((size_t)nch));
+        CUDA_TRY(b->tp_slot_flags.reserve(2 * (size_t)tp_slots));
         // pageable sources: the copies are staged before the calls return
         CUDA_TRY(cudaMemcpyAsync(b->tp_items.p, tp_heads.data(), sizeof(TpItem) * tp_heads.size(), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemcpyAsync(b->tp_items.p + tp_heads.size(), tp_items.data(), sizeof(TpItem) * tp_items.size(), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemcpyAsync(b->tp_chans.p, tp_chans.data(), sizeof(TpChan) * tp_chans.size(), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemsetAsync(b->tp_fail.p, 0, sizeof(int) * nch, b->stream));
-    }
-
-    LaunchCtx L{};
-    L.stream = b->stream; L.n_channels = nch; L.Kmax = Kmax; L.Smax = Smax; L.Amax = Amax;
-    L.S_mask = S_mask; L.S_mask_fast = S_mask_fast; L.Amax_fast = Amax_fast; L.Amin_fast = Amin_fast; L.Pmax_fast = Pmax_fast; L.n_fast_channels = n_fast; L.n_seq_channels = n_seq;
-    L.d_desc = b->d_desc; L.d_state = b->d_state; L.d_ring = b->d_ring;
-    L.d_sel = b->sel.p; L.d_theta = b->theta.p; L.d_phase_tmp = b->phase_tmp.p;
-    L.out_soft = dev_soft; L.out_bits = dev_bits; L.out_phase = dev_phase; L.out_sidx = dev_sidx;
-    L.sri_xdelta = in->sri_xdelta; L.d_counters = b->d_counters; L.launches = &b->launches; L.prof = &b->prof;
-    if (!tp_chans.empty()) {
-        L.tp_head_items = b->tp_items.p; L.tp_n_head = (int)tp_heads.size();
-        L.tp_items = b->tp_items.p + tp_heads.size(); L.tp_n_items = (int)tp_items.size();
-        L.tp_chans = b->tp_chans.p; L.tp_n_chans = (int)tp_chans.size(); L.tp_n_slots = tp_slots;
-        L.tp_pkts = b->tp_pkts.p; L.tp_ends = b->tp_ends.p; L.tp_end_ring = b->tp_end_ring.p; L.tp_start_ring = b->tp_start_ring.p;
-        L.tp_ring_stride = tp_stride; L.tp_fail = b->tp_fail.p;
+        CUDA_TRY(cudaMemsetAsync(b->tp_slot_flags.p, 0, sizeof(int) * 2 * (size_t)tp_slots, b->stream));
     }
 
     // the kernels of one slab of channels [lo, hi)
-    auto run_slab = [&](const LaunchCtx& Ls, int slab, int lo) -> int {
+    auto run_slab = [&](int slab, int lo, int hi) -> int {
+        const SlabInfo& si = slabs[slab];
+        LaunchCtx Ls{};
+        Ls.stream = b->stream; Ls.n_channels = hi - lo; Ls.Kmax = si.Kmax; Ls.Smax = si.Smax; Ls.Amax = si.Amax;
+        Ls.S_mask = si.S_mask; Ls.S_mask_fast = si.S_mask_fast; Ls.Amax_fast = si.Amax_fast; Ls.Amin_fast = si.Amin_fast;
+        Ls.Pmax_fast = si.Pmax_fast; Ls.n_fast_channels = si.n_fast; Ls.n_seq_channels = si.n_seq;
+        Ls.d_desc = b->d_desc + lo; Ls.h_desc = b->h_desc + lo; Ls.d_state = b->d_state + lo; Ls.d_ring = b->d_ring;
+        Ls.d_sel = b->sel.p; Ls.d_theta = b->theta.p; Ls.d_phase_tmp = b->phase_tmp.p;
+        Ls.out_soft = dev_soft; Ls.out_bits = dev_bits; Ls.out_phase = dev_phase; Ls.out_sidx = dev_sidx;
+        Ls.sri_xdelta = in->sri_xdelta; Ls.d_counters = b->d_counters; Ls.launches = &b->launches; Ls.prof = &b->prof;
+        if (si.n_chan > 0) {
+            Ls.tp_head_items = b->tp_items.p + si.head0; Ls.tp_n_head = si.n_head;
+            Ls.tp_items = b->tp_items.p + tp_heads.size() + si.item0; Ls.tp_n_items = si.n_item;
+            Ls.tp_chans = b->tp_chans.p + si.chan0; Ls.tp_n_chans = si.n_chan; Ls.tp_n_slots = si.n_slot;
+            Ls.tp_pkts = b->tp_pkts.p; Ls.tp_ends = b->tp_ends.p; Ls.tp_end_ring = b->tp_end_ring.p; Ls.tp_start_ring = b->tp_start_ring.p;
+            Ls.tp_ring_stride = tp_stride; Ls.tp_fail = b->tp_fail.p + lo;
+            Ls.tp_slot_fail = b->tp_slot_flags.p; Ls.tp_slot_run = b->tp_slot_flags.p + tp_slots;
+            Ls.tp_n_chans_fzs = si.tp_fzs;
+        }
+        Ls.n_fzs_channels = si.n_fzs; Ls.Pmax_fzs = si.Pmax_fzs; Ls.S_mask_fzs = si.S_mask_fzs; Ls.Kmax_fzs = si.Kmax_fzs;
+        Ls.d_fzs_ticket = b->d_ticket + FUSED_TICKETS; Ls.fzs_ticket_next = &b->fzs_ticket_next; Ls.fzs_ticket_cap = FZS_TICKETS;
         for (const FusedSeg& g : segs) {
             if (g.slab != slab) continue;
             FusedLaunch f{};
-            f.S = g.S; f.d_list = b->d_list + g.first; f.n_list = g.count;
+            f.S = g.S; f.d_list = b->d_list + g.first; f.h_list = h_list + g.first; f.n_list = g.count;
             // a unit = enough consecutive packets for >= ~4096 symbols
             static const long long unit_syms = getenv("PSKD_FUSED_UNIT") ? std::max(256, atoi(getenv("PSKD_FUSED_UNIT"))) : 4096;
             const long long ppu = std::max<long long>(1, (unit_syms * g.S + g.pkt_len_min - 1) / g.pkt_len_min);
@@ -708,8 +863,9 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             f.d_done = b->d_done + lo;
             CUDA_TRY(launch_fused(Ls, f));
         }
-        if (any_staged) {
+        if (si.n_fast + si.n_seq > 0) {
             CUDA_TRY(launch_front(Ls));
+            CUDA_TRY(launch_fzs_front(Ls));
             CUDA_TRY(launch_chain_par(Ls));
             CUDA_TRY(launch_chain_seq(Ls));
             CUDA_TRY(launch_back(Ls));
@@ -718,37 +874,41 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         return PSKD_OK;
     };
     if (!host_bufs) {
-        rc = run_slab(L, 0, 0);
+        rc = run_slab(0, 0, nch);
         if (rc != PSKD_OK) return rc;
     } else {
-        // host buffers: channel slabs flow H2D (copy_in) -> kernels (stream) -> D2H (copy_out), so the
-        // PCIe transfers of neighbouring slabs overlap the kernels (channels are independent)
         for (int s = 0; s < n_slabs; s++) {
-            const int lo = (int)((long long)s * nch / n_slabs), hi = (int)((long long)(s + 1) * nch / n_slabs);
+            const int lo = slab_lo(s), hi = slab_lo(s + 1);
+            const int r = (int)(b->slab_seq % RING);
+            b->slab_seq++;
+            const size_t rows = (size_t)(hi - lo);
+            // H2D into ring slot r once the kernels of the slab that used it last have read their input
+            CUDA_TRY(cudaStreamWaitEvent(b->copy_in, b->ev_kern[r], 0));
             if (nmax > 0)
-                CUDA_TRY(cudaMemcpy2DAsync(b->st_in.p + 2 * in_stride * lo, in_stride * 8, in->iq + 2 * in->iq_stride * lo,
-                                           in->iq_stride * 8, (size_t)nmax * 8, hi - lo, cudaMemcpyHostToDevice, b->copy_in));
-            CUDA_TRY(cudaEventRecord(b->slab_in[s], b->copy_in));
-        }
-        for (int s = 0; s < n_slabs; s++) {
-            const int lo = (int)((long long)s * nch / n_slabs), hi = (int)((long long)(s + 1) * nch / n_slabs);
-            LaunchCtx Ls = L;
-            Ls.d_desc = b->d_desc + lo; Ls.d_state = b->d_state + lo; Ls.n_channels = hi - lo;
-            CUDA_TRY(cudaStreamWaitEvent(b->stream, b->slab_in[s], 0));
-            rc = run_slab(Ls, s, lo);
+                CUDA_TRY(cudaMemcpy2DAsync(b->st_in.p + (size_t)r * slot_in, in_stride * 8, in->iq + 2 * in->iq_stride * lo,
+                                           in->iq_stride * 8, (size_t)nmax * 8, rows, cudaMemcpyHostToDevice, b->copy_in));
+            CUDA_TRY(cudaEventRecord(b->ev_h2d[r], b->copy_in));
+            // kernels once the input is there and the slot's previous outputs have left for the host
+            CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_h2d[r], 0));
+            CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_d2h[r], 0));
+            dev_soft = out->soft ? b->st_soft.p + (size_t)r * 2 * slot_sym : nullptr;
+            dev_phase = out->phase ? b->st_phase.p + (size_t)r * slot_sym : nullptr;
+            dev_bits = out->bits ? b->st_bits.p + (size_t)r * slot_bits : nullptr;
+            dev_sidx = out->sample_index ? b->st_sidx.p + (size_t)r * slot_sym : b->sidx_tmp.p;
+            rc = run_slab(s, lo, hi);
             if (rc != PSKD_OK) return rc;
-            CUDA_TRY(cudaEventRecord(b->slab_done[s], b->stream));
-            CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->slab_done[s], 0));
+            CUDA_TRY(cudaEventRecord(b->ev_kern[r], b->stream));
+            CUDA_TRY(cudaStreamWaitEvent(b->copy_out, b->ev_kern[r], 0));
             if (Kmax > 0) {
-                const size_t rows = (size_t)(hi - lo);
-                if (out->soft) CUDA_TRY(cudaMemcpy2DAsync(out->soft + 2 * out->sym_stride * lo, out->sym_stride * 8, dev_soft + 2 * sym_stride * lo, sym_stride * 8, (size_t)Kmax * 8, rows, cudaMemcpyDeviceToHost, b->copy_out));
-                if (out->phase) CUDA_TRY(cudaMemcpy2DAsync(out->phase + out->sym_stride * lo, out->sym_stride * 4, dev_phase + sym_stride * lo, sym_stride * 4, (size_t)Kmax * 4, rows, cudaMemcpyDeviceToHost, b->copy_out));
-                if (out->sample_index) CUDA_TRY(cudaMemcpy2DAsync(out->sample_index + out->sym_stride * lo, out->sym_stride * 2, dev_sidx + sym_stride * lo, sym_stride * 2, (size_t)Kmax * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                if (out->soft) CUDA_TRY(cudaMemcpy2DAsync(out->soft + 2 * out->sym_stride * lo, out->sym_stride * 8, dev_soft, sym_stride * 8, (size_t)Kmax * 8, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                if (out->phase) CUDA_TRY(cudaMemcpy2DAsync(out->phase + out->sym_stride * lo, out->sym_stride * 4, dev_phase, sym_stride * 4, (size_t)Kmax * 4, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                if (out->sample_index) CUDA_TRY(cudaMemcpy2DAsync(out->sample_index + out->sym_stride * lo, out->sym_stride * 2, dev_sidx, sym_stride * 2, (size_t)Kmax * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));
                 if (out->bits) {
                     size_t w = std::min((size_t)Kmax * 3, out->bits_stride);
-                    CUDA_TRY(cudaMemcpy2DAsync(out->bits + out->bits_stride * lo, out->bits_stride * 2, dev_bits + bits_stride * lo, bits_stride * 2, w * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                    CUDA_TRY(cudaMemcpy2DAsync(out->bits + out->bits_stride * lo, out->bits_stride * 2, dev_bits, bits_stride * 2, w * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));
                 }
             }
+            CUDA_TRY(cudaEventRecord(b->ev_d2h[r], b->copy_out));
         }
     }
 
@@ -757,16 +917,25 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         ChanHost& c = b->ch[i];
         const ChanDesc& d = b->h_desc[i];
         c.tail_len = d.next_tail_len;
+        c.win_size = stalled[i] ? c.win_size + d.n_in : d.next_tail_len;
         c.latched = c.props;
         if (d.n_pkts > 0) {
+            // the LinearFit history is cleared by resetNumSymbols (:416-420) and by a change of the SRI rate (:91-102);
+            // a phaseAvg change keeps at most the newest values (:103-109)
+            if (c.resetNumSymbols || c.resetPhaseAvg || c.last_xdelta != in->sri_xdelta) c.hist_syms = 0;
+            c.hist_syms += d.K;
+            const bool sri_block = !stalled[i] || (d.flags & (CH_SRI_CHANGED | CH_RESET_NUMSYMS));
+            if (sri_block) c.last_xdelta = in->sri_xdelta; else c.last_xdelta = 0.0;
             c.resetNumSymbols = false; c.resetPhaseAvg = false;
             c.fit_n = d.P;
-            // out-port SRIs (cpp/psk_soft.cpp:399-404), pushed on every packet
-            double xd = in->sri_xdelta * (double)d.S;
-            c.sri.soft_xdelta = xd; c.sri.soft_mode = 1;
-            c.sri.phase_xdelta = xd; c.sri.phase_mode = 0;
-            c.sri.bits_xdelta = xd / (double)d.bpb; c.sri.bits_mode = 0;
-            c.sri.sri_pushes += d.n_pkts;
+            if (sri_block) {
+                // out-port SRIs (cpp/psk_soft.cpp:399-404), pushed on every packet (a stalled one: only with sriChanged / resetNumSymbols)
+                double xd = in->sri_xdelta * (double)d.S;
+                c.sri.soft_xdelta = xd; c.sri.soft_mode = 1;
+                c.sri.phase_xdelta = xd; c.sri.phase_mode = 0;
+                c.sri.bits_xdelta = xd / (double)d.bpb; c.sri.bits_mode = 0;
+                c.sri.sri_pushes += d.n_pkts;
+            }
         }
         if (out->n_symbols) out->n_symbols[i] = (size_t)d.K;
         if (out->n_bits) out->n_bits[i] = (size_t)(d.K * d.bpb);
@@ -776,10 +945,8 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     }
     b->tail_cur = next_tail;
 
-    if (host_bufs) {
-        CUDA_TRY(cudaStreamSynchronize(b->copy_out));
-        CUDA_TRY(cudaStreamSynchronize(b->stream));
-    } else if (!(in->flags & PSKD_FLAG_NO_SYNC)) {
+    if (!(in->flags & PSKD_FLAG_NO_SYNC)) {
+        if (host_bufs) CUDA_TRY(cudaStreamSynchronize(b->copy_out));
         CUDA_TRY(cudaStreamSynchronize(b->stream));
     }
     return any_nobits ? PSKD_NO_BITS : PSKD_OK;

@@ -52,7 +52,10 @@ struct GlobalRing {
 template <class Ring>
 __device__ __forceinline__ void chain_packet_prologue(ChanState& st, Ring ring, const ChanDesc& d,
                                                        double sri_xdelta, int& flags) {
-    if (sri_xdelta != (double)st.sampleRate) {                                         // :394-398
+    // :393 -- the SRI block runs when sriChanged, resetNumSymbols or resetSamplesPerBaud; the last one holds at every
+    // packet start except while the component is stalled on an over-full window (:380-383)
+    const bool sri_block = !(flags & CH_STALLED) || (flags & (CH_SRI_CHANGED | CH_RESET_NUMSYMS));
+    if (sri_block && sri_xdelta != (double)st.sampleRate) {                            // :394-398
         st.sampleRate = __double2float_rn(__ddiv_rn(1.0, sri_xdelta));
         fit_reset(st.fit, ring, nullptr, &st.sampleRate, false);
     }

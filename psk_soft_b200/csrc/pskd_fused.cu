@@ -40,6 +40,8 @@
 
 namespace pskd {
 
+bool fused_supports(int S, int A, int P);
+
 #ifndef PSKD_FZ_WARPS
 #define PSKD_FZ_WARPS 4
 #endif
@@ -90,6 +92,11 @@ struct FzCtx {                         // one per warp, shared memory
     int end_mid;                       // the unit ends inside its packet: no epilogue, the next unit carries on
     int c;                             // next chunk
     int inflight;                      // chunk c's blocks are already on their way (cp.async)
+    // chain + back kernel of the staged path (k_fzs_cb): run-time samplesPerBaud, the unit's end record
+    int S_rt, dst, k_begin;
+    float est_start_used;
+    int n_first, n_last, have_first;   // exact unwrap counts of the unit's first / last symbol (TpEnd)
+    float est_pre;                     // estimate before the last packet-end wrap
 };
 
 constexpr int fz_align16(int x) { return (x + 15) & ~15; }
@@ -109,6 +116,8 @@ template <int S> struct FzCfg {
 // compile-time layout of one warp's shared-memory region.  PC = phaseAvg capacity.
 template <int S, int PC> struct FzL {
     using C = FzCfg<S>;
+    static constexpr int S_STATIC = S;                                     // samplesPerBaud known at compile time
+    static constexpr bool TRACK_N = false;                                 // no end records (TpEnd) in the fused kernel
     static constexpr int BLK = C::CHS * 8;                                 // one staged block of raw samples
     static constexpr int OFF_L = 0;                                        // float2 lead[32*S]
     static constexpr int OFF_T = BLK;                                      // float2 trail[32*S]
@@ -207,11 +216,14 @@ static __device__ __noinline__ void fz_normalize_ring(float* yh, float* tmp, Fit
 static __device__ __noinline__ void fz_block_sequential(FzCtx& cx, float* yh, const float* th, float* estv, int nb) {
     SmemRing ring{yh};
     ChanState st = cx.st;
+    long long n = 0;
     for (int i = 0; i < nb; i++) {
-        float y = unwrap_against(st.est, th[i], nullptr);
+        float y = unwrap_against(st.est, th[i], &n);
+        if (i == 0 && !cx.have_first) { cx.n_first = (int)n; cx.have_first = 1; }
         st.est = fit_next(st.fit, ring, y);
         estv[i] = st.est;
     }
+    if (nb > 0) cx.n_last = (int)n;
     cx.st = st;
     if (st.fit.pts == st.fit.n && st.fit.pts > 1) cx.fc = fit_const(st.fit);
 }
@@ -231,6 +243,7 @@ static __device__ __noinline__ void fz_epilogue(FzCtx& cx, float* yh) {
     SmemRing r{yh};
     ChanState st = cx.st;
     const unsigned long long w0 = st.wraps;
+    cx.est_pre = st.est;
     chain_packet_epilogue(st, r, cx.M);
     if (st.wraps != w0) { cx.st = st; cx.cz_valid = 0; }
 }
@@ -394,10 +407,9 @@ static __device__ __noinline__ void fz_back_rolled(const float2* __restrict__ se
 // cpp/psk_soft.cpp:476-482 with LinearFit::next (:48-87).  Returns false if the counts did not settle
 // within FZ_MAX_ITERS passes (the caller then runs the literal recursion); on success the state, the
 // history (yh, cz) and th[0..m) = est are updated.
-template <int S, int PC>
+template <class L>
 static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
 {
-    using L = FzL<S, PC>;
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
@@ -528,7 +540,14 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
         float mm, bb;
         cx.st.est = fit_eval_fast(fc, Yv, Xv, &mm, &bb);
         f.ySum = Yv; f.xySum = Xv; f.m = mm; f.b = bb; f.count += m;
+        if (L::TRACK_N) {                      // the verified (= the reference's) count of the block's last symbol
+            int nl = nloc[0];
+#pragma unroll
+            for (int v = 1; v < 4; v++) if (v == (last & 3)) nl = nloc[v];
+            cx.n_last = nl;
+        }
     }
+    if (L::TRACK_N && lane == 0 && !cx.have_first) { cx.n_first = nloc[0]; cx.have_first = 1; }
     // phase_dataFloat_out (:482) is staged in th[0..m): the angles are consumed
     if (i0 + 3 < m) *reinterpret_cast<float4*>(th + i0) = make_float4(el[0], el[1], el[2], el[3]);
     else if (i0 < m) {
@@ -555,10 +574,9 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
 // (cpp/psk_soft.cpp:484-566) from selb[] (samples) and th[] (estimates) into the staging buffers
 // (soft, bits: the chain's buffers are dead by now), then the coalesced stores of phase / soft /
 // bits for symbols [kchain, kchain + m).
-template <int S, int PC>
+template <class L>
 static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
 {
-    using L = FzL<S, PC>;
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
     float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
@@ -634,10 +652,9 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
 }
 
 // literal recursion for one block (lane 0) and its estimates into th[0..m)
-template <int S, int PC>
+template <class L>
 static __device__ __noinline__ void fz_chain_slow(const unsigned wofs, const int m)
 {
-    using L = FzL<S, PC>;
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
@@ -653,8 +670,9 @@ static __device__ __noinline__ void fz_chain_slow(const unsigned wofs, const int
 
 // a packet is exhausted: its epilogue (cpp/psk_soft.cpp:592-603) and, unless it was the unit's last, the
 // next packet's prologue (:393-426).  Returns true when the unit is done.
-template <int S>
+template <int S_STATIC>
 static __device__ __noinline__ bool fz_next_packet(FzCtx& cx, float* yh, const int lane) {
+    const int S = S_STATIC ? S_STATIC : cx.S_rt;
     if (cx.end_mid) { if (lane == 0) cx.unit_done = 1; __syncwarp(); return true; }    // the packet goes on in the next unit
     if (lane == 0) fz_epilogue(cx, yh);
     __syncwarp();
@@ -672,10 +690,9 @@ static __device__ __noinline__ bool fz_next_packet(FzCtx& cx, float* yh, const i
 
 // fz_drain: consume buffered symbols: chain blocks of FZ_B (shorter at a packet end) followed by
 // the output stage; runs the packet epilogue / next prologue whenever a packet is exhausted.
-template <int S, int PC>
+template <class L>
 static __device__ FZ_HOT void fz_drain(const unsigned wofs)
 {
-    using L = FzL<S, PC>;
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
     float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
@@ -687,7 +704,7 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
         const int kchain = cx.kchain;
         const int rem = cx.pk_hi - kchain;
         if (rem == 0) {
-            if (fz_next_packet<S>(cx, yh, lane)) break;
+            if (fz_next_packet<L::S_STATIC>(cx, yh, lane)) break;
             continue;
         }
         const int nbuf = cx.nbuf;
@@ -710,10 +727,10 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
         if (!fast) m = min(m, max(1, P - pts));                                     // fill-up runs sequentially
         const float2 prev_new = selb[2 + m - 1];
         bool done = false;
-        if (fast) done = fz_chain_fast<S, PC>(wofs, m);
-        if (!done) fz_chain_slow<S, PC>(wofs, m);
+        if (fast) done = fz_chain_fast<L>(wofs, m);
+        if (!done) fz_chain_slow<L>(wofs, m);
         if (lane == 0) cx.blocks++;
-        fz_back_block<S, PC>(wofs, m);
+        fz_back_block<L>(wofs, m);
         // ---- drop the consumed symbols from the buffer ------------------------------------------------
         const int left = nbuf - m;
         for (int base = 0; base < left; base += 32) {
@@ -1187,13 +1204,489 @@ k_fused(const FusedParams prm)
         if (u >= prm.n_units) break;
         const int nchunks = fz_unit_begin<S, PC>(prm, wofs, u);
         if (nchunks < 0) continue;
-        fz_drain<S, PC>(wofs);         // packets without symbols before the first chunk (and units without any symbol)
+        fz_drain<L>(wofs);             // packets without symbols before the first chunk (and units without any symbol)
         if (cx.a16) {
-            while (cx.c < nchunks) { fz_chunk<S, PC, true>(wofs); fz_drain<S, PC>(wofs); }
+            while (cx.c < nchunks) { fz_chunk<S, PC, true>(wofs); fz_drain<L>(wofs); }
         } else {
-            while (cx.c < nchunks) { fz_chunk<S, PC, false>(wofs); fz_drain<S, PC>(wofs); }
+            while (cx.c < nchunks) { fz_chunk<S, PC, false>(wofs); fz_drain<L>(wofs); }
         }
         fz_unit_end<S, PC>(prm, wofs);
+    }
+}
+
+// =============================================================================================
+// Staged path built from the fused kernel's stages (few channels / long channels: the regime where
+// one warp per channel leaves the GPU empty).  The two data-dependent halves of the path are split at
+// the only sequential quantity, the integer level of the unwrapped phase:
+//   k_fzs_front<S>  timing + M-th power angle of EVERY symbol, fully time-parallel: a unit is a
+//                   segment of one channel (the carried window sums of a segment are rebuilt exactly
+//                   from the numAvg-1 rows in front of it, as fz_unit_begin does).  Writes sampleIndex
+//                   and 12 B/symbol of scratch (selected sample, angle).  cpp/psk_soft.cpp:442-474.
+//   k_fzs_cb<PC>    unwrap / LinearFit chain + derotate / slice of one unit = consecutive packets of
+//                   one channel, from the scratch.  With the time-parallel plan (TpCtl, pskd_internal.h)
+//                   every packet is its own unit, started from a history ring synthesised from the
+//                   resolved integer levels and proven afterwards by k_tp_check.  :476-603.
+// =============================================================================================
+#ifndef PSKD_FZS_FRONT_MIN_CTAS
+#define PSKD_FZS_FRONT_MIN_CTAS 6
+#endif
+#ifndef PSKD_FZS_CB_MIN_CTAS
+#define PSKD_FZS_CB_MIN_CTAS 6
+#endif
+
+template <int S> struct FzsFL {          // per-warp shared memory of the front kernel
+    using C = FzCfg<S>;
+    static constexpr int BLK = C::CHS * 8;
+    static constexpr int OFF_L = 0;                    // float2 lead[32*S]
+    static constexpr int OFF_T = BLK;                  // float2 trail[32*S]
+    static constexpr int OFF_E = 2 * BLK;              // double e[32][ES] window sums
+    static constexpr int OFF_CW = OFF_E + 32 * C::ES * 8;   // double cw[16]
+    static constexpr int BYTES = OFF_CW + 16 * 8;
+};
+
+struct FzsFrontParams {
+    const ChanDesc* desc; int n_channels;
+    int seg_syms;                      // symbols per unit (multiple of 32)
+    int n_units;                       // n_channels * ceil(Kmax / seg_syms), segment-major
+    int* ticket;
+    float2* sel; float* theta; int16_t* out_sidx;
+};
+
+template <int S>
+static __device__ __noinline__ void fzs_fill_slow(float2* st, long long s0, long long V, long long tail_len,
+                                                  const float2* tailp, const float2* in_mt, int lane) {
+    using C = FzCfg<S>;
+#pragma unroll 2
+    for (int q = 0; q < S; q++) {
+        const int n = lane + 32 * q;
+        const long long v = s0 + n;
+        float2 x = make_float2(0.f, 0.f);
+        if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
+        st[C::phys(n)] = x;
+    }
+}
+
+// all chunks of one front unit: rows [kA, kB) of one channel (same arithmetic as fz_chunk; the angle and
+// the selected sample go to the scratch arrays instead of the block buffer)
+template <int S, bool A16>
+static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const int lane, const int kA, const int kB,
+                                                       const int lag, const int c_lo, const int c_hi, const int nchunks,
+                                                       bool inflight, const int M, const float2* in_mt, const float2* tailp,
+                                                       const long long tail_len, const long long V,
+                                                       int16_t* o_sidx, float* o_th, float2* o_sel)
+{
+    using C = FzCfg<S>;
+    using L = FzsFL<S>;
+    constexpr int G = C::G, R = C::R, ES = C::ES;
+    constexpr int CHS = C::CHS;
+    float2* Lst  = reinterpret_cast<float2*>(wb + L::OFF_L);
+    float2* Tst  = reinterpret_cast<float2*>(wb + L::OFF_T);
+    double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
+    double* ebuf = reinterpret_cast<double*>(wb + L::OFF_E);
+    const bool wact = lane < G * S;
+    const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
+    const bool m_ok = (M == 2 || M == 4 || M == 8);
+    double Cw = cwp[wp];
+    const int od = (S == 8) ? (wg & 1) : 0;
+    const int ofs_e = (R * wg + od) * S + wp, ofs_o = (R * wg - od) * S + wp;
+    const int rowp = (S == 8) ? (lane ^ ((lane >> 3) & 1)) * S : lane * S;
+
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c++) {
+        const int krow = kA + FZ_CH * c;
+        if (!inflight) {
+            if (c >= c_lo && c < c_hi) {
+                fz_issue<S, A16>(Tst, in_mt + (long long)krow * S, lane);
+                fz_issue<S, A16>(Lst, in_mt + (long long)(krow + lag) * S, lane);
+            } else {
+                fzs_fill_slow<S>(Tst, (long long)krow * S, V, tail_len, tailp, in_mt, lane);
+                fzs_fill_slow<S>(Lst, (long long)(krow + lag) * S, V, tail_len, tailp, in_mt, lane);
+            }
+        }
+        fz_cp_async_wait_all();
+        __syncwarp();
+        // ---- timing, part 1: exact sliding window sums (:451, :576), lane = (phase wp, row group wg)
+        double Eloc[R];
+        double x = 0.0;
+        {
+            const float2* le = Lst + ofs_e; const float2* lo = Lst + ofs_o;
+            const float2* te = Tst + ofs_e; const float2* to = Tst + ofs_o;
+#pragma unroll
+            for (int i = 0; i < R; i++) {
+                if (G * R == 32 || R * wg + i < 32) {
+                    const float2 a = (i & 1) ? lo[i * S] : le[i * S];
+                    const float2 b = (i & 1) ? to[i * S] : te[i * S];
+                    x = daddr(x, (double)fz_energy(a));                       // :448-451
+                    Eloc[i] = x;
+                    x = dsubr(x, (double)fz_energy(b));                       // :576
+                } else Eloc[i] = 0.0;
+            }
+        }
+        {
+            double incl = x;
+#pragma unroll
+            for (int d = 1; d < G; d <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, incl, d * S, 32);
+                if (wg >= d) incl = daddr(incl, t);
+            }
+            const double ex = __shfl_up_sync(0xffffffffu, incl, S, 32);
+            const double tot = __shfl_sync(0xffffffffu, incl, (G - 1) * S + wp, 32);
+            const double off = (wg >= 1) ? daddr(Cw, ex) : Cw;
+            Cw = daddr(Cw, tot);
+            if (wact) {
+                double* eo = ebuf + (R * wg) * ES + wp;
+#pragma unroll
+                for (int i = 0; i < R; i++)
+                    if (G * R == 32 || R * wg + i < 32) eo[i * ES] = daddr(off, Eloc[i]);
+            }
+        }
+        __syncwarp();
+        const bool nfast = (c + 1 >= c_lo) && (c + 1 < c_hi);
+        if (nfast) fz_issue<S, A16>(Lst, in_mt + (long long)(krow + FZ_CH + lag) * S, lane);
+        // ---- timing, part 2: lane = row: first maximum (:462), the selected sample (:465)
+        const int nrows = min(FZ_CH, kB - krow);
+        float2 gx;
+        {
+            const double* er = ebuf + lane * ES;
+            double e[S];
+#pragma unroll
+            for (int q = 0; q < S; q++) e[q] = er[q];
+            int ix[S];
+#pragma unroll
+            for (int q = 0; q < S; q++) ix[q] = q;
+#pragma unroll
+            for (int lv = 0; lv < 5; lv++) {
+                const int w = 1 << lv;
+#pragma unroll
+                for (int q = 0; q < S; q++) {
+                    if (w < S && (q % (2 * w)) == 0 && q + w < S) {
+                        if (e[q] < e[q + w]) { e[q] = e[q + w]; ix[q] = ix[q + w]; }
+                    }
+                }
+            }
+            const int idx = ix[0];
+            if (lane < nrows) __stcs(o_sidx + krow + lane, (int16_t)idx);                  // :466
+            gx = Tst[rowp + idx];
+        }
+        __syncwarp();
+        if (nfast) {
+            fz_issue<S, A16>(Tst, in_mt + (long long)(krow + FZ_CH) * S, lane);
+            if (c + FZ_PF < c_hi) {
+                const float2* nx = in_mt + (long long)(krow + FZ_PF * FZ_CH + lag) * S;
+                if (A16) { if (lane == 0) fz_prefetch_l2(nx, (unsigned)CHS * 8u); }
+                else if (lane * 16 < CHS) fz_prefetch_line(nx + lane * 16);
+            }
+        }
+        inflight = nfast;
+        // ---- M-th power angle (:474) -> scratch
+        bool bad = false;
+        const float thv = fz_theta(gx, M, bad);
+        bad = (bad || !m_ok) && lane < nrows;
+        if (lane < nrows) {
+            o_th[krow + lane] = thv;
+            o_sel[krow + lane] = gx;
+        }
+        if (__any_sync(0xffffffffu, bad)) {            // rare: literal angle for odd inputs / other M
+            __syncwarp();
+            if (bad) fz_theta_fixup(o_th, o_sel, krow + lane, (unsigned)M);
+        }
+    }
+    __syncwarp();
+}
+
+template <int S>
+__global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZS_FRONT_MIN_CTAS)
+k_fzs_front(const FzsFrontParams prm)
+{
+    using C = FzCfg<S>;
+    using L = FzsFL<S>;
+    constexpr int G = C::G, ES = C::ES, CHS = C::CHS;
+    const int lane = fz_lane();
+    unsigned char* wb = fz_smem + (threadIdx.x >> 5) * (unsigned)L::BYTES;
+    float2* Lst  = reinterpret_cast<float2*>(wb + L::OFF_L);
+    float2* Tst  = reinterpret_cast<float2*>(wb + L::OFF_T);
+    double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
+    double* ebuf = reinterpret_cast<double*>(wb + L::OFF_E);
+    const bool wact = lane < G * S;
+    const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
+
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(prm.ticket, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= prm.n_units) break;
+        const int seg = u / prm.n_channels;
+        const int ch = u - seg * prm.n_channels;
+        const ChanDesc* dgp = prm.desc + ch;
+        if (!(dgp->flags & CH_FZS) || dgp->S != S) continue;
+        const int K = (int)dgp->K;
+        const int kA = seg * prm.seg_syms;
+        if (kA >= K) continue;
+        const int kB = min(K, kA + prm.seg_syms);
+        const int A = dgp->A, lag = A - 1;
+        const long long tail_len = dgp->tail_len;
+        const long long V = tail_len + dgp->n_in;
+        const int nchunks = (kB - kA + FZ_CH - 1) / FZ_CH;
+        const float2* in_mt = dgp->in - tail_len;
+        const float2* tailp = dgp->tail;
+        int c_lo = 0, c_hi = 0, a16 = 0;
+        {
+            const long long sT0 = (long long)kA * S, sL0 = (long long)(kA + lag) * S;
+            long long lo = (tail_len - sT0 + CHS - 1) / CHS;
+            if (lo < 0) lo = 0;
+            long long hi = (V - sL0) / CHS;
+            if (hi > nchunks) hi = nchunks;
+            if (lo < hi) { c_lo = (int)lo; c_hi = (int)hi; }
+            a16 = (((reinterpret_cast<uintptr_t>(in_mt + sT0) | reinterpret_cast<uintptr_t>(in_mt + sL0)) & 15) == 0) ? 1 : 0;
+            if (lane == 0 && c_lo < c_hi && a16)
+                fz_prefetch_l2(in_mt + sL0 + (long long)c_lo * CHS, (unsigned)min(FZ_PF, c_hi - c_lo) * CHS * 8);
+        }
+        const bool pre0 = c_lo == 0 && c_hi > 0;
+        __syncwarp();                                                 // the previous unit's last reads of the staged blocks
+        if (pre0) {
+            if (a16) {
+                fz_issue<S, true>(Tst, in_mt + (long long)kA * S, lane);
+                fz_issue<S, true>(Lst, in_mt + (long long)(kA + lag) * S, lane);
+            } else {
+                fz_issue<S, false>(Tst, in_mt + (long long)kA * S, lane);
+                fz_issue<S, false>(Lst, in_mt + (long long)(kA + lag) * S, lane);
+            }
+        }
+        // carried window sums: rows [kA, kA+lag) per phase, exact double sums
+        {
+            const long long s0 = (long long)kA * S;
+            double acc = 0.0;
+            if (wact) {
+                for (int i = wg; i < lag; i += G) {
+                    const long long v = s0 + (long long)i * S + wp;
+                    float2 x = make_float2(0.f, 0.f);
+                    if (v < V) x = (v < tail_len) ? tailp[v] : __ldg(in_mt + v);
+                    acc = daddr(acc, (double)energy_f32(x.x, x.y));
+                }
+                ebuf[wg * ES + wp] = acc;
+            }
+            __syncwarp();
+            if (lane < S) {
+                double Cw = 0.0;
+#pragma unroll
+                for (int g2 = 0; g2 < G; g2++) Cw = daddr(Cw, ebuf[g2 * ES + lane]);
+                cwp[lane] = Cw;
+            }
+            __syncwarp();
+        }
+        int16_t* o_sidx = prm.out_sidx + dgp->sym_off;
+        float* o_th = prm.theta + dgp->scr_off;
+        float2* o_sel = prm.sel + dgp->scr_off;
+        if (a16) fzs_front_chunks<S, true>(wb, lane, kA, kB, lag, c_lo, c_hi, nchunks, pre0, dgp->M, in_mt, tailp, tail_len, V, o_sidx, o_th, o_sel);
+        else     fzs_front_chunks<S, false>(wb, lane, kA, kB, lag, c_lo, c_hi, nchunks, pre0, dgp->M, in_mt, tailp, tail_len, V, o_sidx, o_th, o_sel);
+    }
+}
+
+// ---- chain + back kernel ------------------------------------------------------------------------
+template <int PC> struct FzsCbL {        // per-warp shared memory of the chain + back kernel (no staged blocks)
+    static constexpr int S_STATIC = 0;
+    static constexpr bool TRACK_N = true;                                   // exact first / last unwrap counts into the end record
+    static constexpr int OFF_TH = 0;                                        // float  th[FZ_BUF]
+    static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                     // float2 selb[FZ_BUF + 2]; [1] = previous sample
+    static constexpr int OFF_YH = fz_align16(OFF_SEL + (FZ_BUF + 2) * 8);   // float  yh[PC]
+    static constexpr int OFF_CTX = fz_align16(OFF_YH + PC * 4);
+    static constexpr int OFF_CZ = fz_align16(OFF_CTX + (int)sizeof(FzCtx)); // double cz[PC + 1], ends where ALIAS starts
+    static constexpr int OFF_ALIAS = OFF_CZ + fz_align16((PC + 1) * 8);
+    static constexpr int C_BYTES = FZ_B * 8 + FZ_B * 4 + (FZ_B + 4) * 4;    // prefix block, y block, est block; back: soft + bits staging
+    static constexpr int BYTES = OFF_ALIAS + fz_align16(C_BYTES);
+};
+
+struct FzsCbParams {
+    const ChanDesc* desc; ChanState* state; float* ring_base; int n_channels;
+    const float2* sel; const float* theta;
+    float2* out_soft; int16_t* out_bits; float* out_phase;
+    double sri_xdelta; DevCounters* counters;
+    TpCtl tp;                          // items: one unit per item; else one unit per channel (all its packets, from state[ch])
+    int n_units; int* ticket;
+};
+
+// set-up of one chain unit; false: nothing to do for this ticket
+template <int PC>
+static __device__ __noinline__ bool fzs_cb_begin(const FzsCbParams& prm, const unsigned wofs, const int u)
+{
+    using L = FzsCbL<PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    const int lane = threadIdx.x & 31;
+    const TpCtl& tp = prm.tp;
+    int ch, pk_a = 0, pk_b = -1, kind = 0, src = -1, dst = -1, pkt_slot = -1;
+    if (tp.items) {
+        const TpItem it = tp.items[u];
+        ch = it.ch; pk_a = it.pk_a; pk_b = it.pk_b; kind = it.kind; src = it.src; dst = it.dst; pkt_slot = it.pkt_slot;
+        if (!(prm.desc[ch].flags & CH_FZS)) return false;
+        if (tp.rerun) {                                   // repair round: only what k_tp_fix asked for
+            const int r = tp.slot_run[pkt_slot];
+            if (r == 0) return false;
+            kind = r;
+            if (r == 2) src = dst - 1;                    // from the proven predecessor's exact end record
+        }
+    } else {
+        ch = u;
+        const int fl = prm.desc[ch].flags;
+        if (!(fl & CH_FZS)) return false;
+        if (tp.fallback) { if (!(fl & CH_TP) || !tp.fail[ch]) return false; }   // re-run of a channel whose hand-overs were not proven
+        else if (fl & CH_TP) return false;                                       // handled through TpItems
+    }
+    const ChanDesc* dgp = prm.desc + ch;
+    const int P = dgp->P, M = dgp->M, S = dgp->S, A = dgp->A, n_pkts = dgp->n_pkts;
+    const int K = (int)dgp->K;
+    const long long pkt_len = dgp->pkt_len, tail_len = dgp->tail_len;
+    const float* thg = prm.theta + dgp->scr_off;
+    if (pk_b < 0) pk_b = n_pkts;
+    const int k_begin = (pk_a == 0) ? 0 : (int)first_symbol_at((long long)pk_a * pkt_len, tail_len, S, A, K);
+    __syncwarp();
+    if (kind == 0) {
+        if (lane == 0) { cx.st = prm.state[ch]; cx.flags = dgp->flags; }
+        const float* gring = prm.ring_base + dgp->ring_off;
+        for (int j = lane; j < P; j += 32) yh[j] = gring[j];
+    } else if (kind == 2) {
+        if (lane == 0) { cx.st = tp.ends[src].st; cx.flags = dgp->flags & ~(CH_RESET_NUMSYMS | CH_RESET_PHASEAVG); }
+        for (int j = lane; j < P; j += 32) {
+            const float v = tp.end_ring[(size_t)src * tp.ring_stride + j];
+            yh[j] = v;
+            if (dst >= 0) tp.start_ring[(size_t)dst * tp.ring_stride + j] = v;       // what k_tp_check compares
+        }
+    } else {
+        // synthesised start of packet pk_a (see k_chain_par): the history ring the previous packet leaves behind,
+        // from the resolved integers: y = f32(theta + 2pi(c + A)), then the packet-end shift f32(y - w*wrapValue)
+        const TpPacket pp = tp.pkts[pkt_slot - 1];
+        const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)M));
+        const float shift = fmulr((float)pp.w, wrapValue);
+        int carry = 0;
+        for (int e = k_begin; e > k_begin - P; e -= 32) {
+            const int m = e - 1 - lane;
+            int dn = 0;
+            float t = 0.0f;
+            const bool in = m >= k_begin - P;
+            if (in) { t = __ldg(thg + m); dn = -__float2int_rn((t - __ldg(thg + m - 1)) * 0.15915494309189535f); }
+            const int incl = warp_scan_int(dn, lane);
+            if (in) {
+                const int c = pp.cEnd - (carry + incl - dn);
+                float y = __double2float_rn(daddr((double)t, dmulr((double)(c + pp.A), PSKD_M_2PI)));
+                if (pp.w != 0) y = fsubr(y, shift);                                      // :131 (subtractConst)
+                yh[m - (k_begin - P)] = y;
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            cx.st = (src >= 0) ? tp.ends[src].st : prm.state[ch];   // fit constants (xdelta, denominator, n) of the channel
+            cx.st.fit.head = 0; cx.st.fit.pts = P; cx.st.wraps = 0;
+            SmemRing ring{yh};
+            cx.st.est = fit_resum(cx.st.fit, ring);
+            cx.flags = dgp->flags & ~(CH_RESET_NUMSYMS | CH_RESET_PHASEAVG);
+        }
+        __syncwarp();
+        if (dst >= 0) for (int j = lane; j < P; j += 32) tp.start_ring[(size_t)dst * tp.ring_stride + j] = yh[j];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const long long sym_off = dgp->sym_off;
+        cx.passes = 0; cx.seq_blocks = 0; cx.blocks = 0;
+        cx.desc = dgp;
+        cx.o_soft = prm.out_soft ? prm.out_soft + sym_off : nullptr;
+        cx.o_phase = prm.out_phase ? prm.out_phase + sym_off : nullptr;
+        cx.o_bits = prm.out_bits ? prm.out_bits + dgp->bits_off : nullptr;
+        cx.o_sidx = nullptr;
+        cx.sri_xdelta = prm.sri_xdelta;
+        cx.tail_len = tail_len; cx.pkt_len = pkt_len;
+        cx.n_pkts = n_pkts; cx.pk1 = pk_b; cx.K = K; cx.A = A; cx.M = M; cx.P = P; cx.bpb = dgp->bpb; cx.diff = dgp->D;
+        cx.pkt = pk_a; cx.kchain = k_begin; cx.nbuf = 0; cx.cz_valid = 0; cx.unit_done = (pk_a >= pk_b) ? 1 : 0;
+        cx.fP1 = (float)(P - 1);
+        cx.pk_hi = (pk_a + 1 >= n_pkts) ? K : (int)first_symbol_at((long long)(pk_a + 1) * pkt_len, tail_len, S, A, K);
+        cx.end_mid = 0;
+        cx.ch = ch; cx.S_rt = S; cx.dst = dst; cx.k_begin = k_begin;
+        cx.est_start_used = cx.st.est;
+        cx.n_first = 0; cx.n_last = 0; cx.have_first = 0; cx.est_pre = cx.st.est;
+        cx.wraps0 = cx.st.wraps;
+        selb[1] = (k_begin > 0) ? prm.sel[dgp->scr_off + k_begin - 1] : cx.st.last;         // :486-489
+        if (pk_a < pk_b) fz_prologue(cx, yh);
+    }
+    __syncwarp();
+    return true;
+}
+
+template <int PC>
+static __device__ __noinline__ void fzs_cb_end(const FzsCbParams& prm, const unsigned wofs)
+{
+    using L = FzsCbL<PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    const int lane = threadIdx.x & 31;
+    const int P = cx.P, ch = cx.ch, dst = cx.dst;
+    const TpCtl& tp = prm.tp;
+    if (cx.st.fit.head != 0 && cx.st.fit.pts == P)
+        fz_normalize_ring(yh, reinterpret_cast<float*>(wb + L::OFF_ALIAS), cx.st.fit, P, lane);
+    __syncwarp();
+    if (dst >= 0) {
+        for (int j = lane; j < P; j += 32) tp.end_ring[(size_t)dst * tp.ring_stride + j] = yh[j];
+        if (lane == 0) {
+            TpEnd& e = tp.ends[dst];
+            e.st = cx.st; e.est_start_used = cx.est_start_used; e.has_symbols = (cx.kchain > cx.k_begin) ? 1 : 0;
+            e.wraps_delta = cx.st.wraps - cx.wraps0;
+            e.n_first = cx.n_first; e.n_last = cx.n_last; e.est_pre = cx.est_pre; e.pad = 0;
+        }
+    } else {
+        float* gring = prm.ring_base + cx.desc->ring_off;
+        for (int j = lane; j < P; j += 32) gring[j] = yh[j];
+        if (lane == 0) prm.state[ch] = cx.st;              // `last` is carried by k_finish
+    }
+    if (lane == 0) {
+        if (cx.st.wraps != cx.wraps0) atomicAdd(&prm.counters->wraps, cx.st.wraps - cx.wraps0);
+        if (cx.blocks) atomicAdd(&prm.counters->spec_chunks, (unsigned long long)cx.blocks);
+        if (cx.passes) atomicAdd(&prm.counters->spec_misses, (unsigned long long)cx.passes);
+        if (cx.seq_blocks) atomicAdd(&prm.counters->seq_channels, (unsigned long long)cx.seq_blocks);
+    }
+    __syncwarp();
+}
+
+template <int PC>
+__global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZS_CB_MIN_CTAS)
+k_fzs_cb(const FzsCbParams prm)
+{
+    using L = FzsCbL<PC>;
+    const int lane = fz_lane();
+    const unsigned wofs = (threadIdx.x >> 5) * (unsigned)L::BYTES;
+    unsigned char* wb = fz_smem + wofs;
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(prm.ticket, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= prm.n_units) break;
+        if (!fzs_cb_begin<PC>(prm, wofs, u)) continue;
+        const float* thg = prm.theta + cx.desc->scr_off;
+        const float2* selg = prm.sel + cx.desc->scr_off;
+        for (;;) {
+            fz_drain<L>(wofs);
+            if (cx.unit_done) break;
+            // the next block of (angle, sample) pairs from the scratch, appended to the block buffer
+            const int nbuf = cx.nbuf, k0 = cx.kchain + nbuf;
+            const int want = min(FZ_B, cx.pk_hi - cx.kchain);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < FZ_B / 32; q++) {
+                const int i = nbuf + lane + 32 * q;
+                if (i < want) {
+                    th[i] = __ldg(thg + k0 - nbuf + i);
+                    selb[2 + i] = __ldg(selg + k0 - nbuf + i);
+                }
+            }
+            if (lane == 0) cx.nbuf = want;
+            __syncwarp();
+        }
+        fzs_cb_end<PC>(prm, wofs);
     }
 }
 
@@ -1212,33 +1705,115 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_sidx = c.out_sidx;
     p.sri_xdelta = c.sri_xdelta;
     p.counters = c.d_counters;
-    static size_t pad = getenv("PSKD_FZ_PAD_SMEM") ? (size_t)atoi(getenv("PSKD_FZ_PAD_SMEM")) : 0;   // tuning: lowers occupancy
+    static const size_t pad = getenv("PSKD_FZ_PAD_SMEM") ? (size_t)atoi(getenv("PSKD_FZ_PAD_SMEM")) : 0;   // tuning: lowers occupancy
+    static const int carve = getenv("PSKD_FZ_CARVEOUT") ? atoi(getenv("PSKD_FZ_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;   // tuning: % of the maximum
     const size_t smem = (size_t)L::BYTES * FZ_WARPS + pad;
-    static int ctas_per_sm = 0, n_sm = 0;
-    cudaError_t e;
-    if (ctas_per_sm == 0) {
-        e = cudaFuncSetAttribute(k_fused<S, PC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        static const int carve = getenv("PSKD_FZ_CARVEOUT") ? atoi(getenv("PSKD_FZ_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;   // tuning: % of the maximum
-        e = cudaFuncSetAttribute(k_fused<S, PC>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_fused<S, PC>, FZ_WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (ctas_per_sm < 1) { ctas_per_sm = 0; return cudaErrorInvalidConfiguration; }
-        int dev = 0;
-        e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (e != cudaSuccess) return e;
-    }
+    static KernelCfg cfg;                       // per device (function attributes and occupancy are per device)
+    int ctas_per_sm = 0, n_sm = 0;
+    cudaError_t e = cfg.ensure(k_fused<S, PC>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm, carve);
+    if (e != cudaSuccess) return e;
     int grid = n_sm * ctas_per_sm;
     const int need = (p.n_units + FZ_WARPS - 1) / FZ_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    c.prof->begin(KID_FUSED, c.stream);
+    double ab = 0.0;
+    if (c.prof->enabled && f.h_list)
+        for (int i = 0; i < f.n_list; i++) { const ChanDesc& d = c.h_desc[f.h_list[i]]; ab += alg_bytes_front(d) + alg_bytes_chain(d) + alg_bytes_back(d); }
+    c.prof->begin(S == 8 ? KID_FUSED : S == 9 ? KID_FUSED_S9 : S == 10 ? KID_FUSED_S10 : KID_FUSED_S16, c.stream, ab);
     k_fused<S, PC><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
     c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
 }
+
+// ---- staged path through the fused kernel's stages ---------------------------------------------
+static int* fzs_take_ticket(const LaunchCtx& c) {
+    if (!c.d_fzs_ticket || !c.fzs_ticket_next || *c.fzs_ticket_next >= c.fzs_ticket_cap) return nullptr;
+    return c.d_fzs_ticket + (*c.fzs_ticket_next)++;
+}
+
+template <int S>
+static cudaError_t launch_fzs_front_t(const LaunchCtx& c) {
+    using L = FzsFL<S>;
+    const size_t smem = (size_t)L::BYTES * FZ_WARPS;
+    static KernelCfg cfg;
+    int ctas_per_sm = 0, n_sm = 0;
+    cudaError_t e = cfg.ensure(k_fzs_front<S>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm);
+    if (e != cudaSuccess) return e;
+    FzsFrontParams p{};
+    p.desc = c.d_desc; p.n_channels = c.n_channels;
+    // unit = a segment of one channel: >= ~8 units per resident warp when the call is large enough, 1024..8192 symbols
+    static const int seg_env = getenv("PSKD_FZS_SEG") ? atoi(getenv("PSKD_FZS_SEG")) : 0;
+    const long long slots = (long long)n_sm * ctas_per_sm * FZ_WARPS;
+    long long seg = seg_env > 0 ? seg_env : (c.Kmax_fzs * c.n_fzs_channels) / (8 * slots);
+    seg = (seg + 31) & ~31LL;
+    if (seg < 1024) seg = 1024;
+    if (seg > 8192 && seg_env <= 0) seg = 8192;
+    p.seg_syms = (int)seg;
+    const long long nseg = (c.Kmax_fzs + seg - 1) / seg;
+    if (nseg * c.n_channels > 0x7fffffffLL) return cudaErrorInvalidValue;
+    p.n_units = (int)(nseg * c.n_channels);
+    p.ticket = fzs_take_ticket(c);
+    if (!p.ticket) return cudaErrorInvalidValue;
+    p.sel = c.d_sel; p.theta = c.d_theta; p.out_sidx = c.out_sidx;
+    int grid = n_sm * ctas_per_sm;
+    const int need = (p.n_units + FZ_WARPS - 1) / FZ_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    double ab = 0.0;
+    if (c.prof->enabled) for (int i = 0; i < c.n_channels; i++) { const ChanDesc& d = c.h_desc[i]; if ((d.flags & CH_FZS) && d.S == S) ab += alg_bytes_front(d); }
+    c.prof->begin(KID_FZS_FRONT, c.stream, ab);
+    k_fzs_front<S><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
+    c.prof->end(c.stream);
+    (*c.launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fzs_front(const LaunchCtx& c) {
+    if (c.n_fzs_channels == 0 || c.Kmax_fzs <= 0) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (c.S_mask_fzs & (1ull << 8))  { e = launch_fzs_front_t<8>(c);  if (e != cudaSuccess) return e; }
+    if (c.S_mask_fzs & (1ull << 9))  { e = launch_fzs_front_t<9>(c);  if (e != cudaSuccess) return e; }
+    if (c.S_mask_fzs & (1ull << 10)) { e = launch_fzs_front_t<10>(c); if (e != cudaSuccess) return e; }
+    if (c.S_mask_fzs & (1ull << 16)) { e = launch_fzs_front_t<16>(c); if (e != cudaSuccess) return e; }
+    return e;
+}
+
+template <int PC>
+static cudaError_t launch_fzs_cb_t(const LaunchCtx& c, const TpCtl& tp, int n_units, double alg_bytes) {
+    using L = FzsCbL<PC>;
+    const size_t smem = (size_t)L::BYTES * FZ_WARPS;
+    static KernelCfg cfg;
+    int ctas_per_sm = 0, n_sm = 0;
+    cudaError_t e = cfg.ensure(k_fzs_cb<PC>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm);
+    if (e != cudaSuccess) return e;
+    FzsCbParams p{};
+    p.desc = c.d_desc; p.state = c.d_state; p.ring_base = c.d_ring; p.n_channels = c.n_channels;
+    p.sel = c.d_sel; p.theta = c.d_theta;
+    p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase;
+    p.sri_xdelta = c.sri_xdelta; p.counters = c.d_counters;
+    p.tp = tp;
+    p.n_units = n_units;
+    p.ticket = fzs_take_ticket(c);
+    if (!p.ticket) return cudaErrorInvalidValue;
+    int grid = n_sm * ctas_per_sm;
+    const int need = (n_units + FZ_WARPS - 1) / FZ_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) return cudaSuccess;
+    c.prof->begin(KID_FZS_CB, c.stream, alg_bytes);
+    k_fzs_cb<PC><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
+    c.prof->end(c.stream);
+    (*c.launches)++;
+    return cudaGetLastError();
+}
+
+// one launch of the chain + back kernel: tp.items != null -> one unit per item, else one unit per channel
+cudaError_t launch_fzs_cb(const LaunchCtx& c, const TpCtl& tp, int n_units, double alg_bytes) {
+    if (n_units <= 0) return cudaSuccess;
+    return c.Pmax_fzs <= 52 ? launch_fzs_cb_t<52>(c, tp, n_units, alg_bytes) : launch_fzs_cb_t<128>(c, tp, n_units, alg_bytes);
+}
+
+bool fzs_supports(int S, int A, int P) { return fused_supports(S, A, P); }
 
 bool fused_supports(int S, int A, int P) {
     if (!(S == 8 || S == 9 || S == 10 || S == 16)) return false;

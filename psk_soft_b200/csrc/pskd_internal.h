@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "pskd_exact.cuh"
 
 namespace pskd {
@@ -30,7 +31,11 @@ enum { CH_RESET_NUMSYMS = 1, CH_RESET_PHASEAVG = 2, CH_SRI_CHANGED = 4,
        CH_FAST = 8 /* phase chain + back run in k_chain_par (scan-based), else k_chain_seq + k_back */,
        CH_FRONT_FAST = 16 /* timing runs in k_front_t<S>, else in the generic k_front */,
        CH_FUSED = 32 /* the whole path of this channel runs in k_fused<S> (pskd_fused.cu); the staged kernels skip it */,
-       CH_TP = 64 /* staged path: the phase chain of this channel runs time-parallel over its packets (TpCtl) */ };
+       CH_TP = 64 /* staged path: the phase chain of this channel runs time-parallel over its packets (TpCtl) */,
+       CH_FZS = 128 /* staged path through the fused kernel's stages: k_fzs_front<S> + k_fzs_cb (pskd_fused.cu) instead of
+                       k_front_t + k_chain_par + k_back_par */,
+       CH_STALLED = 256 /* the timing window is over-full (numAvg*samplesPerBaud shrank): the channel consumes its input and emits
+                           nothing (cpp/psk_soft.cpp:457); of the packet prologue only what a pending reset asks for runs */ };
 constexpr int FRONT_FAST_AMAX = 768;   // largest numAvg the specialised front tile (1024 symbols) still uses efficiently
 constexpr int CHAIN_PAR_PMAX = 1024;
 constexpr int FUSED_AMAX = 256;        // largest numAvg whose energy ring the fused kernel keeps in shared memory
@@ -74,7 +79,7 @@ struct TpItem {            // one warp of work for k_chain_par
     int ch;                // channel (index into d_desc)
     int pk_a, pk_b;        // emulated packets [pk_a, pk_b)
     int kind;              // 0: start from state[ch]; 1: synthesised start of packet pk_a; 2: start from end record `src`
-    int src;               // kind 2: end record to start from; kind 1: end record holding the channel's fit constants
+    int src;               // kind 2: end record to start from; kind 1: end record holding the channel's fit constants (< 0: state[ch])
     int dst;               // end record this item writes
     int pkt_slot;          // index of packet pk_a in the TpPacket array
     int pad;
@@ -92,12 +97,18 @@ struct TpEnd {             // what a chain item leaves behind
     float est_start_used;  // the estimate the item's first symbol was unwrapped against
     int   has_symbols;
     unsigned long long wraps_delta;
+    // k_fzs_cb items only (the repair round of k_tp_fix): the EXACT unwrap counts of the item's first and last
+    // symbol (in the frame of the level it ran at) and the estimate before the last packet-end wrap
+    int   n_first, n_last;
+    float est_pre;
+    int   pad;
 };
 struct TpChan {            // per time-parallel channel
     int ch, pkt0, n_pkts;  // first time-parallel packet, packets in the call
-    int first_item;        // index of the channel's first TpItem (the sequential head); items follow in packet order
+    int first_item;        // index of the channel's first end record (the sequential head's, if any); records follow in packet order
     int first_slot;        // index of packet pkt0 in the TpPacket array
-    int pad;
+    int has_head;          // 1: packets [0, pkt0) ran as a sequential head item (record first_item); 0: pkt0 == 0, the first
+                           //    packet starts from the channel's carried state (its history is known to be full)
 };
 struct TpCtl {
     const TpItem* items; int n_items;
@@ -106,23 +117,67 @@ struct TpCtl {
     TpEnd* ends; float* end_ring; float* start_ring; int ring_stride;   // per item: ring after the last epilogue / ring the item started from
     int* fail;             // [n_channels] set by k_tp_check when a hand-over could not be proven
     int fallback;          // launch flag: process only channels with fail[ch] != 0, from state[ch]
+    // repair round (k_tp_fix, k_fzs_cb channels): per packet slot
+    int* slot_fail;        // set by k_tp_check: the hand-over INTO this packet could not be proven
+    int* slot_run;         // set by k_tp_fix: 0 leave, 1 re-run from a re-synthesised ring, 2 re-run from the predecessor's end record
+    int rerun;             // launch flag: process only items with slot_run != 0
 };
 
 // ---- optional per-kernel event timing --------------------------------------------------------
-enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_FUSED, KID_TP, KID_COUNT };
+enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_FUSED, KID_TP, KID_FZS_FRONT, KID_FZS_CB, KID_FUSED_S9, KID_FUSED_S10, KID_FUSED_S16, KID_COUNT };
 struct Profiler {
     bool enabled = false;
     struct Pair { cudaEvent_t a, b; int kid; };
     Pair* pending = nullptr; int n_pending = 0, cap_pending = 0;
     cudaEvent_t* pool = nullptr; int n_pool = 0, cap_pool = 0;
     double ms[KID_COUNT] = {0}; unsigned long long launches[KID_COUNT] = {0};
+    double bytes[KID_COUNT] = {0};   // algorithmic bytes of the channels the timed launches served
     cudaEvent_t get();
-    void begin(int kid, cudaStream_t s);
+    void begin(int kid, cudaStream_t s, double alg_bytes = 0.0);
     void end(cudaStream_t s);
     void drain();          // caller has synchronised the stream
     void destroy();
 };
 const char* kernel_name(int kid);
+
+// ---- per-device launch configuration of one kernel --------------------------------------------
+// cudaFuncSetAttribute (dynamic shared memory opt-in, carve-out) and the occupancy it yields are PER DEVICE:
+// a process that drives several GPUs (one bank per GPU, one host thread each -- include/pskd.h) must
+// configure every kernel once on every device it launches on.
+constexpr int PSKD_MAX_DEVICES = 64;
+struct KernelCfg {
+    std::mutex mu;
+    size_t smem[PSKD_MAX_DEVICES] = {};
+    int ctas[PSKD_MAX_DEVICES] = {}, nsm[PSKD_MAX_DEVICES] = {};
+    bool done[PSKD_MAX_DEVICES] = {};
+    // make `kernel` launchable with `need` bytes of dynamic shared memory on the current device; optionally
+    // returns resident CTAs per SM (for `threads` per CTA) and the SM count
+    template <class K>
+    cudaError_t ensure(K kernel, size_t need, int threads, int* ctas_per_sm = nullptr, int* n_sm = nullptr, int carveout = -2) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= PSKD_MAX_DEVICES) return cudaErrorInvalidDevice;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!done[dev] || need > smem[dev]) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     carveout == -2 ? (int)cudaSharedmemCarveoutMaxShared : carveout);
+            if (e != cudaSuccess) return e;
+            int c = 0, n = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kernel, threads, need);
+            if (e != cudaSuccess) return e;
+            if (c < 1) return cudaErrorInvalidConfiguration;
+            e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+            if (e != cudaSuccess) return e;
+            smem[dev] = need; ctas[dev] = c; nsm[dev] = n; done[dev] = true;
+        }
+        if (ctas_per_sm) *ctas_per_sm = ctas[dev];
+        if (n_sm) *n_sm = nsm[dev];
+        return cudaSuccess;
+    }
+};
 
 // ---- kernel launchers (pskd_kernels.cu) ----
 struct LaunchCtx {
@@ -135,6 +190,7 @@ struct LaunchCtx {
     int Amax_fast, Amin_fast;
     int n_seq_channels, n_fast_channels;
     const ChanDesc* d_desc;
+    const ChanDesc* h_desc;  // the same descriptors on the host (valid during the call)
     ChanState* d_state;
     float* d_ring;
     float2* d_sel;           // scratch: timing-selected sample per symbol
@@ -150,13 +206,22 @@ struct LaunchCtx {
     const TpItem* tp_items; int tp_n_items;          // one item per time-parallel packet
     const TpChan* tp_chans; int tp_n_chans; int tp_n_slots;
     TpPacket* tp_pkts; TpEnd* tp_ends; float* tp_end_ring; float* tp_start_ring; int tp_ring_stride;
-    int* tp_fail;
+    int* tp_fail; int* tp_slot_fail; int* tp_slot_run;
+    int tp_n_chans_fzs;      // how many of the time-parallel channels run through k_fzs_cb (the rest through k_chain_par)
+    // staged path through the fused kernel's stages (CH_FZS channels)
+    int n_fzs_channels, Pmax_fzs;
+    unsigned long long S_mask_fzs;
+    long long Kmax_fzs;
+    int* d_fzs_ticket;       // zeroed ticket counters for this call's k_fzs_* launches
+    int* fzs_ticket_next;    // host-side index of the next unused counter
+    int fzs_ticket_cap;
 };
 
 // one launch of the fused kernel: the CH_FUSED channels of one samplesPerBaud value
 struct FusedLaunch {
     int S;
     const int* d_list; int n_list;     // channel indices (relative to LaunchCtx::d_desc)
+    const int* h_list;                 // the same list on the host
     int units_per_channel;             // ceil(max n_pkts / pkts_per_unit)
     int pkts_per_unit;
     int parts_per_pkt;                 // > 1 (only with pkts_per_unit == 1): every packet is cut into this many units
@@ -164,8 +229,16 @@ struct FusedLaunch {
     int* d_ticket;                     // one int, zero before the launch
     int* d_done;                       // [n_channels] zero before the launch (indexed like d_desc)
 };
+// algorithmic bytes of a channel's stages (8 N in; per symbol 8 soft + 4 phase + 2 sampleIndex + 2 b bits)
+inline double alg_bytes_front(const ChanDesc& d) { return 8.0 * (double)d.n_in + 2.0 * (double)d.K; }
+inline double alg_bytes_chain(const ChanDesc& d) { return 4.0 * (double)d.K; }
+inline double alg_bytes_back(const ChanDesc& d) { return (8.0 + 2.0 * d.bpb) * (double)d.K; }
 bool fused_supports(int S, int A, int P);
 cudaError_t launch_fused(const LaunchCtx& c, const FusedLaunch& f);
+
+cudaError_t launch_fzs_front(const LaunchCtx& c);
+cudaError_t launch_fzs_cb(const LaunchCtx& c, const TpCtl& tp, int n_units, double alg_bytes = 0.0);
+bool fzs_supports(int S, int A, int P);
 
 cudaError_t launch_front(const LaunchCtx& c);
 cudaError_t launch_chain_seq(const LaunchCtx& c);

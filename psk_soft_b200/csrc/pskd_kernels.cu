@@ -10,11 +10,12 @@
 // reference's rounding order through the intrinsics of pskd_exact.cuh.
 #include "pskd_internal.h"
 #include "pskd_device.cuh"
+#include <cstdlib>
 
 namespace pskd {
 
 const char* kernel_name(int kid) {
-    static const char* names[KID_COUNT] = {"k_front", "k_chain_seq", "k_chain_par", "k_back_par", "k_chain_exact", "k_back", "k_finish", "k_fused", "k_tp_aux"};
+    static const char* names[KID_COUNT] = {"k_front", "k_chain_seq", "k_chain_par", "k_back_par", "k_chain_exact", "k_back", "k_finish", "k_fused", "k_tp_aux", "k_fzs_front", "k_fzs_cb", "k_fused_s9", "k_fused_s10", "k_fused_s16"};
     return (kid >= 0 && kid < KID_COUNT) ? names[kid] : "?";
 }
 cudaEvent_t Profiler::get() {
@@ -23,8 +24,9 @@ cudaEvent_t Profiler::get() {
     cudaEventCreate(&e);
     return e;
 }
-void Profiler::begin(int kid, cudaStream_t s) {
+void Profiler::begin(int kid, cudaStream_t s, double alg_bytes) {
     if (!enabled) return;
+    bytes[kid] += alg_bytes;
     if (n_pending == cap_pending) {
         int nc = cap_pending ? 2 * cap_pending : 64;
         Pair* np = new Pair[nc];
@@ -81,7 +83,7 @@ k_front(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
         float2* __restrict__ sel, float* __restrict__ theta, unsigned long long S_mask)
 {
     const ChanDesc& d = desc[blockIdx.y];
-    if (d.flags & (CH_FRONT_FAST | CH_FUSED)) return;   // handled by the specialised / fused kernel
+    if (d.flags & (CH_FRONT_FAST | CH_FUSED | CH_FZS)) return;   // handled by the specialised / fused kernels
     const long long k0 = (long long)blockIdx.x * FT;
     if (k0 >= d.K) return;
     const int S = d.S, A = d.A, M = d.M;
@@ -192,7 +194,7 @@ k_front_t(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
     using C = FrontCfg<S>;
     constexpr int SE = C::SE;
     const ChanDesc& d = desc[blockIdx.y];
-    if (d.S != S || !(d.flags & CH_FRONT_FAST) || (d.flags & CH_FUSED)) return;
+    if (d.S != S || !(d.flags & CH_FRONT_FAST) || (d.flags & (CH_FUSED | CH_FZS))) return;
     const int A = d.A;
     const int T_out = FT_ROWS - A + 1;           // output symbols per tile (host guarantees >= 64)
     const long long k0 = (long long)blockIdx.x * T_out;
@@ -395,19 +397,18 @@ k_front_t(const ChanDesc* __restrict__ desc, int16_t* __restrict__ out_sidx,
 template <int S>
 static cudaError_t launch_front_t(const LaunchCtx& c) {
     using C = FrontCfg<S>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_front_t<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    static KernelCfg cfg;
+    {
+        cudaError_t e = cfg.ensure(k_front_t<S>, C::SMEM, FT_THREADS);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_front_t<S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = true;
     }
     const int T_out = FT_ROWS - c.Amin_fast + 1;   // smallest tile count that covers every fast channel is per channel; use the worst case
     (void)T_out;
     const int T_min = FT_ROWS - c.Amax_fast + 1;
     dim3 grid((unsigned)((c.Kmax + T_min - 1) / T_min), (unsigned)c.n_channels);
-    c.prof->begin(KID_FRONT, c.stream);
+    double ab = 0.0;
+    if (c.prof->enabled) for (int i = 0; i < c.n_channels; i++) { const ChanDesc& d = c.h_desc[i]; if (d.S == S && (d.flags & CH_FRONT_FAST) && !(d.flags & (CH_FUSED | CH_FZS))) ab += alg_bytes_front(d); }
+    c.prof->begin(KID_FRONT, c.stream, ab);
     k_front_t<S><<<grid, FT_THREADS, C::SMEM, c.stream>>>(c.d_desc, c.out_sidx, c.d_sel, c.d_theta);
     c.prof->end(c.stream);
     (*c.launches)++;
@@ -427,14 +428,13 @@ cudaError_t launch_front(const LaunchCtx& c) {
     if (!mask) return cudaSuccess;
     int SPmax = c.Smax | 1;
     size_t smem = ((size_t)(FT + c.Amax) * SPmax + (size_t)(FRONT_THREADS / 2) * SPmax) * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        e = cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    static KernelCfg cfg;
+    e = cfg.ensure(k_front, smem, FRONT_THREADS, nullptr, nullptr, -1 /* default carve-out */);
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((c.Kmax + FT - 1) / FT), (unsigned)c.n_channels);
-    c.prof->begin(KID_FRONT, c.stream);
+    double ab = 0.0;
+    if (c.prof->enabled) for (int i = 0; i < c.n_channels; i++) { const ChanDesc& d = c.h_desc[i]; if (!(d.flags & (CH_FRONT_FAST | CH_FUSED | CH_FZS))) ab += alg_bytes_front(d); }
+    c.prof->begin(KID_FRONT, c.stream, ab);
     k_front<<<grid, FRONT_THREADS, smem, c.stream>>>(c.d_desc, c.out_sidx, c.d_sel, c.d_theta, mask);
     c.prof->end(c.stream);
     (*c.launches)++;
@@ -480,7 +480,9 @@ cudaError_t launch_chain_seq(const LaunchCtx& c) {
     int threads = 32;
     int blocks = (c.n_channels + threads - 1) / threads;
     float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
-    c.prof->begin(KID_CHAIN_SEQ, c.stream);
+    double ab = 0.0;
+    if (c.prof->enabled) for (int i = 0; i < c.n_channels; i++) { const ChanDesc& d = c.h_desc[i]; if (!(d.flags & (CH_FAST | CH_FUSED))) ab += alg_bytes_chain(d); }
+    c.prof->begin(KID_CHAIN_SEQ, c.stream, ab);
     k_chain_seq<<<blocks, threads, 0, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, phase,
                                                   c.sri_xdelta, c.n_channels, c.d_counters);
     c.prof->end(c.stream);
@@ -523,7 +525,9 @@ cudaError_t launch_back(const LaunchCtx& c) {
     if (c.n_seq_channels == 0) return cudaSuccess;
     dim3 grid((unsigned)((c.Kmax + 255) / 256), (unsigned)c.n_channels);
     const float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
-    c.prof->begin(KID_BACK, c.stream);
+    double ab = 0.0;
+    if (c.prof->enabled) for (int i = 0; i < c.n_channels; i++) { const ChanDesc& d = c.h_desc[i]; if (!(d.flags & (CH_FAST | CH_FUSED))) ab += alg_bytes_back(d); }
+    c.prof->begin(KID_BACK, c.stream, ab);
     k_back<<<grid, 256, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
     c.prof->end(c.stream);
     (*c.launches)++;
@@ -652,10 +656,11 @@ k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, fl
         if (widx >= tp.n_items) return;
         const TpItem it = tp.items[widx];
         ch = it.ch; pk_a = it.pk_a; pk_b = it.pk_b; kind = it.kind; src = it.src; dst = it.dst; pkt_slot = it.pkt_slot;
+        if (desc[ch].flags & CH_FZS) return;                                            // k_fzs_cb's item
     } else {
         ch = widx;
         if (ch >= n_channels) return;
-        if (!(desc[ch].flags & CH_FAST) || (desc[ch].flags & CH_FUSED)) return;
+        if (!(desc[ch].flags & CH_FAST) || (desc[ch].flags & (CH_FUSED | CH_FZS))) return;
         if (tp.fallback) { if (!(desc[ch].flags & CH_TP) || !tp.fail[ch]) return; }   // re-run of a channel whose hand-overs were not proven
         else if (desc[ch].flags & CH_TP) return;                                        // handled through TpItems
     }
@@ -712,7 +717,7 @@ k_chain_par(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, fl
         }
         __syncwarp();
         if (lane == 0) {
-            sh.st = tp.ends[src].st;                        // fit constants (xdelta, denominator, n) of the channel
+            sh.st = (src >= 0) ? tp.ends[src].st : state[ch];   // fit constants (xdelta, denominator, n) of the channel
             sh.st.fit.head = 0; sh.st.fit.pts = P; sh.st.wraps = 0;
             SmemRing ring{yb};
             sh.st.est = fit_resum(sh.st.fit, ring);         // exact after a wrap (:601-602); else within rounding of the
@@ -963,7 +968,7 @@ k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ stat
            float2* __restrict__ out_soft, int16_t* __restrict__ out_bits)
 {
     const ChanDesc& d = desc[blockIdx.y];
-    if (!(d.flags & CH_FAST) || (d.flags & CH_FUSED)) return;
+    if (!(d.flags & CH_FAST) || (d.flags & (CH_FUSED | CH_FZS))) return;
     const int K = (int)d.K;
     const int k0 = blockIdx.x * BP_TILE;
     if (k0 >= K) return;
@@ -1028,28 +1033,33 @@ k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ stat
 // k_tp_scan: one warp per (channel, packet): classic unwrap over the packet (integer scan) and the
 // linear-fit estimate of the relative phases at the packet end (double, regression over the last P)
 __global__ void __launch_bounds__(128)
-k_tp_scan(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, const TpChan* __restrict__ chans,
-          int n_chans, TpPacket* __restrict__ pkts, int n_slots)
+k_tp_scan(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, const TpItem* __restrict__ items,
+          int n_items, TpPacket* __restrict__ pkts)
 {
     const int lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (slot >= n_slots) return;
-    // which channel owns this slot (few channels: linear search)
-    int ci = 0;
-    while (ci + 1 < n_chans && chans[ci + 1].first_slot <= slot) ci++;
-    const TpChan tc = chans[ci];
-    const ChanDesc& d = desc[tc.ch];
-    const int pkt = tc.pkt0 + (slot - tc.first_slot);
+    const int iidx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (iidx >= n_items) return;
+    const TpItem it = items[iidx];                         // one item per time-parallel packet
+    const int slot = it.pkt_slot;
+    const ChanDesc& d = desc[it.ch];
+    const int pkt = it.pk_a;
     const int K = (int)d.K, P = d.P;
     const int klo = (int)first_symbol_at((long long)pkt * d.pkt_len, d.tail_len, d.S, d.A, K);
     const int khi = (pkt + 1 == d.n_pkts) ? K : (int)first_symbol_at((long long)(pkt + 1) * d.pkt_len, d.tail_len, d.S, d.A, K);
     const float* thg = theta + d.scr_off;
     int c = 0;                                             // count at the last symbol processed so far
-    for (int base = klo + 1; base < khi; base += 32) {
-        const int m = base + lane;
-        int dn = 0;
-        if (m < khi) dn = classic_dn(__ldg(thg + m), __ldg(thg + m - 1));
-        c += __shfl_sync(0xffffffffu, warp_scan_int(dn, lane), 31);
+    {
+        int acc = 0;                                       // per-lane partial sums, one warp reduction at the end
+        for (int base = klo + 1; base < khi; base += 128) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int m = base + lane + 32 * q;
+                if (m < khi) acc += classic_dn(__ldg(thg + m), __ldg(thg + m - 1));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        c = acc;
     }
     // regression of phi = theta + 2pi*c over the last min(P, n) symbols, evaluated at the newest one
     const int n = khi - klo, np = min(P, n);
@@ -1093,7 +1103,7 @@ k_tp_scan(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, co
 __global__ void __launch_bounds__(128)
 k_tp_resolve(const ChanDesc* __restrict__ desc, const float* __restrict__ theta,
              const TpChan* __restrict__ chans, int n_chans, TpPacket* __restrict__ pkts,
-             const TpEnd* __restrict__ ends)
+             const TpEnd* __restrict__ ends, const ChanState* __restrict__ state)
 {
     const int lane = threadIdx.x & 31;
     const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1105,29 +1115,35 @@ k_tp_resolve(const ChanDesc* __restrict__ desc, const float* __restrict__ theta,
     const int np = tc.n_pkts - tc.pkt0;
     const int M = d.M;
     // level of the first time-parallel packet: the reference's rule with the exact estimate the head left
+    // (no head: the channel's carried estimate)
     long long A = 0;
     {
         const TpPacket p0 = pkts[tc.first_slot];
-        if (p0.khi > p0.klo) { long long n = 0; (void)unwrap_against(ends[tc.first_item].st.est, thg[p0.klo], &n); A = n; }
+        const float est0 = tc.has_head ? ends[tc.first_item].st.est : state[tc.ch].est;
+        if (p0.khi > p0.klo) { long long n = 0; (void)unwrap_against(est0, thg[p0.klo], &n); A = n; }
     }
+    // |trunc(est)| > wrapValue (the integer abs of cpp/psk_soft.cpp:596)  <=>  |est| >= floor(wrapValue) + 1; the
+    // estimates here are regression values (not the exact chain's), every decision is proven later by k_tp_check
+    const float wrapThr = floorf(wrapValue) + 1.0f, rWrap = 1.0f / wrapValue;
+    double Ad = (double)A;
     for (int base = 0; base < np; base += 32) {
         const int j = base + lane;
-        int cEnd = 0, dNext = 0, has = 0; double er = 0.0;
+        int step = 0, has = 0; double er = 0.0;
         if (j < np) {
             const TpPacket p = pkts[tc.first_slot + j];
-            cEnd = p.cEnd; er = p.estRelEnd; has = p.khi > p.klo;
-            if (j + 1 < np) dNext = pkts[tc.first_slot + j + 1].dLink;
+            step = p.cEnd; er = p.estRelEnd; has = p.khi > p.klo;
+            if (j + 1 < np) step += pkts[tc.first_slot + j + 1].dLink;
         }
         int myA = 0, myW = 0;
         const int cnt = min(32, np - base);
         for (int l = 0; l < cnt; l++) {                       // uniform loop: every lane follows the same recurrence
-            const int c_l = __shfl_sync(0xffffffffu, cEnd, l), d_l = __shfl_sync(0xffffffffu, dNext, l), h_l = __shfl_sync(0xffffffffu, has, l);
+            const int s_l = __shfl_sync(0xffffffffu, step, l), h_l = __shfl_sync(0xffffffffu, has, l);
             const double e_l = __shfl_sync(0xffffffffu, er, l);
-            const float est_end = (float)(e_l + PSKD_M_2PI * (double)A);
+            const float est_end = (float)fma(PSKD_M_2PI, Ad, e_l);
             int w = 0;
-            if (h_l && wrap_needed(est_end, wrapValue)) w = (int)roundf(__fdiv_rn(est_end, wrapValue));
-            if (l == lane) { myA = (int)A; myW = w; }
-            A = A + c_l + d_l - (long long)M * w;
+            if (h_l && fabsf(est_end) >= wrapThr) w = (int)rintf(est_end * rWrap);
+            if (l == lane) { myA = (int)Ad; myW = w; }
+            Ad += (double)(s_l - M * w);
         }
         if (j < np) { pkts[tc.first_slot + j].A = myA; pkts[tc.first_slot + j].w = myW; }
     }
@@ -1158,7 +1174,65 @@ k_tp_check(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, c
         (void)unwrap_against(tp.ends[prev].st.est, t0, &n_true);
         same = n_used == n_true;
     }
-    if (!same && lane == 0) tp.fail[item.ch] = 1;
+    if (!same && lane == 0) { tp.fail[item.ch] = 1; if (tp.slot_fail) tp.slot_fail[item.pkt_slot] = 1; }
+}
+
+// k_tp_fix: the repair round (k_fzs_cb channels).  One warp per channel whose proof failed.  Packets before the
+// first unproven hand-over jf are exact (induction from the exact start).  What went wrong is the LEVEL: somewhere
+// the classic sample-to-sample count differs from the reference's unwrap-against-the-fit rule.  Every packet has
+// by now run the exact chain once, and the integer advance of the unwrap count over a packet does not depend on
+// the level it ran at -- so the exact advances replace the classic ones in the recurrence, packet jf restarts from
+// its predecessor's exact end record, and the later packets from re-synthesised rings; k_tp_check then proves the
+// new hand-overs.  A channel that fails again goes to the sequential chain.
+__global__ void __launch_bounds__(128)
+k_tp_fix(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, const TpCtl tp)
+{
+    const int lane = threadIdx.x & 31;
+    const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ci >= tp.n_chans) return;
+    const TpChan tc = tp.chans[ci];
+    const ChanDesc& d = desc[tc.ch];
+    const int np = tc.n_pkts - tc.pkt0;
+    const bool mine = (d.flags & CH_FZS) && tp.fail[tc.ch];
+    if (!mine) {
+        for (int j = lane; j < np; j += 32) tp.slot_run[tc.first_slot + j] = 0;
+        return;
+    }
+    int jf = 0x7fffffff;
+    for (int j = lane; j < np; j += 32) if (tp.slot_fail[tc.first_slot + j]) jf = min(jf, j);
+    jf = (int)__reduce_min_sync(0xffffffffu, (unsigned)jf);
+    if (jf < 1 || jf >= np) {                                         // nothing to restart from: stays failed
+        for (int j = lane; j < np; j += 32) tp.slot_run[tc.first_slot + j] = 0;
+        return;
+    }
+    for (int j = lane; j < np; j += 32) {
+        tp.slot_run[tc.first_slot + j] = (j < jf) ? 0 : (j == jf ? 2 : 1);
+        tp.slot_fail[tc.first_slot + j] = 0;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    const float* thg = theta + d.scr_off;
+    const int M = d.M;
+    const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)M));
+    const int rec0 = tc.first_item + tc.has_head;                     // end record of packet jj: rec0 + jj
+    // exact level of packet jf's first symbol: the reference's rule with the proven predecessor's end estimate
+    long long A = 0;
+    {
+        const TpPacket pf = tp.pkts[tc.first_slot + jf];
+        if (pf.khi > pf.klo) (void)unwrap_against(tp.ends[rec0 + jf - 1].st.est, thg[pf.klo], &A);
+    }
+    for (int j = jf; j < np; j++) {
+        TpPacket& p = tp.pkts[tc.first_slot + j];
+        const TpEnd& e = tp.ends[rec0 + j];
+        const int adv = e.has_symbols ? e.n_last - e.n_first : 0;     // exact advance over the packet (level-invariant)
+        const float est_end = (float)((double)e.est_pre + PSKD_M_2PI * (double)(A - (long long)e.n_first));
+        int w = 0;
+        if (e.has_symbols && wrap_needed(est_end, wrapValue)) w = (int)roundf(__fdiv_rn(est_end, wrapValue));
+        p.A = (int)A; p.w = w; p.cEnd = adv;
+        const int dl = (j + 1 < np) ? tp.pkts[tc.first_slot + j + 1].dLink : 0;
+        A = A + adv + dl - (long long)M * w;
+    }
+    tp.fail[tc.ch] = 0;                                               // the next k_tp_check decides again
 }
 
 // k_tp_install: one warp per channel: all hand-overs proven -> the last packet's end state becomes the
@@ -1175,10 +1249,11 @@ k_tp_install(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, f
     const int P = d.P, np = tc.n_pkts - tc.pkt0;
     if (tp.fail[tc.ch]) { if (lane == 0) atomicAdd(&counters->seq_channels, 1ULL); return; }
     unsigned long long wraps = 0;
-    for (int j = lane; j <= np; j += 32) wraps += tp.ends[tc.first_item + j].wraps_delta;
+    const int n_rec = np + tc.has_head;                               // end records of the channel: [head,] one per packet
+    for (int j = lane; j < n_rec; j += 32) wraps += tp.ends[tc.first_item + j].wraps_delta;
 #pragma unroll
     for (int o = 16; o; o >>= 1) wraps += __shfl_xor_sync(0xffffffffu, wraps, o);
-    const int last = tc.first_item + np;                              // record of the last packet
+    const int last = tc.first_item + n_rec - 1;                       // record of the last packet
     for (int i = lane; i < P; i += 32) ring_base[d.ring_off + i] = tp.end_ring[(size_t)last * tp.ring_stride + i];
     if (lane == 0) {
         ChanState st = tp.ends[last].st;
@@ -1188,11 +1263,11 @@ k_tp_install(const ChanDesc* __restrict__ desc, ChanState* __restrict__ state, f
     }
 }
 
-static cudaError_t launch_chain_kernel(const LaunchCtx& c, int Pcap, size_t smem, int n_warps, const TpCtl& tp) {
+static cudaError_t launch_chain_kernel(const LaunchCtx& c, int Pcap, size_t smem, int n_warps, const TpCtl& tp, double ab = 0.0) {
     float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
     int blocks = (n_warps + CW_WARPS - 1) / CW_WARPS;
     if (blocks < 1) return cudaSuccess;
-    c.prof->begin(KID_CHAIN_PAR, c.stream);
+    c.prof->begin(KID_CHAIN_PAR, c.stream, ab);
     k_chain_par<<<blocks, CW_WARPS * 32, smem, c.stream>>>(c.d_desc, c.d_state, c.d_ring, c.d_theta, phase,
                                                           c.sri_xdelta, Pcap, c.n_channels, c.d_counters, tp);
     c.prof->end(c.stream);
@@ -1201,57 +1276,96 @@ static cudaError_t launch_chain_kernel(const LaunchCtx& c, int Pcap, size_t smem
 }
 
 cudaError_t launch_chain_par(const LaunchCtx& c) {
-    if (c.n_fast_channels == 0) return cudaSuccess;
+    const int n_legacy = c.n_fast_channels - c.n_fzs_channels;       // scan-chain channels of k_chain_par + k_back_par
+    const int n_fzs = c.n_fzs_channels;                              // ... and of k_fzs_cb (chain + back in one kernel)
+    if (n_legacy <= 0 && n_fzs <= 0) return cudaSuccess;
     int Pcap = c.Pmax_fast < 1 ? 1 : c.Pmax_fast;
     Pcap = (Pcap + 3) & ~3;
     size_t per_warp = ((size_t)CW_B + Pcap + 2) * sizeof(double) + ((size_t)Pcap + 3 * CW_B + 4) * sizeof(float);
     size_t smem = per_warp * CW_WARPS;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain_par, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e;
+    if (n_legacy > 0) {
+        static KernelCfg cfg;
+        e = cfg.ensure(k_chain_par, smem, CW_WARPS * 32);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_chain_par, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = smem;
     }
     float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
-    cudaError_t e;
     TpCtl tp{};
     tp.chans = c.tp_chans; tp.n_chans = c.tp_n_chans; tp.pkts = c.tp_pkts; tp.ends = c.tp_ends;
     tp.end_ring = c.tp_end_ring; tp.start_ring = c.tp_start_ring; tp.ring_stride = c.tp_ring_stride; tp.fail = c.tp_fail;
-    if (c.n_fast_channels > c.tp_n_chans) {            // channels whose chain runs packet after packet
-        e = launch_chain_kernel(c, Pcap, smem, c.n_channels, tp);
-        if (e != cudaSuccess) return e;
-    }
+    tp.slot_fail = c.tp_slot_fail; tp.slot_run = c.tp_slot_run;
+    const int tp_fzs = c.tp_n_chans_fzs, tp_legacy = c.tp_n_chans - c.tp_n_chans_fzs;
+    // one round of chain work over `items` (null: one unit per channel), each kernel taking its own channels
+    // algorithmic bytes per kernel and class of channels (profiling only): [0] packet-after-packet, [1] time-parallel
+    double ab_legacy[2] = {0, 0}, ab_fzs[2] = {0, 0}, ab_back = 0;
+    if (c.prof->enabled)
+        for (int i = 0; i < c.n_channels; i++) {
+            const ChanDesc& d = c.h_desc[i];
+            if (!(d.flags & CH_FAST) || (d.flags & CH_FUSED)) continue;
+            const int k = (d.flags & CH_TP) ? 1 : 0;
+            if (d.flags & CH_FZS) ab_fzs[k] += alg_bytes_chain(d) + alg_bytes_back(d);
+            else { ab_legacy[k] += alg_bytes_chain(d); ab_back += alg_bytes_back(d); }
+        }
+    // one round of chain work over `items` (null: one unit per channel), each kernel taking its own channels; the
+    // algorithmic bytes of the time-parallel channels are booked on the round over their packets (which = 1)
+    auto chain_round = [&](const TpCtl& t, int n_units, bool legacy, bool fzs, int which = -1) -> cudaError_t {
+        cudaError_t r = cudaSuccess;
+        if (legacy) { r = launch_chain_kernel(c, Pcap, smem, n_units, t, which >= 0 ? ab_legacy[which] : 0.0); if (r != cudaSuccess) return r; }
+        if (fzs) r = launch_fzs_cb(c, t, n_units, which >= 0 ? ab_fzs[which] : 0.0);
+        return r;
+    };
+    // channels whose chain runs packet after packet
+    e = chain_round(tp, c.n_channels, n_legacy > tp_legacy, n_fzs > tp_fzs, 0);
+    if (e != cudaSuccess) return e;
     if (c.tp_n_chans > 0) {
         // heads (packets before the time-parallel range), scan, resolve, all packets in parallel, proof, re-runs
-        TpCtl t1 = tp; t1.items = c.tp_head_items; t1.n_items = c.tp_n_head;
-        e = launch_chain_kernel(c, Pcap, smem, c.tp_n_head, t1);
-        if (e != cudaSuccess) return e;
+        if (c.tp_n_head > 0) {
+            TpCtl t1 = tp; t1.items = c.tp_head_items; t1.n_items = c.tp_n_head;
+            e = chain_round(t1, c.tp_n_head, tp_legacy > 0, tp_fzs > 0);
+            if (e != cudaSuccess) return e;
+        }
         c.prof->begin(KID_TP, c.stream);
-        k_tp_scan<<<(c.tp_n_slots + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_n_slots);
-        k_tp_resolve<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_ends);
+        k_tp_scan<<<(c.tp_n_items + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_items, c.tp_n_items, c.tp_pkts);
+        k_tp_resolve<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, c.tp_chans, c.tp_n_chans, c.tp_pkts, c.tp_ends, c.d_state);
         c.prof->end(c.stream);
         (*c.launches) += 2;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         TpCtl t2 = tp; t2.items = c.tp_items; t2.n_items = c.tp_n_items;
-        e = launch_chain_kernel(c, Pcap, smem, c.tp_n_items, t2);
+        e = chain_round(t2, c.tp_n_items, tp_legacy > 0, tp_fzs > 0, 1);
         if (e != cudaSuccess) return e;
         c.prof->begin(KID_TP, c.stream);
         k_tp_check<<<(c.tp_n_items + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2);
+        c.prof->end(c.stream);
+        (*c.launches)++;
+        // repair rounds (k_fzs_cb channels): exact advances instead of classic ones from the first unproven hand-over on
+        static const int rounds = getenv("PSKD_TP_ROUNDS") ? atoi(getenv("PSKD_TP_ROUNDS")) : 1;
+        for (int r = 0; r < rounds && tp_fzs > 0; r++) {
+            c.prof->begin(KID_TP, c.stream);
+            k_tp_fix<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2);
+            c.prof->end(c.stream);
+            (*c.launches)++;
+            TpCtl t2r = t2; t2r.rerun = 1;
+            e = chain_round(t2r, c.tp_n_items, false, true);
+            if (e != cudaSuccess) return e;
+            c.prof->begin(KID_TP, c.stream);
+            k_tp_check<<<(c.tp_n_items + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2);
+            c.prof->end(c.stream);
+            (*c.launches)++;
+        }
+        c.prof->begin(KID_TP, c.stream);
         k_tp_install<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_state, c.d_ring, tp, c.d_counters);
         c.prof->end(c.stream);
-        (*c.launches) += 2;
+        (*c.launches)++;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         TpCtl t3 = tp; t3.fallback = 1;
-        e = launch_chain_kernel(c, Pcap, smem, c.n_channels, t3);
+        e = chain_round(t3, c.n_channels, tp_legacy > 0, tp_fzs > 0);
         if (e != cudaSuccess) return e;
     }
-    if ((c.out_soft || c.out_bits) && c.Kmax > 0) {
+    if (n_legacy > 0 && (c.out_soft || c.out_bits) && c.Kmax > 0) {
         dim3 grid((unsigned)((c.Kmax + BP_TILE - 1) / BP_TILE), (unsigned)c.n_channels);
-        c.prof->begin(KID_BACK_PAR, c.stream);
+        c.prof->begin(KID_BACK_PAR, c.stream, ab_back);
         k_back_par<<<grid, BP_THREADS, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
         c.prof->end(c.stream);
         (*c.launches)++;

@@ -26,8 +26,12 @@ k_synth(float2* __restrict__ iq, size_t iq_stride, int ch0, size_t n_complex, ps
     // per-channel constants
     const uint64_t h0 = mix64(ckey ^ 0x1111), h1 = mix64(ckey ^ 0x2222), h2 = mix64(ckey ^ 0x3333);
     const float phase0 = 6.2831853f * u01((uint32_t)h0);
-    const double freq = (double)cfg.freq_max * (2.0 * (double)u01((uint32_t)(h0 >> 32)) - 1.0);
     const int S = cfg.samplesPerBaud, M = cfg.constelationSize;
+    double freq = (double)cfg.freq_max * (2.0 * (double)u01((uint32_t)(h0 >> 32)) - 1.0);
+    if (cfg.period > 0) {                          // replayable buffer: M * freq * period is a whole number of cycles
+        const double q = (double)M * (double)cfg.period;
+        freq = rint(freq * q) / q;
+    }
     const int shift = (int)((uint32_t)h1 % (uint32_t)S);
     const double wf0 = 2e-6 + 2e-5 * (double)u01((uint32_t)(h1 >> 32));
     const double wf1 = 2e-6 + 2e-5 * (double)u01((uint32_t)h2);

@@ -98,7 +98,10 @@ public:
         o.phase = out.phase.data(); o.sample_index = out.sampleIndex.data();
         o.sym_stride = cap; o.bits_stride = 3 * cap; o.n_symbols = &ns; o.n_bits = &nb;
         psk_check(pskd_process(h_, &in, &o));
-        resetState = false;                                                          // :371
+        // resetState stays pending until a COMPLEX packet consumes it (:353-372): read it back, so that a flag
+        // raised by a queue flush on an ignored real-data packet (:359-363) survives the next property snapshot
+        psk_check(pskd_get_props(h_, 0, &p));
+        resetState = p.resetState != 0;
         out.softDecision.resize(ns); out.phase.resize(ns); out.sampleIndex.resize(ns); out.bits.resize(nb);
         pskd_get_sri(h_, 0, &out.sri);
         return PSK_NORMAL;                                                           // :362, :617

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/pskd.h but not exported by libpskd.so"
     assert set(binding.EXPORTS) == set(names)
-    assert lib.pskd_abi_version() == 1
+    assert lib.pskd_abi_version() == 2
 
 
 def test_default_properties_match_reference_prf():
@@ -41,7 +41,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(B.Props) == 16       # uint16, uint32, uint16, uint16, uint8, uint8 with natural alignment
     assert B.Props.numAvg.offset == 4 and B.Props.differentialDecoding.offset == 12
     assert ctypes.sizeof(B.Input) == 64 and ctypes.sizeof(B.Output) == 64
-    assert ctypes.sizeof(B.KernelTime) == 48
+    assert ctypes.sizeof(B.KernelTime) == 56 and ctypes.sizeof(B.Synth) == 32
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -14,12 +14,14 @@ GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.n
 PROP_NAMES = ("samplesPerBaud", "numAvg", "constelationSize", "phaseAvg", "differentialDecoding")
 
 
-@pytest.fixture(params=["fused", "staged", "tp"], autouse=True)
+@pytest.fixture(params=["fused", "staged", "tp", "legacy"], autouse=True)
 def fused_mode(request, monkeypatch):
-    """every test of this module runs through the fused kernel, the staged kernels, and the staged
-    kernels with the time-parallel chain"""
+    """every test of this module runs through the fused kernel, the staged kernels (k_fzs_front +
+    k_fzs_cb), the staged kernels with the time-parallel chain, and the legacy staged kernels
+    (PSKD_FZS=0: k_front_t + k_chain_par + k_back_par, time-parallel chain on)"""
     monkeypatch.setenv("PSKD_FUSED", "1" if request.param == "fused" else "0")
-    monkeypatch.setenv("PSKD_TP", "1" if request.param == "tp" else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if request.param in ("tp", "legacy") else "0")
+    monkeypatch.setenv("PSKD_FZS", "0" if request.param == "legacy" else "1")
     return request.param
 
 
@@ -78,12 +80,74 @@ def test_unsupported_and_error_paths():
     import psk_soft_b200 as pk
     with pytest.raises(pk.PskdError):
         pk.PskSoft(samplesPerBaud=1)                  # reference's sps==1 branch: not on the GPU path
-    dev = pk.PskSoft(samplesPerBaud=8, numAvg=100)
-    dev.push(siggen.gen_shaped(20000, 8, 4, seed=2))
-    dev.configure(numAvg=10)                          # window shrink: the reference stalls forever (cpp/psk_soft.cpp:457)
     with pytest.raises(pk.PskdError) as e:
-        dev.push(siggen.gen_shaped(1000, 8, 4, seed=3))
+        pk.PskSoft(samplesPerBaud=8, numAvg=0)        # never emits in the reference
     assert e.value.code == -4
+
+
+def test_stall_after_window_shrink_matches_oracle(oracle_built):
+    """numAvg*samplesPerBaud shrinks below the carried window: the reference keeps consuming packets and emits
+    NOTHING (`samples.size()==numDataPts`, cpp/psk_soft.cpp:457, cannot become true while the deque only grows) until
+    the window length grows past the deque size; resetState only truncates the deque to its oldest samples
+    (resyncEnergy, :619-636) and the stall goes on.  The C ABI emulates exactly that (no error)."""
+    import psk_soft_b200 as pk
+    iq = siggen.gen_shaped(120000, 8, 8, seed=13, sigma=0.03, freq=2e-5, timing_shift=3)
+    props = dict(samplesPerBaud=8, constelationSize=8, numAvg=100, phaseAvg=50)
+    orc = oracle_built.OracleComponent(**props)
+    dev = pk.PskSoft(**props)
+    script = [(0, 20000, {}), (20000, 20300, dict(numAvg=50)),                 # shrink -> stall (deque 799+300)
+              (20300, 20301, {}), (20301, 20500, dict(constelationSize=4)),    # still stalled; a pending reset runs its prologue
+              (20500, 40000, dict(numAvg=200, constelationSize=8)),            # 1600 > deque size: recovers, window = the grown deque
+              (40000, 60000, dict(numAvg=20)), (60000, 60700, dict(resetState=1)),   # stall; reset truncates, stall goes on
+              (60700, 61000, dict(phaseAvg=30)), (61000, 90000, dict(numAvg=150)),   # 1200 > 160+700+300: recovers
+              (90000, 120000, {})]
+    emitted = []
+    for a, b, ch in script:
+        orc.configure(**ch)
+        dev.configure(**ch)
+        ref = orc.push(iq[a:b], xdelta=0.01)
+        got = dev.push(iq[a:b], xdelta=0.01)
+        emitted.append(len(ref["sidx"]))
+        assert_parity(got, ref, tag=f"{a}:{b} {ch}")
+        s_ref, s_dev = orc.sri(0), dev.sri()
+        assert s_dev["sri_pushes"] == s_ref["count"], (a, b, s_dev, s_ref)
+    assert emitted[1] == emitted[2] == emitted[3] == 0 and emitted[4] > 0, emitted
+    assert emitted[5] == emitted[6] == emitted[7] == 0 and emitted[8] > 0, emitted
+
+
+def test_state_import_rejects_corrupt_blobs():
+    """pskd_state_import validates the blob against its own size and the bank before touching the bank"""
+    import psk_soft_b200 as pk
+    props = dict(samplesPerBaud=8, constelationSize=8, numAvg=100, phaseAvg=50)
+    bank = pk.Bank(2, props)
+    iq = np.stack([siggen.gen_shaped(30000, 8, 8, seed=60 + c) for c in range(2)])
+    first = bank.process_host(iq[:, :15000].copy(), xdelta=0.01, packet_len=8000)
+    blob = bytearray(bank.export_state())
+    import struct
+    hdr = struct.Struct("<IIiiQ")
+    magic, ver, nch, ring_cap, total = hdr.unpack_from(blob, 0)
+    assert total == len(blob)
+
+    def rejected(mut):
+        with pytest.raises(pk.PskdError) as e:
+            bank.import_state(bytes(mut))
+        assert e.value.code == -1, e.value
+
+    rejected(blob[:len(blob) - 8])                                    # truncated
+    rejected(blob[:hdr.size + 10])
+    bad = bytearray(blob); hdr.pack_into(bad, 0, magic, ver, nch, 1 << 30, total); rejected(bad)   # absurd ring
+    bad = bytearray(blob); hdr.pack_into(bad, 0, magic, ver, nch, ring_cap, total - 4); rejected(bad)
+    bad = bytearray(blob) + b"\0" * 16; rejected(bad[:])             # trailing bytes: size must match exactly
+    # corrupt LinearFit head / n of channel 0 (offsets inside the first StateChan are implementation details: flip every
+    # int32 of the device part that currently equals phaseAvg or the ring head and expect either a rejection or parity)
+    second = bank.process_host(iq[:, 15000:].copy(), xdelta=0.01, packet_len=8000)
+    ref = pk.Bank(2, props)
+    r1 = ref.process_host(iq[:, :15000].copy(), xdelta=0.01, packet_len=8000)
+    ref.import_state(bytes(blob))                                      # a valid blob still imports ...
+    r2 = ref.process_host(iq[:, 15000:].copy(), xdelta=0.01, packet_len=8000)
+    for c in range(2):
+        for k in ("sidx", "bits", "phase", "soft"):
+            assert np.array_equal(second[c][k], r2[c][k], equal_nan=True), (c, k)   # ... and the rejected ones left the bank untouched
 
 
 def test_cpp_host_mirror_demo_runs():
@@ -157,8 +221,8 @@ def test_tiny_and_ragged_calls(oracle_built):
 def test_randomized_reconfiguration_scripts(seed, oracle_built):
     """random sequences of packets with property changes in between (any constellation / phaseAvg / differential
     toggle, resetState, queue flush, SRI rate changes, window growth) against the oracle, state carried across every
-    call (reference: cpp/psk_soft.cpp:353-426, 619-651).  Window shrinks are left out: the reference stalls there
-    (:457 never true again) and the C ABI reports them as unsupported."""
+    call (reference: cpp/psk_soft.cpp:353-426, 619-651).  Window shrinks stall the component (:457 never true again until
+    the window grows past the deque): emulated, both sides emit nothing."""
     import psk_soft_b200 as pk
     rs = np.random.RandomState(7000 + seed)
     S, A = int(rs.choice([8, 9, 10, 16])), int(rs.choice([3, 20, 64, 100]))
@@ -178,9 +242,9 @@ def test_randomized_reconfiguration_scripts(seed, oracle_built):
             ch["differentialDecoding"] = int(rs.randint(0, 2))
         elif r < 0.50:
             ch["resetState"] = 1
-        elif r < 0.62:                                         # window growth only
+        elif r < 0.62:                                         # window growth; one change in four may shrink it (stall)
             S2, A2 = int(rs.choice([8, 9, 10, 16])), int(rs.choice([3, 20, 64, 100, 150]))
-            if S2 * A2 >= S * A:
+            if S2 * A2 >= S * A or rs.rand() < 0.25:
                 if S2 != S: ch["samplesPerBaud"] = S2
                 if A2 != A: ch["numAvg"] = A2
                 S, A = S2, A2

@@ -23,15 +23,19 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["fused", "tp", "par", "seq"])
+@pytest.fixture(params=["fused", "tp", "par", "seq", "legacy_tp", "legacy_par"])
 def chain_mode(request, monkeypatch):
     """run every case through the fused kernel (where the configuration qualifies), the staged
-    kernels with the time-parallel chain (where the packets qualify), the staged kernels with the
-    packet-after-packet scan chain, and the staged kernels with the literal sequential chain"""
-    monkeypatch.setenv("PSKD_CHAIN", "seq" if request.param == "seq" else "par")
-    monkeypatch.setenv("PSKD_FUSED", "1" if request.param == "fused" else "0")
-    monkeypatch.setenv("PSKD_TP", "1" if request.param == "tp" else "0")
-    return request.param
+    kernels (k_fzs_front + k_fzs_cb where the configuration qualifies) with the time-parallel chain
+    (where the packets qualify) and with the packet-after-packet scan chain, the staged kernels with
+    the literal sequential chain, and the legacy staged kernels (k_front_t + k_chain_par +
+    k_back_par, PSKD_FZS=0) with and without the time-parallel chain"""
+    mode = request.param
+    monkeypatch.setenv("PSKD_CHAIN", "seq" if mode == "seq" else "par")
+    monkeypatch.setenv("PSKD_FUSED", "1" if mode == "fused" else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if mode in ("tp", "legacy_tp") else "0")
+    monkeypatch.setenv("PSKD_FZS", "0" if mode.startswith("legacy") else "1")
+    return mode
 
 
 def _props(t):
@@ -112,13 +116,14 @@ LOW_SNR = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["fused", "staged", "tp"])
+@pytest.mark.parametrize("mode", ["fused", "staged", "tp", "legacy"])
 @pytest.mark.parametrize("t", LOW_SNR, ids=lambda t: f"M{t['M']}sig{t['sig']}")
 def test_low_snr_unwrap_repairs(t, mode, oracle_built, monkeypatch):
     import psk_soft_b200 as pk
     monkeypatch.setenv("PSKD_CHAIN", "par")
     monkeypatch.setenv("PSKD_FUSED", "1" if mode == "fused" else "0")
-    monkeypatch.setenv("PSKD_TP", "1" if mode == "tp" else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if mode in ("tp", "legacy") else "0")
+    monkeypatch.setenv("PSKD_FZS", "0" if mode == "legacy" else "1")
     iq = siggen.gen_shaped(t["n"], t["S"], t["M"], seed=21, sigma=t["sig"], freq=t["f"], timing_shift=1)
     ref = oracle_built.OracleComponent(**_props(t)).demod(iq, packet_len=t["pkt"], xdelta=t["xd"])
     dev = pk.PskSoft(**_props(t))
@@ -157,7 +162,7 @@ def test_time_parallel_chain_long_single_channel(oracle_built, monkeypatch):
     assert_parity(got2, r2, tag="second call, time-parallel from carried state")
 
 
-@pytest.mark.parametrize("path", ["fused", "staged"])
+@pytest.mark.parametrize("path", ["fused", "staged", "legacy"])
 @pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("PSKD_FUZZ_SEEDS", "24")))))
 def test_randomized_configurations(seed, path, oracle_built, monkeypatch):
     """Randomized sweep of the fused kernel's whole domain (samplesPerBaud 8/9/10/16, numAvg 1..256, phaseAvg
@@ -168,6 +173,7 @@ def test_randomized_configurations(seed, path, oracle_built, monkeypatch):
     import psk_soft_b200 as pk
     monkeypatch.setenv("PSKD_FUSED", "1" if path == "fused" else "0")
     monkeypatch.setenv("PSKD_TP", "0" if path == "fused" else "auto")
+    monkeypatch.setenv("PSKD_FZS", "0" if path == "legacy" else "1")
     rs = np.random.RandomState(1000 + seed)
     nch = 5
     props, iqs = [], []
