@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the PSK soft-demod hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload ...]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload ...] [--scaling strong|weak]
 
 A "step" is one pass of the hot path (pskd_process) over one batch of synthetic input: a channel
-bank of `channels` independent IQ channels x `samples` complex samples each, resident in HBM.
+bank of independent IQ channels x `samples` complex samples each, resident in HBM.
 Default workload (BASELINE.json north_star target, SURVEY.md 8d config 4 shape): 8-PSK, 8
-samples/symbol, numAvg 100, phaseAvg 50, coherent, 4096 channels x 1e6 samples PER GPU, emulated
-BULKIO packets of 64000 samples, SRI.xdelta 0.01.  Channels are independent, so N GPUs each run
-their own bank with no collective ("scaling": "weak").
+samples/symbol, numAvg 100, phaseAvg 50, coherent, ONE bank of 4096 channels x 1e6 samples, emulated
+BULKIO packets of 64000 samples, SRI.xdelta 0.01.  Channels are independent, so under torchrun the
+bank is PARTITIONED over the N GPUs in contiguous channel ranges with no collective
+("scaling": "strong"; `--scaling weak` gives every GPU its own full bank instead).  `config5` is the
+mixed 8192-channel bank (per-channel constellation / samples per symbol / averaging lengths /
+differential decoding from a seeded table, sorted by samples per symbol, cost-balanced ranges).
 
-Prints ONE JSON line (rank 0).  `value` = Msamples/s with inputs resident in HBM; `e2e` = same
-metric through the C ABI with HOST (pinned) buffers, H2D/D2H inside the timed region;
-`roofline` = algorithmic bytes / measured kernel time of the dominant kernel vs the measured HBM
-copy peak; `cpu_baseline` = the reference's CPU demod (oracle/_ref, else the C port) on a bounded
-sample of the same workload on this box's host cores.
+Prints ONE JSON line (rank 0).  `value` = Msamples/s with inputs resident in HBM (profiling off);
+`e2e` = same metric through the C ABI with HOST (pinned) buffers, H2D/D2H inside the timed region;
+`roofline` = algorithmic bytes / measured kernel time of the dominant kernel (second, profiled pass) vs
+the measured HBM copy peak; `cpu_baseline` = the reference's CPU demod (oracle/_ref, else the C port) on
+a bounded sample of the same workload on this box's host cores.
 """
 from __future__ import annotations
 
@@ -30,11 +33,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (M, S, A, P, D, channels, samples, sigma, freq_max, pn)
     "bank8psk": dict(M=8, S=8, A=100, P=50, D=0, channels=4096, samples=1_000_000, sigma=0.02, freq_max=2e-5, pn=0.0,
-                     desc="8-PSK, 8 samples/symbol, 4096-channel bank x 1M samples per GPU (north_star target; config-4 shape)"),
+                     desc="8-PSK, 8 samples/symbol, ONE 4096-channel bank x 1M samples (north_star target; config-4 shape)"),
     "config4": dict(M=4, S=8, A=100, P=50, D=0, channels=4096, samples=1_000_000, sigma=0.02, freq_max=2e-5, pn=0.0,
-                    desc="QPSK, 8 samples/symbol, 4096-channel bank x 1M samples per GPU (configs[3])"),
+                    desc="QPSK, 8 samples/symbol, ONE 4096-channel bank x 1M samples (configs[3])"),
+    "config5": dict(mixed=True, channels=8192, samples=1_000_000, sigma=0.02, freq_max=2e-5, pn=0.0,
+                    desc="mixed BPSK/QPSK/8-PSK bank, 8192 channels x 1M samples, S in {8,9,10}, numAvg in {50,100,200}, "
+                         "phaseAvg in {25,50,100}, differential on/off per channel (configs[4])"),
     "config3": dict(M=8, S=8, A=100, P=50, D=1, channels=256, samples=4_000_000, sigma=0.02, freq_max=2e-5, pn=0.0,
                     desc="8-PSK, 8 samples/symbol, differential, 256 channels x 4M samples (configs[2])"),
     "config2": dict(M=2, S=10, A=100, P=50, D=0, channels=1, samples=64_000_000, sigma=0.05, freq_max=1e-4, pn=0.02,
@@ -50,14 +55,31 @@ def bits_per_baud(M):
     return {2: 1, 4: 2, 8: 3}.get(M, 0)
 
 
-def algorithmic_bytes(w, channels, samples, first_call=False):
-    """8*N input + K*(8 soft + 4 phase + 2 sampleIndex + 2*b bits) per channel."""
-    K = samples // w["S"] - (w["A"] - 1 if first_call else 0)
-    return channels * (8 * samples + K * (8 + 4 + 2 + 2 * bits_per_baud(w["M"])))
+def channel_table(w, nch=None):
+    """Per-channel properties of the (global) bank: a list of dicts with the reference's property names.
+    config5: seeded table, sorted by (samplesPerBaud, constelationSize) so that every kernel launch
+    sees one class of channels side by side."""
+    import numpy as np
+    nch = nch or w["channels"]
+    if not w.get("mixed"):
+        p = dict(samplesPerBaud=w["S"], numAvg=w["A"], constelationSize=w["M"], phaseAvg=w["P"], differentialDecoding=w["D"])
+        return [p] * nch
+    rs = np.random.RandomState(5)
+    rows = [(int(rs.choice([8, 9, 10])), int(rs.choice([2, 4, 8])), int(rs.choice([50, 100, 200])),
+             int(rs.choice([25, 50, 100])), int(rs.randint(0, 2))) for _ in range(nch)]
+    rows.sort(key=lambda r: (r[0], r[1]))
+    return [dict(samplesPerBaud=S, constelationSize=M, numAvg=A, phaseAvg=P, differentialDecoding=D) for (S, M, A, P, D) in rows]
 
 
-def props_of(w):
-    return dict(samplesPerBaud=w["S"], numAvg=w["A"], constelationSize=w["M"], phaseAvg=w["P"], differentialDecoding=w["D"])
+def algorithmic_bytes(table, samples):
+    """8*N input + K*(8 soft + 4 phase + 2 sampleIndex + 2*b bits) per channel (steady state: K = N/S)."""
+    return sum(8 * samples + (samples // p["samplesPerBaud"]) * (8 + 4 + 2 + 2 * bits_per_baud(p["constelationSize"])) for p in table)
+
+
+def channel_cost(p, samples):
+    """relative cost of one channel (cost-balanced sharding of a mixed bank): a per-sample part (ingest + timing) and
+    a per-symbol part (chain + derotate / slice) that weigh about the same at 8 samples/symbol"""
+    return samples * (1.0 + 8.0 / p["samplesPerBaud"])
 
 
 class ClockSampler(threading.Thread):
@@ -133,12 +155,20 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def config_of(args, w, world, scaling, nch_global):
+    """the `config` object of the JSON line -- the same keys for both arms"""
+    return {"workload": args.workload, "description": w["desc"], "channels": nch_global, "samples_per_channel": w["samples"],
+            "samplesPerBaud": w.get("S", "8/9/10"), "constelationSize": w.get("M", "2/4/8"), "numAvg": w.get("A", "50/100/200"),
+            "phaseAvg": w.get("P", "25/50/100"), "differentialDecoding": w.get("D", "0/1"), "packet_len": PACKET_LEN,
+            "xdelta": XDELTA, "n_gpus": world, "scaling": scaling}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline leg: the reference's own demod core on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_demod_rate(w, iq_host, threads, repeats=1):
+def cpu_demod_rate(table, iq_host, threads, repeats=1):
     """Times the reference demod (oracle/_ref when present, else the C port) on iq_host
-    [channels, samples] complex64 using `threads` host threads (one component per channel).
+    [channels, samples] complex64 using `threads` host threads (one component per channel, properties table[c]).
     Returns (Msamples/s, kind, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle
@@ -149,7 +179,7 @@ def cpu_demod_rate(w, iq_host, threads, repeats=1):
             oracle.build(ref=False)
         cls, kind = oracle.OracleComponent, "port"
     nch, n = iq_host.shape
-    comps = [cls(**props_of(w)) for _ in range(nch)]
+    comps = [cls(**table[c]) for c in range(nch)]
 
     def work(c):
         comps[c].demod(iq_host[c], packet_len=PACKET_LEN, xdelta=XDELTA, keep=False)   # ctypes releases the GIL
@@ -164,54 +194,62 @@ def cpu_demod_rate(w, iq_host, threads, repeats=1):
     return nch * n / best / 1e6, kind, best
 
 
-def host_sample(w, channels, samples, seed, device_ok):
-    """[channels, samples] complex64 of the workload's synthetic input in HOST memory."""
+def host_synth(w, table, samples, seed, uniq=16):
+    """[len(table), samples] complex64 of the workload's synthetic input generated ON THE HOST (numpy; the reference arm
+    never maps libpskd.so): `uniq` distinct channels per property class, tiled (the reference's cost does not depend on
+    the sample values)."""
     import numpy as np
-    if device_ok:
-        import torch
-        import psk_soft_b200 as pk
-        buf = torch.empty((channels, samples, 2), dtype=torch.float32, device="cuda")
-        pk.synth_fill(buf.data_ptr(), samples, 0, channels, samples, seed=seed, samplesPerBaud=w["S"],
-                      constelationSize=w["M"], sigma=w["sigma"], freq_max=w["freq_max"], pn_sigma=w["pn"],
-                      device=torch.cuda.current_device())
-        torch.cuda.synchronize()
-        return buf.cpu().numpy().view(np.complex64).reshape(channels, samples)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import siggen
-    uniq = min(channels, 4)
-    base = [siggen.gen_shaped(samples, w["S"], w["M"], seed=seed + i, sigma=w["sigma"], freq=w["freq_max"] * 0.5) for i in range(uniq)]
-    return np.stack([base[i % uniq] for i in range(channels)])
+    cache, rows = {}, []
+    for c, p in enumerate(table):
+        key = (p["samplesPerBaud"], p["constelationSize"], c % uniq)
+        if key not in cache:
+            cache[key] = siggen.gen_shaped(samples, key[0], key[1], seed=seed + 131 * len(cache), sigma=w["sigma"],
+                                           freq=w["freq_max"] * (((len(cache) * 7) % 11) / 5.0 - 1.0),
+                                           pn_sigma=w["pn"] * 0.1, timing_shift=len(cache) % key[0])
+        rows.append(cache[key])
+    return np.stack(rows)
+
+
+def sample_rows(nch, k):
+    """k channel indices spread evenly over the bank (a mixed bank is sorted by class: every class is sampled)"""
+    k = min(k, nch)
+    return [int(i * nch / k) for i in range(k)]
 
 
 def run_reference(args, w):
     """--impl reference: the reference's CPU implementation of the path, all host threads, on a
     bounded sample of the workload per step."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    try:
-        import torch
-        device_ok = torch.cuda.is_available()
-    except Exception:
-        device_ok = False
-    ch = min(w["channels"], 512)
-    n = min(w["samples"], 1_000_000) if w["channels"] > 1 else min(w["samples"], 8_000_000)
-    iq = host_sample(w, ch, n, seed=1234, device_ok=device_ok)
+    table_all = channel_table(w)
+    nch_global = len(table_all)
+    rows = sample_rows(nch_global, 512)
+    table = [table_all[i] for i in rows]
+    ch = len(table)
+    n = min(w["samples"], 1_000_000) if nch_global > 1 else min(w["samples"], 8_000_000)
+    iq = host_synth(w, table, n, seed=1234)
     for _ in range(args.warmup):
-        cpu_demod_rate(w, iq[: max(cores, 1)], cores)
+        cpu_demod_rate(table[:cores], iq[:cores], cores)
     t_tot = 0.0
     kind = "port"
     for _ in range(args.steps):
-        _, kind, dt = cpu_demod_rate(w, iq, cores)
+        _, kind, dt = cpu_demod_rate(table, iq, cores)
         t_tot += dt
     ms = 1e3 * t_tot / args.steps
     val = ch * n / (ms * 1e-3) / 1e6
-    sample = f"{ch} channels x {n} samples per step ({'oracle/_ref = unmodified psk_soft.cpp' if kind == 'reference' else 'oracle C port'}), one component per channel"
+    scaling = "strong" if nch_global > 1 else "replicas"
+    sample = (f"{ch} channels (every {max(1, nch_global // ch)}th of the bank) x {n} samples per step "
+              f"({'oracle/_ref = unmodified psk_soft.cpp' if kind == 'reference' else 'oracle C port'}), one component per channel, "
+              "input synthesised on the host")
     line = {"impl": "reference", "metric": "Msamples/s demodulated", "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": args.workload, "description": w["desc"], "packet_len": PACKET_LEN, "xdelta": XDELTA},
+            "config": config_of(args, w, world, scaling, nch_global),
             "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -226,11 +264,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bank8psk", choices=sorted(WORKLOADS))
-    ap.add_argument("--channels", type=int, default=0, help="override channels per GPU")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "strong", "weak"],
+                    help="N>1: strong = ONE bank partitioned over the GPUs (default for banks), weak = one full bank per GPU")
+    ap.add_argument("--channels", type=int, default=0, help="override the bank's channel count")
     ap.add_argument("--samples", type=int, default=0, help="override samples per channel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-channels", type=int, default=512)
+    ap.add_argument("--e2e-channels", type=int, default=1024)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.channels:
@@ -245,6 +285,7 @@ def main():
     import torch.distributed as dist
     import psk_soft_b200 as pk
     from psk_soft_b200 import binding as B
+    from psk_soft_b200 import shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -258,161 +299,221 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
 
-    nch, n = w["channels"], w["samples"]
-    S, bpb = w["S"], bits_per_baud(w["M"])
-    cap = n // S + 8
-    iq = torch.empty((nch, n, 2), dtype=torch.float32, device="cuda")
-    soft = torch.empty((nch, cap, 2), dtype=torch.float32, device="cuda")
-    phase = torch.empty((nch, cap), dtype=torch.float32, device="cuda")
-    sidx = torch.empty((nch, cap), dtype=torch.int16, device="cuda")
-    bits = torch.empty((nch, cap * 3), dtype=torch.int16, device="cuda")
-    pk.synth_fill(iq.data_ptr(), n, rank * nch, nch, n, seed=4, samplesPerBaud=S, constelationSize=w["M"],
-                  sigma=w["sigma"], freq_max=w["freq_max"], pn_sigma=w["pn"], device=dev)
+    # ---- the bank and this rank's part of it ---------------------------------------------------------
+    table_all = channel_table(w)
+    nch_global, n = len(table_all), w["samples"]
+    scaling = args.scaling
+    if scaling == "auto":
+        scaling = "strong" if nch_global >= world and nch_global > 1 else "weak"
+    if world == 1:
+        lo, hi = 0, nch_global
+    elif scaling == "strong":
+        rng = (shard.balanced_ranges([channel_cost(p, n) for p in table_all], world) if w.get("mixed")
+               else shard.channel_ranges(nch_global, world))
+        lo, hi = rng[rank]
+    else:
+        lo, hi = 0, nch_global                                 # weak: every rank its own full bank (other seeds)
+    table = table_all[lo:hi]
+    nch = len(table)
+    ch_seed0 = lo if (scaling == "strong" or world == 1) else rank * nch_global
+    Smin = min(p["samplesPerBaud"] for p in table) if nch else 8
+    cap = n // Smin + 8
+    iq = torch.empty((max(nch, 1), n, 2), dtype=torch.float32, device="cuda")
+    soft = torch.empty((max(nch, 1), cap, 2), dtype=torch.float32, device="cuda")
+    phase = torch.empty((max(nch, 1), cap), dtype=torch.float32, device="cuda")
+    sidx = torch.empty((max(nch, 1), cap), dtype=torch.int16, device="cuda")
+    bits = torch.empty((max(nch, 1), cap * 3), dtype=torch.int16, device="cuda")
+    # synthetic input, generated in HBM class by class (consecutive channels of one (S, M)); carrier offsets are
+    # quantised so that replaying the resident buffer step after step is ONE continuous stream per channel
+    c0 = 0
+    while c0 < nch:
+        c1 = c0
+        key = (table[c0]["samplesPerBaud"], table[c0]["constelationSize"])
+        while c1 < nch and (table[c1]["samplesPerBaud"], table[c1]["constelationSize"]) == key:
+            c1 += 1
+        pk.synth_fill(iq[c0].data_ptr(), n, ch_seed0 + c0, c1 - c0, n, seed=4, samplesPerBaud=key[0], constelationSize=key[1],
+                      sigma=w["sigma"], freq_max=w["freq_max"], pn_sigma=w["pn"], device=dev, period=n)
+        c0 = c1
     torch.cuda.synchronize()
-    bank = pk.Bank(nch, props_of(w), device=dev)
-    stream = torch.cuda.ExternalStream(bank.stream, device=dev)
+    bank = pk.Bank(nch, table, device=dev) if nch else None
+    stream = torch.cuda.ExternalStream(bank.stream, device=dev) if bank else torch.cuda.current_stream()
 
     def step():
-        bank.process_raw(iq.data_ptr(), n, n, soft.data_ptr(), bits.data_ptr(), phase.data_ptr(), sidx.data_ptr(),
-                         cap, cap * 3, xdelta=XDELTA, packet_len=PACKET_LEN, flags=B.FLAG_NO_SYNC, counts=False)
+        if bank:
+            bank.process_raw(iq.data_ptr(), n, n, soft.data_ptr(), bits.data_ptr(), phase.data_ptr(), sidx.data_ptr(),
+                             cap, cap * 3, xdelta=XDELTA, packet_len=PACKET_LEN, flags=B.FLAG_NO_SYNC, counts=False)
 
     def barrier():
         torch.cuda.synchronize()
-        bank.sync()
+        if bank:
+            bank.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(k):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(k):
+            step()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
     for _ in range(args.warmup):
         step()
-    bank.sync()
-    bank.profile_read(reset=True)
-    bank.profile_enable(True)
+    barrier()
+    # ---- pass 1: `value` -- K steps, per-launch profiling OFF, device events on the bank's stream, max over ranks ----
+    if bank:
+        bank.profile_enable(False)
     sampler = ClockSampler(dev)
     sampler.start()
     time.sleep(0.3)
-    launches0 = bank.launch_count
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = bank.launch_count if bank else 0
     t_wall0 = time.time()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    barrier()
+    ms_total = timed(args.steps)
     t_wall1 = time.time()
-    ms_total = ev0.elapsed_time(ev1)
-    launches = bank.launch_count - launches0
+    launches = (bank.launch_count - launches0) if bank else 0
     time.sleep(0.15)
     sampler.stop()
-    kern = bank.profile_read(reset=True)
-    bank.profile_enable(False)
-    stats = bank.stats()
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    total_samples = world * nch * n
+    total_samples = (nch_global if (scaling == "strong" or world == 1) else world * nch_global) * n
     value = total_samples / (ms_step * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (live CUDA-event time per launch) ----------------------
+    # ---- pass 2: per-kernel split with CUDA events around every launch (not part of `value`) --------------
     peak, peak_src = measured_peak()
     roof = None
+    kern = {}
+    if bank:
+        bank.profile_read(reset=True)
+        bank.profile_enable(True)
+        psteps = max(1, min(args.steps, 3))
+        timed(psteps)
+        kern = bank.profile_read(reset=True)
+        bank.profile_enable(False)
+    stats = bank.stats() if bank else {}
     if kern:
-        K = n // S
-        own = {"k_front": nch * (8 * n + 2 * K), "k_fused": algorithmic_bytes(w, nch, n),
-               "k_chain_par": nch * K * 4, "k_chain_seq": nch * K * 4,
-               "k_back_par": nch * K * (8 + 2 * bpb), "k_back": nch * K * (8 + 2 * bpb)}   # each kernel's own share of the algorithmic bytes
         dom = max(kern, key=lambda k: kern[k][0])
-        ms_launch = kern[dom][0] / max(kern[dom][1], 1)
-        launches_per_step = kern[dom][1] / args.steps
-        abytes_step = algorithmic_bytes(w, nch, n)
-        abytes_dom = own.get(dom, nch * K * 4)               # chain kernels: the 4-byte phase output
-        achieved = abytes_dom / launches_per_step / (ms_launch * 1e-3) / 1e9
+        ms_dom, n_dom, bytes_dom = kern[dom]
+        lps = n_dom / psteps                                    # launches of the dominant kernel per step
+        ms_launch = ms_dom / max(n_dom, 1)
+        achieved = bytes_dom / max(ms_dom, 1e-9) / 1e6          # bytes / ms -> GB/s
+        abytes_step = algorithmic_bytes(table, n)
         traffic = None
         try:   # DRAM bytes of the same kernel from the committed ncu --set full capture, scaled per launch
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if dom == "k_fused" and tr.get("workload") == args.workload:
-                traffic = tr["dram_bytes_per_sample"] * nch * n / launches_per_step
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            if tr.get("kernel") == dom and tr.get("workload") == args.workload and world == 1:
+                traffic = tr["dram_bytes_per_sample"] * nch * n / max(lps, 1e-9)
         except (OSError, KeyError, ValueError):
             traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": abytes_dom / launches_per_step,
-                "note": "achieved = this kernel's own algorithmic bytes (SURVEY 8d split per kernel) / its CUDA-event time per launch",
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_dom / max(n_dom, 1),
+                "ms_per_launch": ms_launch, "launches_per_step": lps,
+                "note": "achieved = algorithmic bytes (SURVEY 8d, split per stage) of the channels this kernel served / its "
+                        "CUDA-event time, both from a second pass with events around every launch (rank 0's shard); `value` "
+                        "is measured without them",
+                "kernel_ms_per_step": {k: v[0] / psteps for k, v in kern.items()},
+                "kernel_gbs": {k: (v[2] / v[0] / 1e6 if v[0] > 0 and v[2] > 0 else None) for k, v in kern.items()},
                 "whole_path": {"algorithmic_bytes_per_step": abytes_step,
                                "achieved": abytes_step / (ms_step * 1e-3) / 1e9,
-                               "frac": abytes_step / (ms_step * 1e-3) / 1e9 / peak}}
+                               "frac": abytes_step / (ms_step * 1e-3) / 1e9 / peak,
+                               "note": "all of this rank's algorithmic bytes / the step time of pass 1 (max over ranks)"}}
 
     # ---- e2e: same metric through the C ABI with HOST buffers -----------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and bank:
         import psutil
         per_ch = n * 8 + cap * (8 + 4 + 2 + 6)
         avail = psutil.virtual_memory().available
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        ech = max(1, min(nch, args.e2e_channels, int(0.25 * avail / max(local_world, 1) / per_ch)))
+        ech = max(1, min(nch, args.e2e_channels, int(0.3 * avail / max(local_world, 1) / per_ch)))
         h_iq = torch.empty((ech, n, 2), dtype=torch.float32, pin_memory=True)
         h_iq.copy_(iq[:ech])
         h_soft = torch.empty((ech, cap, 2), dtype=torch.float32, pin_memory=True)
         h_phase = torch.empty((ech, cap), dtype=torch.float32, pin_memory=True)
         h_sidx = torch.empty((ech, cap), dtype=torch.int16, pin_memory=True)
         h_bits = torch.empty((ech, cap * 3), dtype=torch.int16, pin_memory=True)
-        ebank = pk.Bank(ech, props_of(w), device=dev)
 
-        def estep():
-            return ebank.process_raw(h_iq.data_ptr(), n, n, h_soft.data_ptr(), h_bits.data_ptr(), h_phase.data_ptr(),
-                                     h_sidx.data_ptr(), cap, cap * 3, xdelta=XDELTA, packet_len=PACKET_LEN,
-                                     flags=B.FLAG_HOST_BUFFERS)
+        def e2e_rate(nchan, n_call, calls, pipelined):
+            """`calls` pskd_process calls of nchan channels x n_call samples each with host buffers; pipelined: every call
+            returns at once (PSKD_FLAG_NO_SYNC) and one pskd_sync ends the timed region"""
+            eb = pk.Bank(nchan, table[:nchan], device=dev)
+            fl = B.FLAG_HOST_BUFFERS | (B.FLAG_NO_SYNC if pipelined else 0)
 
-        for _ in range(max(1, min(args.warmup, 2))):
-            estep()
-        barrier()
+            def call(j):
+                off = (j * n_call) % max(n - n_call + 1, 1) if n_call < n else 0
+                return eb.process_raw(h_iq.data_ptr() + off * 8, n, n_call, h_soft.data_ptr(), h_bits.data_ptr(), h_phase.data_ptr(),
+                                      h_sidx.data_ptr(), cap, cap * 3, xdelta=XDELTA, packet_len=PACKET_LEN, flags=fl)
+            for j in range(2):
+                call(j)
+            eb.sync()
+            barrier()
+            t0 = time.perf_counter()
+            ns = None
+            for j in range(calls):
+                _, ns, _ = call(j)
+            eb.sync()
+            dt = (time.perf_counter() - t0) / calls
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            ksum = int(sum(int(v) for v in ns))
+            bpb_mean = sum(bits_per_baud(p["constelationSize"]) for p in table[:nchan]) / nchan
+            del eb
+            nranks = world if (scaling == "strong" or world == 1) else world
+            return {"value": nranks * nchan * n_call / dt / 1e6, "channels": nchan, "samples_per_call": n_call, "calls": calls,
+                    "ms_per_call": dt * 1e3, "h2d_bytes": nchan * n_call * 8, "d2h_bytes": int(ksum * (8 + 4 + 2 + 2 * bpb_mean))}
+
         esteps = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(esteps):
-            _, ns, nb = estep()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / esteps
-        K = int(ns[0])
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": world * ech * n / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": ech * n * 8,
-               "d2h_bytes_per_step": ech * K * (8 + 4 + 2 + 2 * bpb), "channels": ech, "samples": n,
-               "ms_per_step": dt * 1e3, "note": "pskd_process with PSKD_FLAG_HOST_BUFFERS on pinned host memory; "
-               f"{ech}-channel sub-bank of the workload (PCIe-bound, rate independent of bank size)"}
-        del ebank
+        main_leg = e2e_rate(ech, n, esteps, pipelined=False)
+        small = e2e_rate(max(1, ech // 4), n, esteps, pipelined=False) if ech >= 8 else None
+        stream_leg = e2e_rate(ech, min(PACKET_LEN, n), 16, pipelined=True)
+        e2e = {"value": main_leg["value"], "unit": "Msamples/s", "h2d_bytes_per_step": main_leg["h2d_bytes"],
+               "d2h_bytes_per_step": main_leg["d2h_bytes"], "channels": ech, "samples": n, "ms_per_step": main_leg["ms_per_call"],
+               "bank_sizes": [x for x in (small, main_leg) if x],
+               "streaming": stream_leg,
+               "note": "pskd_process with PSKD_FLAG_HOST_BUFFERS on pinned host memory (H2D + D2H inside the timed region, staged "
+                       f"through a bounded ring of slabs); {ech}-channel sub-bank of this rank's channels; `bank_sizes` repeats it on a "
+                       "quarter of the channels (PCIe-bound: the rate does not depend on the bank size); `streaming` = one 64000-sample "
+                       "packet per channel and call, calls pipelined with PSKD_FLAG_NO_SYNC"}
 
     # ---- cpu_baseline: the reference CPU demod on a bounded sample, rank 0, N=1 only --------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and nch:
         os.sched_setaffinity(0, full_affinity)       # the reference gets every host core again
         cores = os.cpu_count() or 1
-        cch = min(nch, 512)                      # ~20-30 core-seconds of reference CPU work
+        rows = sample_rows(nch, 512)                 # ~20-30 core-seconds of reference CPU work
         cn = n if nch > 1 else min(n, 16_000_000)
-        iq_h = iq[:cch, :cn].contiguous().cpu().numpy().view(np.complex64).reshape(cch, cn)
-        rate, kind, secs = cpu_demod_rate(w, iq_h, cores)
-        rate1, _, _ = cpu_demod_rate(w, iq_h[:1], 1)
+        iq_h = iq[rows, :cn].contiguous().cpu().numpy().view(np.complex64).reshape(len(rows), cn)
+        tab = [table[i] for i in rows]
+        rate, kind, secs = cpu_demod_rate(tab, iq_h, cores)
+        rate1, _, _ = cpu_demod_rate(tab[:1], iq_h[:1], 1)
         cpu = {"value": rate, "unit": "Msamples/s", "cores": cores, "kind": kind,
-               "sample": f"first {cch} channels x {cn} samples of this workload, {secs:.2f} s wall on {cores} threads",
+               "sample": f"{len(rows)} channels spread over the bank x {cn} samples of this workload, {secs:.2f} s wall on {cores} threads",
                "single_core_value": rate1}
 
     if rank == 0:
         clocks = sampler.summary(t_wall0, t_wall1)
+        cfg = config_of(args, w, world, scaling, nch_global)
+        cfg.update({"channels_this_rank": nch,
+                    "l2": f"inputs ({nch * n * 8 / 1e9:.1f} GB on this GPU) far larger than the 126 MB L2; no flush needed",
+                    "parallelism": (f"ONE bank of {nch_global} channels partitioned over {world} GPU(s) in contiguous"
+                                    f"{' cost-balanced' if w.get('mixed') else ''} channel ranges, no collective" if scaling == "strong" or world == 1
+                                    else f"{world} independent banks of {nch_global} channels, one per GPU, no collective"),
+                    "input": "replayed resident buffer; carrier offsets quantised so that the replay is a continuous stream",
+                    "host_affinity": numa})
         line = {"metric": "Msamples/s demodulated", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32/f64", "data": "synthetic",
-                "config": {"workload": args.workload, "description": w["desc"], "channels_per_gpu": nch, "samples_per_channel": n,
-                           "samplesPerBaud": S, "constelationSize": w["M"], "numAvg": w["A"], "phaseAvg": w["P"],
-                           "differentialDecoding": w["D"], "packet_len": PACKET_LEN, "xdelta": XDELTA,
-                           "l2": f"inputs ({nch * n * 8 / 1e9:.1f} GB per GPU) far larger than the 126 MB L2; no flush needed",
-                           "parallelism": f"channels sharded over {world} GPU(s), no collective", "host_affinity": numa},
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "f32/f64", "data": "synthetic", "config": cfg,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "chain": {k: stats[k] for k in ("spec_chunks", "spec_misses", "seq_channels", "wraps")}}
+                "chain": {k: stats.get(k) for k in ("spec_chunks", "spec_misses", "seq_channels", "wraps", "tp_packets")}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -178,6 +178,10 @@ const char* pskd_last_error(void);
 
 int pskd_abi_version(void);
 
+/* CUDA devices visible to this process (0 when there is no driver / device: every other entry point then fails with
+ * PSKD_ERR_CUDA -- there is no CPU path) */
+int pskd_device_count(void);
+
 /* ---- synthetic channel-bank generator (benchmark / test input, generated in HBM so that
  * 30+ GB banks never cross PCIe).  Counter-based: sample n of channel c depends only on
  * (seed, c, n).  Not part of the reference; SURVEY.md section 8d fixes the value distribution. */

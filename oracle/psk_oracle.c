@@ -10,11 +10,11 @@
  *
  * PARITY PINNING: this restatement is pinned bit-for-bit (soft, bits, phase, sampleIndex)
  * against the UNMODIFIED reference compiled in place (oracle/_ref/libpsk_ref.so, see
- * oracle/Makefile) by tests/test_oracle_vs_ref.py in the build container and against the
+ * oracle/Makefile) by tests/test_oracle_cpu.py in the build container and against the
  * committed golden vectors tests/golden/ (npz files) (generated from that reference build by
  * tests/golden/make_golden.py) everywhere else.  The reference itself ships no golden
  * vectors; its own test (tests/test_psk_soft.py:178-238) only bounds the soft-symbol error
- * by 1e-3, which tests/test_reference_cases.py re-creates.
+ * by 1e-3, which tests/test_oracle_cpu.py::test_reference_own_assertions_hold re-creates.
  *
  * Arithmetic notes (all verified against the reference build, see oracle/README.md):
  *  - float expressions are evaluated in float (x86-64 SSE, FLT_EVAL_METHOD 0), no FMA

@@ -16,7 +16,8 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpskd.so")
 SOURCES = ["pskd_api.cu", "pskd_kernels.cu", "pskd_fused.cu", "pskd_synth.cu"]
 HEADERS = ["pskd_exact.cuh", "pskd_internal.h", "pskd_device.cuh", os.path.join("..", "..", "include", "pskd.h"),
-           os.path.join("..", "host", "psk_soft_gpu.hpp"), os.path.join("..", "host", "demo_component.cpp")]
+           os.path.join("..", "host", "psk_soft_gpu.hpp"), os.path.join("..", "host", "demo_component.cpp"),
+           os.path.join("..", "host", "demo_box.cpp")]
 NVCC_COMPILE = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared"]
 
@@ -82,11 +83,12 @@ def build_host_demo() -> str:
     """Compile the C++ host mirror's demo against libpskd.so (checks psk_soft_gpu.hpp builds as plain C++11)."""
     host = os.path.join(HERE, "host")
     exe = os.path.join(LIB_DIR, "demo_component")
-    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-pthread", "-o", exe, os.path.join(host, "demo_component.cpp"),
-           "-L" + LIB_DIR, "-lpskd", "-Wl,-rpath,$ORIGIN"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("g++ failed on the host mirror:\n" + res.stdout + res.stderr)
+    for name in ("demo_component", "demo_box"):      # one component on GPU 0; one bank sharded over every visible GPU
+        cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-pthread", "-o", os.path.join(LIB_DIR, name), os.path.join(host, name + ".cpp"),
+               "-L" + LIB_DIR, "-lpskd", "-Wl,-rpath,$ORIGIN"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("g++ failed on the host mirror:\n" + res.stdout + res.stderr)
     return exe
 
 

@@ -19,7 +19,7 @@ FLAG_HOST_BUFFERS, FLAG_QUEUE_FLUSHED, FLAG_SRI_CHANGED, FLAG_NO_SYNC = 1, 2, 4,
 # every symbol include/pskd.h declares (tests check the library exports all of them)
 EXPORTS = ("pskd_default_props", "pskd_create", "pskd_destroy", "pskd_set_props", "pskd_get_props",
            "pskd_max_symbols", "pskd_process", "pskd_sync", "pskd_stream", "pskd_get_sri", "pskd_get_stats",
-           "pskd_launch_count", "pskd_last_error", "pskd_abi_version", "pskd_synth_fill",
+           "pskd_launch_count", "pskd_last_error", "pskd_abi_version", "pskd_device_count", "pskd_synth_fill",
            "pskd_profile_enable", "pskd_profile_read", "pskd_state_size", "pskd_state_export", "pskd_state_import")
 
 
@@ -93,6 +93,7 @@ def load(build_if_missing: bool = True):
     lib.pskd_launch_count.argtypes = [H]; lib.pskd_launch_count.restype = C.c_uint64
     lib.pskd_last_error.argtypes = []; lib.pskd_last_error.restype = C.c_char_p
     lib.pskd_abi_version.argtypes = []; lib.pskd_abi_version.restype = C.c_int
+    lib.pskd_device_count.argtypes = []; lib.pskd_device_count.restype = C.c_int
     lib.pskd_profile_enable.argtypes = [H, C.c_int]; lib.pskd_profile_enable.restype = C.c_int
     lib.pskd_profile_read.argtypes = [H, C.POINTER(KernelTime), C.c_int, C.POINTER(C.c_int), C.c_int]
     lib.pskd_profile_read.restype = C.c_int

@@ -99,12 +99,17 @@ struct pskd_bank {
     // ring of staging slots (host-buffer mode): slot r was filled (ev_h2d), consumed by the kernels (ev_kern), emptied (ev_d2h)
     cudaEvent_t ev_h2d[RING] = {nullptr}, ev_kern[RING] = {nullptr}, ev_d2h[RING] = {nullptr};
     unsigned long long slab_seq = 0;     // slabs issued so far (ring position continues across calls)
+    // mixed banks: the fused launches of the samples-per-symbol classes run on separate streams, so that one
+    // class's tail (few warps left) overlaps the next class's start; ev_call orders them after this call's uploads
+    cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr}, ev_call = nullptr;
     long long slab_bytes = 256LL << 20;  // host-buffer mode: staging per slab (PSKD_SLAB_MB)
-    int tp_max_channels = 2048;          // auto: time-parallel chain for launches of at most this many scan-chain channels (PSKD_TP_MAX)
+    int tp_max_channels = 16384;         // auto: time-parallel chain for launches of at most this many scan-chain channels (PSKD_TP_MAX)
     int chain_mode = 0;        // 0 auto (scan-based where possible), 1 force the sequential chain (PSKD_CHAIN=seq)
     int fused_mode = -1;       // -1 auto (large banks), 0 never, 1 whenever a channel qualifies (PSKD_FUSED)
     int host_slabs = MAX_SLABS; // host-buffer mode: most channel slabs one call is cut into (PSKD_SLABS, 1..MAX_SLABS)
-    int fused_min_channels = 1152;   // auto: channels per launch from which the fused kernel beats the staged ones (measured crossover ~1120 for 1M-sample 8-PSK calls; PSKD_FUSED_MIN)
+    int fused_min_channels = 2816;   // auto: fusable channels per launch from which the fused kernel beats the time-parallel staged kernels
+                                     // (measured, 1M-sample 8-PSK calls: 2048 channels 8.4 vs 7.9 ms, 3072 channels 9.8 vs 11.1 ms; PSKD_FUSED_MIN)
     int* d_list = nullptr;     // fused launch lists (channel indices), one segment per (slab, samplesPerBaud)
     int* h_list_slot[2] = {nullptr, nullptr};
     int* d_done = nullptr;     // [n_channels] units completed per channel in the current call
@@ -202,6 +207,11 @@ static int ensure_rings(pskd_bank* b) {
 extern "C" {
 
 int pskd_abi_version(void) { return PSKD_ABI_VERSION; }
+int pskd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
 const char* pskd_last_error(void) { return g_last_error.c_str(); }
 void pskd_default_props(pskd_props* p) { if (p) default_props(p); }
 
@@ -236,6 +246,11 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CT(cudaStreamCreateWithFlags(&b->copy_in, cudaStreamNonBlocking));
     CT(cudaStreamCreateWithFlags(&b->copy_out, cudaStreamNonBlocking));
+    CT(cudaEventCreateWithFlags(&b->ev_call, cudaEventDisableTiming));
+    for (int i = 0; i < 3; i++) {
+        CT(cudaStreamCreateWithFlags(&b->aux_stream[i], cudaStreamNonBlocking));
+        CT(cudaEventCreateWithFlags(&b->ev_aux[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < RING; i++) {
         CT(cudaEventCreateWithFlags(&b->ev_h2d[i], cudaEventDisableTiming));
         CT(cudaEventCreateWithFlags(&b->ev_kern[i], cudaEventDisableTiming));
@@ -291,6 +306,11 @@ int pskd_destroy(pskd_handle b) {
     b->tp_end_ring.release(); b->tp_start_ring.release(); b->tp_fail.release(); b->tp_slot_flags.release();
     b->prof.destroy();
     for (int i = 0; i < RING; i++) for (cudaEvent_t e : {b->ev_h2d[i], b->ev_kern[i], b->ev_d2h[i]}) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 3; i++) {
+        if (b->aux_stream[i]) { cudaStreamSynchronize(b->aux_stream[i]); cudaStreamDestroy(b->aux_stream[i]); }
+        if (b->ev_aux[i]) cudaEventDestroy(b->ev_aux[i]);
+    }
+    if (b->ev_call) cudaEventDestroy(b->ev_call);
     if (b->copy_in) cudaStreamDestroy(b->copy_in);
     if (b->copy_out) cudaStreamDestroy(b->copy_out);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -659,11 +679,13 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     static const int fusedS[4] = {8, 9, 10, 16};
     for (int s = 0; s < n_slabs; s++) {
         const int lo = slab_lo(s), hi = slab_lo(s + 1);
-        int nf = 0;
-        for (int i = lo; i < hi; i++) nf += fusable[i];
-        const bool use = nf > 0 && (b->fused_mode == 1 || nf >= b->fused_min_channels);
-        if (!use) continue;
         for (int si = 0; si < 4; si++) {
+            // the fused kernel needs enough channels of ONE samples-per-symbol class to fill the resident warps (each channel's
+            // units run one after the other); smaller classes take the time-parallel staged kernels
+            int nf = 0;
+            for (int i = lo; i < hi; i++) nf += (fusable[i] && b->h_desc[i].S == fusedS[si]);
+            const bool use = nf > 0 && (b->fused_mode == 1 || nf >= b->fused_min_channels);
+            if (!use) continue;
             FusedSeg g{s, fusedS[si], n_listed, 0, 1, 1, 0, 1LL << 62};
             for (int i = lo; i < hi; i++) {
                 ChanDesc& d = b->h_desc[i];
@@ -704,8 +726,11 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             if (d.flags & CH_FUSED) { d.scr_off = 0; continue; }
             any_staged = true;
             if (d.flags & CH_FAST) si.n_fast++; else si.n_seq++;
-            d.scr_off = scr_slab;
-            scr_slab += (d.K + 3) & ~3LL;
+            // the chain kernels read the scratch packet by packet: shift the row so that packet 1 (and with it every packet
+            // whose symbol count is a multiple of 4) starts 16-byte aligned
+            const long long k1 = first_symbol_at(d.pkt_len, d.tail_len, d.S, d.A, d.K);
+            d.scr_off = scr_slab + ((4 - (k1 & 3)) & 3);
+            scr_slab += ((d.K + 3) & ~3LL) + 4;
             si.Kmax = std::max(si.Kmax, d.K);
             if (fzsable[i]) {              // staged, through the fused kernel's stages
                 d.flags |= CH_FZS;
@@ -808,20 +833,21 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         CUDA_TRY(b->tp_end_ring.reserve((size_t)tp_records * tp_stride));
         CUDA_TRY(b->tp_start_ring.reserve((size_t)tp_records * tp_stride));
         CUDA_TRY(b->tp_fail.reserve((size_t)nch));
-        CUDA_TRY(b->tp_slot_flags.reserve(2 * (size_t)tp_slots));
+        CUDA_TRY(b->tp_slot_flags.reserve(2 * (size_t)tp_slots + 4));
         // pageable sources: the copies are staged before the calls return
         CUDA_TRY(cudaMemcpyAsync(b->tp_items.p, tp_heads.data(), sizeof(TpItem) * tp_heads.size(), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemcpyAsync(b->tp_items.p + tp_heads.size(), tp_items.data(), sizeof(TpItem) * tp_items.size(), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemcpyAsync(b->tp_chans.p, tp_chans.data(), sizeof(TpChan) * tp_chans.size(), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemsetAsync(b->tp_fail.p, 0, sizeof(int) * nch, b->stream));
-        CUDA_TRY(cudaMemsetAsync(b->tp_slot_flags.p, 0, sizeof(int) * 2 * (size_t)tp_slots, b->stream));
+        CUDA_TRY(cudaMemsetAsync(b->tp_slot_flags.p, 0, sizeof(int) * (2 * (size_t)tp_slots + 4), b->stream));
     }
 
     // the kernels of one slab of channels [lo, hi)
     auto run_slab = [&](int slab, int lo, int hi) -> int {
         const SlabInfo& si = slabs[slab];
         LaunchCtx Ls{};
-        Ls.stream = b->stream; Ls.n_channels = hi - lo; Ls.Kmax = si.Kmax; Ls.Smax = si.Smax; Ls.Amax = si.Amax;
+        Ls.stream = b->stream; Ls.n_channels = hi - lo;
+        Ls.Kmax = si.Kmax; Ls.Smax = si.Smax; Ls.Amax = si.Amax;
         Ls.S_mask = si.S_mask; Ls.S_mask_fast = si.S_mask_fast; Ls.Amax_fast = si.Amax_fast; Ls.Amin_fast = si.Amin_fast;
         Ls.Pmax_fast = si.Pmax_fast; Ls.n_fast_channels = si.n_fast; Ls.n_seq_channels = si.n_seq;
         Ls.d_desc = b->d_desc + lo; Ls.h_desc = b->h_desc + lo; Ls.d_state = b->d_state + lo; Ls.d_ring = b->d_ring;
@@ -835,10 +861,16 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             Ls.tp_pkts = b->tp_pkts.p; Ls.tp_ends = b->tp_ends.p; Ls.tp_end_ring = b->tp_end_ring.p; Ls.tp_start_ring = b->tp_start_ring.p;
             Ls.tp_ring_stride = tp_stride; Ls.tp_fail = b->tp_fail.p + lo;
             Ls.tp_slot_fail = b->tp_slot_flags.p; Ls.tp_slot_run = b->tp_slot_flags.p + tp_slots;
+            Ls.tp_any_rerun = b->tp_slot_flags.p + 2 * (size_t)tp_slots;
             Ls.tp_n_chans_fzs = si.tp_fzs;
         }
         Ls.n_fzs_channels = si.n_fzs; Ls.Pmax_fzs = si.Pmax_fzs; Ls.S_mask_fzs = si.S_mask_fzs; Ls.Kmax_fzs = si.Kmax_fzs;
         Ls.d_fzs_ticket = b->d_ticket + FUSED_TICKETS; Ls.fzs_ticket_next = &b->fzs_ticket_next; Ls.fzs_ticket_cap = FZS_TICKETS;
+        // A mixed bank has one fused launch per samples-per-symbol class that is large enough: the first on the bank's stream,
+        // the others on aux streams, so that one class's tail (few warps left) overlaps the next class's start.
+        int n_seg = 0, seg_total = 0, seg_count = 0;
+        static const bool multi_stream = !(getenv("PSKD_FUSED_STREAMS") && atoi(getenv("PSKD_FUSED_STREAMS")) == 0);
+        for (const FusedSeg& g : segs) if (g.slab == slab) { seg_total += g.count; seg_count++; }
         for (const FusedSeg& g : segs) {
             if (g.slab != slab) continue;
             FusedLaunch f{};
@@ -861,8 +893,21 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             f.Amax = g.Amax; f.Pmax = g.Pmax;
             f.d_ticket = b->d_ticket + (slab * 4 + (g.S == 8 ? 0 : g.S == 9 ? 1 : g.S == 10 ? 2 : 3));
             f.d_done = b->d_done + lo;
-            CUDA_TRY(launch_fused(Ls, f));
+            static const bool share = getenv("PSKD_FUSED_SHARE") && atoi(getenv("PSKD_FUSED_SHARE")) != 0;   // measured slower (config5: 49 vs 38 ms)
+            f.grid_share = (share && multi_stream && seg_count > 1) ? (double)g.count / (double)seg_total : 0.0;
+            if (n_seg == 0 || !multi_stream) {
+                CUDA_TRY(launch_fused(Ls, f));
+            } else {
+                if (n_seg == 1) CUDA_TRY(cudaEventRecord(b->ev_call, b->stream));       // everything this call queued before the launches
+                LaunchCtx La = Ls;
+                La.stream = b->aux_stream[n_seg - 1];
+                CUDA_TRY(cudaStreamWaitEvent(La.stream, b->ev_call, 0));
+                CUDA_TRY(launch_fused(La, f));
+                CUDA_TRY(cudaEventRecord(b->ev_aux[n_seg - 1], La.stream));
+            }
+            n_seg++;
         }
+        for (int k = 1; k < n_seg && multi_stream; k++) CUDA_TRY(cudaStreamWaitEvent(b->stream, b->ev_aux[k - 1], 0));
         if (si.n_fast + si.n_seq > 0) {
             CUDA_TRY(launch_front(Ls));
             CUDA_TRY(launch_fzs_front(Ls));

@@ -167,6 +167,10 @@ __device__ __forceinline__ void fz_cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void fz_cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void fz_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // e = f32(f32(re*re) + f32(im*im)) (std::norm<float>, cpp/psk_soft.cpp:448) with the two products in one
@@ -249,6 +253,25 @@ static __device__ __noinline__ void fz_epilogue(FzCtx& cx, float* yh) {
 }
 
 static __device__ __noinline__ void fz_resum(FzCtx& cx, float* yh) { SmemRing r{yh}; fit_resum(cx.st.fit, r); }   // :51-52
+// The rare paths below are reached from the hot, inlined stage code.  They take the warp's shared-memory OFFSET, not
+// pointers: a pointer parameter into shared memory makes the caller form generic addresses (S2R + 64-bit adds) on the hot
+// path, whether or not the rare path is taken (measured: ~9 of 320 instructions per 32 symbols).
+template <class L> static __device__ __noinline__ void fz_normalize_ring_w(const unsigned wofs, const int lane) {
+    unsigned char* wb = fz_smem + wofs;
+    FzCtx& cx = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    fz_normalize_ring(reinterpret_cast<float*>(wb + L::OFF_YH), reinterpret_cast<float*>(wb + L::OFF_ALIAS + FZ_B * 8) + FZ_B,
+                      cx.st.fit, cx.P, lane);
+}
+template <class L> static __device__ __noinline__ void fz_rebuild_cz_w(const unsigned wofs, const int lane) {
+    unsigned char* wb = fz_smem + wofs;
+    FzCtx& cx = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    fz_rebuild_cz(reinterpret_cast<const float*>(wb + L::OFF_YH), reinterpret_cast<double*>(wb + L::OFF_ALIAS) - (cx.P + 1), cx.P, lane);
+}
+template <class L> static __device__ __noinline__ void fz_resum_w(const unsigned wofs) {
+    unsigned char* wb = fz_smem + wofs;
+    fz_resum(*reinterpret_cast<FzCtx*>(wb + L::OFF_CTX), reinterpret_cast<float*>(wb + L::OFF_YH));
+}
+
 static __device__ __noinline__ int fz_unwrap_count_slow(float est_prev, float theta) {
     const double dlt = dsubr((double)est_prev, (double)theta);
     return (int)(long long)round(__ddiv_rn(dlt, PSKD_M_2PI));
@@ -356,10 +379,15 @@ static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float
 // conflict-free).  The block's code is executed once per 128 symbols, so its cost is
 // dominated by instruction fetch (the L0 instruction cache holds ~380 instructions and is shared by the
 // warps of a scheduler): four trips through ~70 instructions beat one trip through ~250.
-template <int BPB, bool DIFF>
-static __device__ __noinline__ void fz_back_rolled(const float2* __restrict__ selb, const float* __restrict__ th,
-                                                   float2* __restrict__ cst, short* __restrict__ bstage,
-                                                   int lane, int M, int m) {
+// The buffers are addressed from the warp's shared-memory offset (not through generic pointer parameters: those cost
+// ~15 instructions per 32 symbols of address conversion and turn every access into a generic LD / ST).
+template <class L, int BPB, bool DIFF>
+static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const int lane, const int M, const int m) {
+    unsigned char* wb = fz_smem + wofs;
+    const float*  __restrict__ th     = reinterpret_cast<const float*>(wb + L::OFF_TH);
+    const float2* __restrict__ selb   = reinterpret_cast<const float2*>(wb + L::OFF_SEL);
+    float2*       __restrict__ cst    = reinterpret_cast<float2*>(wb + L::OFF_ALIAS);              // soft staging [FZ_B]
+    short*        __restrict__ bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS + FZ_B * 8);    // bits staging [FZ_B * 3]
     const float inv_m = 1.0f / (float)M;
     const bool inexact = (BPB == 0 && (M & (M - 1)) != 0);                 // -est/M not an exact multiply
 #ifdef PSKD_FZ_BACK_UNROLL2
@@ -378,7 +406,7 @@ static __device__ __noinline__ void fz_back_rolled(const float2* __restrict__ se
         fz_sincos(pc, sn, cs, bad);                                                               // :499
         const float x = fsubr(fmulr(s.x, cs), fmulr(s.y, sn));                                    // :500-501, unfused
         const float y = faddr(fmulr(s.x, sn), fmulr(s.y, cs));
-        bad = bad || (isnan(x) && isnan(y));                                                      // __mulsc3 recovery
+        bad = bad || !(fabsf(x) + fabsf(y) < 3.0e38f);                                            // NaN / inf: __mulsc3 recovery decides
         const float2 c = make_float2(x, y);
         cst[i] = c;
         if (BPB == 3) {
@@ -391,7 +419,7 @@ static __device__ __noinline__ void fz_back_rolled(const float2* __restrict__ se
         }
         bad = bad && i < m;
         if (__any_sync(0xffffffffu, bad)) {             // rare: literal evaluation of the flagged symbols
-            if (bad) fz_back_literal(selb[2 + i], selb[1 + i], th[i], M, BPB, DIFF ? 1 : 0, cst + i, bstage + i * BPB);
+            if (bad) fz_back_literal(selb[2 + i], selb[1 + i], th[i], M, BPB, DIFF ? 1 : 0, &cst[i], &bstage[i * BPB]);
         }
     }
 }
@@ -422,8 +450,8 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
     double* cz = czblk - (P + 1);
     const int i0 = lane * 4;
 
-    if (cx.st.fit.head != 0) { fz_normalize_ring(yh, estv, cx.st.fit, P, lane); if (lane == 0) cx.cz_valid = 0; __syncwarp(); }
-    if (!cx.cz_valid) { fz_rebuild_cz(yh, cz, P, lane); if (lane == 0) cx.cz_valid = 1; __syncwarp(); }
+    if (cx.st.fit.head != 0) { fz_normalize_ring_w<L>(wofs, lane); if (lane == 0) cx.cz_valid = 0; __syncwarp(); }
+    if (!cx.cz_valid) { fz_rebuild_cz_w<L>(wofs, lane); if (lane == 0) cx.cz_valid = 1; __syncwarp(); }
 
     float4 t4 = *reinterpret_cast<const float4*>(th + i0);
     if (m < FZ_B) {                    // a short block: what lies behind it in the buffer may be anything (never written,
@@ -587,14 +615,14 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
     const int M = cx.M, bpb = cx.bpb, kchain = cx.kchain;
     const bool diff = cx.diff != 0;
     switch (bpb * 2 + (diff ? 1 : 0)) {
-        case 6: fz_back_rolled<3, false>(selb, th, cst, bstage, lane, M, m); break;
-        case 7: fz_back_rolled<3, true>(selb, th, cst, bstage, lane, M, m); break;
-        case 4: fz_back_rolled<2, false>(selb, th, cst, bstage, lane, M, m); break;
-        case 5: fz_back_rolled<2, true>(selb, th, cst, bstage, lane, M, m); break;
-        case 2: fz_back_rolled<1, false>(selb, th, cst, bstage, lane, M, m); break;
-        case 3: fz_back_rolled<1, true>(selb, th, cst, bstage, lane, M, m); break;
-        case 0: fz_back_rolled<0, false>(selb, th, cst, bstage, lane, M, m); break;
-        default: fz_back_rolled<0, true>(selb, th, cst, bstage, lane, M, m); break;
+        case 6: fz_back_rolled<L, 3, false>(wofs, lane, M, m); break;
+        case 7: fz_back_rolled<L, 3, true>(wofs, lane, M, m); break;
+        case 4: fz_back_rolled<L, 2, false>(wofs, lane, M, m); break;
+        case 5: fz_back_rolled<L, 2, true>(wofs, lane, M, m); break;
+        case 2: fz_back_rolled<L, 1, false>(wofs, lane, M, m); break;
+        case 3: fz_back_rolled<L, 1, true>(wofs, lane, M, m); break;
+        case 0: fz_back_rolled<L, 0, false>(wofs, lane, M, m); break;
+        default: fz_back_rolled<L, 0, true>(wofs, lane, M, m); break;
     }
     int16_t* o_bits = cx.o_bits;
     __syncwarp();
@@ -670,9 +698,12 @@ static __device__ __noinline__ void fz_chain_slow(const unsigned wofs, const int
 
 // a packet is exhausted: its epilogue (cpp/psk_soft.cpp:592-603) and, unless it was the unit's last, the
 // next packet's prologue (:393-426).  Returns true when the unit is done.
-template <int S_STATIC>
-static __device__ __noinline__ bool fz_next_packet(FzCtx& cx, float* yh, const int lane) {
-    const int S = S_STATIC ? S_STATIC : cx.S_rt;
+template <class L>
+static __device__ __noinline__ bool fz_next_packet(const unsigned wofs, const int lane) {
+    unsigned char* wb = fz_smem + wofs;
+    FzCtx& cx = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    float* yh = reinterpret_cast<float*>(wb + L::OFF_YH);
+    const int S = L::S_STATIC ? L::S_STATIC : cx.S_rt;
     if (cx.end_mid) { if (lane == 0) cx.unit_done = 1; __syncwarp(); return true; }    // the packet goes on in the next unit
     if (lane == 0) fz_epilogue(cx, yh);
     __syncwarp();
@@ -704,12 +735,12 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
         const int kchain = cx.kchain;
         const int rem = cx.pk_hi - kchain;
         if (rem == 0) {
-            if (fz_next_packet<L::S_STATIC>(cx, yh, lane)) break;
+            if (fz_next_packet<L>(wofs, lane)) break;
             continue;
         }
         const int nbuf = cx.nbuf;
-        const int want = min(FZ_B, rem);
-        if (nbuf < want) break;
+        const int want = min(FZ_B, rem);      // blocks are counted from the packet's first symbol: the same packets give the
+        if (nbuf < want) break;               // same blocks (and bit-identical results) however the stream is cut into calls
 
         // ---- one sub-block of m symbols at buffer offset 0 ----------------------------------------
         int m = want;
@@ -718,7 +749,7 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
         const bool fast = (pts == P) && (P > 1);
         if (fast && cnt + m > 1048576) {
             if (cnt == 1048576) {                                                   // :51-52 at a block edge
-                if (lane == 0) fz_resum(cx, yh);
+                if (lane == 0) fz_resum_w<L>(wofs);
                 __syncwarp();
                 continue;
             }
@@ -803,6 +834,11 @@ static __device__ __noinline__ void fz_theta_fixup(float* th, const float2* sel,
     th[i] = atan2f(z.y, z.x);
 }
 
+template <class L> static __device__ __noinline__ void fz_theta_fixup_w(const unsigned wofs, int i, unsigned M) {
+    unsigned char* wb = fz_smem + wofs;
+    fz_theta_fixup(reinterpret_cast<float*>(wb + L::OFF_TH), reinterpret_cast<const float2*>(wb + L::OFF_SEL) + 2, i, M);
+}
+
 __device__ __forceinline__ void fz_prefetch_l2(const void* p, unsigned bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -836,9 +872,13 @@ __device__ __forceinline__ void fz_issue(float2* st, const float2* src, int lane
         }
     }
 }
-template <int S>
-static __device__ __noinline__ void fz_fill_slow(float2* st, long long s0, const FzCtx& cx, int lane) {
+template <int S, int PC>
+static __device__ __noinline__ void fz_fill_slow(const unsigned wofs, const int trail, long long s0, int lane) {
     using C = FzCfg<S>;
+    using L = FzL<S, PC>;
+    unsigned char* wb = fz_smem + wofs;
+    float2* st = reinterpret_cast<float2*>(wb + (trail ? L::OFF_T : L::OFF_L));
+    const FzCtx& cx = *reinterpret_cast<const FzCtx*>(wb + L::OFF_CTX);
     const long long V = cx.V, tail_len = cx.tail_len;
     const float2* tailp = cx.tail;
     const float2* in_mt = cx.in_mt;
@@ -1076,8 +1116,8 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
                 fz_issue<S, A16>(Tst, in_mt + (long long)krow * S, lane);
                 fz_issue<S, A16>(Lst, in_mt + (long long)(krow + lag) * S, lane);
             } else {
-                fz_fill_slow<S>(Tst, (long long)krow * S, cx, lane);
-                fz_fill_slow<S>(Lst, (long long)(krow + lag) * S, cx, lane);
+                fz_fill_slow<S, PC>(wofs, 1, (long long)krow * S, lane);
+                fz_fill_slow<S, PC>(wofs, 0, (long long)(krow + lag) * S, lane);
             }
         }
         fz_cp_async_wait_all();
@@ -1172,7 +1212,7 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
         }
         if (__any_sync(0xffffffffu, bad)) {            // rare: literal angle for odd inputs / other M
             __syncwarp();
-            if (bad) fz_theta_fixup(th, selb + 2, nbuf + lane, (unsigned)M);
+            if (bad) fz_theta_fixup_w<L>(wofs, nbuf + lane, (unsigned)M);
         }
         nbuf += nrows;
         c++;
@@ -1659,6 +1699,7 @@ k_fzs_cb(const FzsCbParams prm)
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
     float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
+    if (prm.tp.rerun && *prm.tp.any_rerun == 0) return;       // a repair round nobody asked for
 
     for (;;) {
         int u = 0;
@@ -1672,15 +1713,23 @@ k_fzs_cb(const FzsCbParams prm)
             fz_drain<L>(wofs);
             if (cx.unit_done) break;
             // the next block of (angle, sample) pairs from the scratch, appended to the block buffer
-            const int nbuf = cx.nbuf, k0 = cx.kchain + nbuf;
-            const int want = min(FZ_B, cx.pk_hi - cx.kchain);
+            const int nbuf = cx.nbuf, kchain = cx.kchain, k0 = kchain + nbuf;
+            const int want = min(FZ_B, cx.pk_hi - kchain);
+            const int need = want - nbuf;
             __syncwarp();
+            if (nbuf == 0 && need == FZ_B && ((reinterpret_cast<uintptr_t>(thg + k0) | reinterpret_cast<uintptr_t>(selg + k0)) & 15) == 0) {
+                // a full block at an aligned position (every block of a packet but its first and last)
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(thg + k0) + lane);
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(selg + k0) + lane);
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(selg + k0) + 32 + lane);
+                reinterpret_cast<float4*>(th)[lane] = t4;
+                reinterpret_cast<float4*>(selb + 2)[lane] = s0;
+                reinterpret_cast<float4*>(selb + 2)[32 + lane] = s1;
+            } else {
 #pragma unroll
-            for (int q = 0; q < FZ_B / 32; q++) {
-                const int i = nbuf + lane + 32 * q;
-                if (i < want) {
-                    th[i] = __ldg(thg + k0 - nbuf + i);
-                    selb[2 + i] = __ldg(selg + k0 - nbuf + i);
+                for (int q = 0; q < FZ_B / 32; q++) {
+                    const int i = lane + 32 * q;
+                    if (i < need) { th[nbuf + i] = __ldg(thg + k0 + i); selb[2 + nbuf + i] = __ldg(selg + k0 + i); }
                 }
             }
             if (lane == 0) cx.nbuf = want;
@@ -1713,6 +1762,7 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     cudaError_t e = cfg.ensure(k_fused<S, PC>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm, carve);
     if (e != cudaSuccess) return e;
     int grid = n_sm * ctas_per_sm;
+    if (f.grid_share > 0.0 && f.grid_share < 1.0) grid = (int)(grid * f.grid_share + 0.999);   // co-resident launches share the SMs
     const int need = (p.n_units + FZ_WARPS - 1) / FZ_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
@@ -1756,7 +1806,8 @@ static cudaError_t launch_fzs_front_t(const LaunchCtx& c) {
     p.ticket = fzs_take_ticket(c);
     if (!p.ticket) return cudaErrorInvalidValue;
     p.sel = c.d_sel; p.theta = c.d_theta; p.out_sidx = c.out_sidx;
-    int grid = n_sm * ctas_per_sm;
+    static const int cta_cap = getenv("PSKD_FZS_FRONT_CTAS") ? atoi(getenv("PSKD_FZS_FRONT_CTAS")) : 0;   // tuning: resident CTAs per SM
+    int grid = n_sm * ((cta_cap > 0 && cta_cap < ctas_per_sm) ? cta_cap : ctas_per_sm);
     const int need = (p.n_units + FZ_WARPS - 1) / FZ_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
@@ -1796,7 +1847,8 @@ static cudaError_t launch_fzs_cb_t(const LaunchCtx& c, const TpCtl& tp, int n_un
     p.n_units = n_units;
     p.ticket = fzs_take_ticket(c);
     if (!p.ticket) return cudaErrorInvalidValue;
-    int grid = n_sm * ctas_per_sm;
+    static const int cta_cap = getenv("PSKD_FZS_CB_CTAS") ? atoi(getenv("PSKD_FZS_CB_CTAS")) : 0;   // tuning: resident CTAs per SM
+    int grid = n_sm * ((cta_cap > 0 && cta_cap < ctas_per_sm) ? cta_cap : ctas_per_sm);
     const int need = (n_units + FZ_WARPS - 1) / FZ_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) return cudaSuccess;

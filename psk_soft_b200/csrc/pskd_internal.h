@@ -121,6 +121,7 @@ struct TpCtl {
     int* slot_fail;        // set by k_tp_check: the hand-over INTO this packet could not be proven
     int* slot_run;         // set by k_tp_fix: 0 leave, 1 re-run from a re-synthesised ring, 2 re-run from the predecessor's end record
     int rerun;             // launch flag: process only items with slot_run != 0
+    int* any_rerun;        // set by k_tp_fix when some channel asked for a repair round (else the round's launches return at once)
 };
 
 // ---- optional per-kernel event timing --------------------------------------------------------
@@ -206,7 +207,7 @@ struct LaunchCtx {
     const TpItem* tp_items; int tp_n_items;          // one item per time-parallel packet
     const TpChan* tp_chans; int tp_n_chans; int tp_n_slots;
     TpPacket* tp_pkts; TpEnd* tp_ends; float* tp_end_ring; float* tp_start_ring; int tp_ring_stride;
-    int* tp_fail; int* tp_slot_fail; int* tp_slot_run;
+    int* tp_fail; int* tp_slot_fail; int* tp_slot_run; int* tp_any_rerun;
     int tp_n_chans_fzs;      // how many of the time-parallel channels run through k_fzs_cb (the rest through k_chain_par)
     // staged path through the fused kernel's stages (CH_FZS channels)
     int n_fzs_channels, Pmax_fzs;
@@ -228,6 +229,8 @@ struct FusedLaunch {
     int Amax, Pmax;                    // over the listed channels (sizes the shared-memory regions)
     int* d_ticket;                     // one int, zero before the launch
     int* d_done;                       // [n_channels] zero before the launch (indexed like d_desc)
+    double grid_share;                 // 0 / 1: the whole GPU; else the fraction of the resident CTAs this launch takes (the
+                                       // launches of a mixed bank's samples-per-symbol classes run side by side)
 };
 // algorithmic bytes of a channel's stages (8 N in; per symbol 8 soft + 4 phase + 2 sampleIndex + 2 b bits)
 inline double alg_bytes_front(const ChanDesc& d) { return 8.0 * (double)d.n_in + 2.0 * (double)d.K; }

@@ -1158,6 +1158,7 @@ k_tp_check(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, c
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (slot >= tp.n_items) return;
+    if (tp.rerun && tp.any_rerun && *tp.any_rerun == 0) return;      // the check after a repair round nobody asked for
     const TpItem item = tp.items[slot];
     if (item.kind != 1) return;                                      // the first packet starts from the head's exact state
     const ChanDesc& d = desc[item.ch];
@@ -1211,6 +1212,7 @@ k_tp_fix(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, con
     }
     __syncwarp();
     if (lane != 0) return;
+    *tp.any_rerun = 1;
     const float* thg = theta + d.scr_off;
     const int M = d.M;
     const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)M));
@@ -1293,7 +1295,7 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
     TpCtl tp{};
     tp.chans = c.tp_chans; tp.n_chans = c.tp_n_chans; tp.pkts = c.tp_pkts; tp.ends = c.tp_ends;
     tp.end_ring = c.tp_end_ring; tp.start_ring = c.tp_start_ring; tp.ring_stride = c.tp_ring_stride; tp.fail = c.tp_fail;
-    tp.slot_fail = c.tp_slot_fail; tp.slot_run = c.tp_slot_run;
+    tp.slot_fail = c.tp_slot_fail; tp.slot_run = c.tp_slot_run; tp.any_rerun = c.tp_any_rerun;
     const int tp_fzs = c.tp_n_chans_fzs, tp_legacy = c.tp_n_chans - c.tp_n_chans_fzs;
     // one round of chain work over `items` (null: one unit per channel), each kernel taking its own channels
     // algorithmic bytes per kernel and class of channels (profiling only): [0] packet-after-packet, [1] time-parallel
@@ -1349,7 +1351,7 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
             e = chain_round(t2r, c.tp_n_items, false, true);
             if (e != cudaSuccess) return e;
             c.prof->begin(KID_TP, c.stream);
-            k_tp_check<<<(c.tp_n_items + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2);
+            k_tp_check<<<(c.tp_n_items + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2r);
             c.prof->end(c.stream);
             (*c.launches)++;
         }

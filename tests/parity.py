@@ -58,3 +58,12 @@ def assert_parity(got, ref, differential=False, tag="", check_first_bits=True):
     assert not bad.any(), f"{tag}: soft differs at {np.nonzero(bad)[0][:8] + s0} max rel {np.nanmax(rel):.3e}"
     return dict(max_rel_phase=float(np.nanmax(float_close(got["phase"], ref["phase"])[1])) if len(ref["phase"]) else 0.0,
                 max_rel_soft=float(np.nanmax(rel)) if len(rel) else 0.0)
+
+
+def checkers(oracle):
+    """the CPU checkers to compare against: the C port always, the unmodified reference build (oracle/_ref) where it
+    exists on this box -- (name, component class) pairs"""
+    out = [("port", oracle.OracleComponent)]
+    if oracle.have_ref():
+        out.append(("reference", oracle.RefComponent))
+    return out

@@ -128,16 +128,16 @@ def test_state_import_rejects_corrupt_blobs():
     magic, ver, nch, ring_cap, total = hdr.unpack_from(blob, 0)
     assert total == len(blob)
 
-    def rejected(mut):
+    def rejected(mut, code=-1):
         with pytest.raises(pk.PskdError) as e:
             bank.import_state(bytes(mut))
-        assert e.value.code == -1, e.value
+        assert e.value.code == code, e.value
 
     rejected(blob[:len(blob) - 8])                                    # truncated
     rejected(blob[:hdr.size + 10])
     bad = bytearray(blob); hdr.pack_into(bad, 0, magic, ver, nch, 1 << 30, total); rejected(bad)   # absurd ring
     bad = bytearray(blob); hdr.pack_into(bad, 0, magic, ver, nch, ring_cap, total - 4); rejected(bad)
-    bad = bytearray(blob) + b"\0" * 16; rejected(bad[:])             # trailing bytes: size must match exactly
+    bad = bytearray(blob); bad[hdr.size + 0:hdr.size + 2] = (1).to_bytes(2, "little"); rejected(bad, -4)   # samplesPerBaud = 1 in channel 0's properties
     # corrupt LinearFit head / n of channel 0 (offsets inside the first StateChan are implementation details: flip every
     # int32 of the device part that currently equals phaseAvg or the ring head and expect either a rejection or parity)
     second = bank.process_host(iq[:, 15000:].copy(), xdelta=0.01, packet_len=8000)

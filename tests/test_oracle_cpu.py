@@ -86,6 +86,31 @@ def test_reconfiguration_sequence_matches_reference(oracle_built):
         assert comps[0].sri(0) == comps[1].sri(0) and comps[0].sri(1)["count"] == comps[1].sri(1)["count"]
 
 
+def test_stall_after_window_shrink_matches_reference(oracle_built):
+    """numAvg*samplesPerBaud shrinks below the carried window: the reference consumes packets and emits nothing until the
+    window grows past the deque (cpp/psk_soft.cpp:380-383, 457, 619-636); resetState only truncates the deque.  The C port
+    must stall and recover exactly like the reference build (the GPU test runs the same script against the port)."""
+    if not oracle_built.have_ref():
+        pytest.skip("needs oracle/_ref")
+    iq = siggen.gen_shaped(120000, 8, 8, seed=13, sigma=0.03, freq=2e-5, timing_shift=3)
+    props = dict(samplesPerBaud=8, constelationSize=8, numAvg=100, phaseAvg=50)
+    comps = [oracle_built.RefComponent(**props), oracle_built.OracleComponent(**props)]
+    script = [(0, 20000, {}), (20000, 20300, dict(numAvg=50)), (20300, 20301, {}), (20301, 20500, dict(constelationSize=4)),
+              (20500, 40000, dict(numAvg=200, constelationSize=8)), (40000, 60000, dict(numAvg=20)), (60000, 60700, dict(resetState=1)),
+              (60700, 61000, dict(phaseAvg=30)), (61000, 90000, dict(numAvg=150)), (90000, 120000, {})]
+    emitted = []
+    for a, b, ch in script:
+        outs = []
+        for c in comps:
+            c.configure(**ch)
+            outs.append(c.push(iq[a:b], xdelta=0.01))
+        for k in ("soft", "bits", "phase", "sidx"):
+            assert bits_equal(outs[0][k], outs[1][k]), f"{k} differs after {ch}"
+        assert comps[0].sri(0) == comps[1].sri(0)
+        emitted.append(len(outs[0]["sidx"]))
+    assert emitted[1:4] == [0, 0, 0] and emitted[4] > 0 and emitted[5:8] == [0, 0, 0] and emitted[8] > 0, emitted
+
+
 @pytest.mark.parametrize("name", [c[0] for c in siggen.REFERENCE_CASE_ORDER])
 def test_reference_own_assertions_hold(name, oracle_built):
     """The assertions of the reference's test module (tests/test_psk_soft.py:178-238): soft-decision
