@@ -68,7 +68,9 @@ constexpr int FZ_PF = PSKD_FZ_PF;      // lead blocks are prefetched into L2 thi
 #define FZ_HOT __forceinline__
 #endif
 #ifndef PSKD_FZ_MIN_CTAS
-#define PSKD_FZ_MIN_CTAS 5
+#define PSKD_FZ_MIN_CTAS 5             // 5 CTAs x 4 warps per SM at 96 registers.  6 CTAs at 80 registers (the shared memory allows it): 4096
+                                       // channels 12.3 vs 12.6 ms per launch, but 3072 channels 10.3 vs 9.6 ms (fewer channels than the
+                                       // 3552 resident warps: every warp is slower and the channels' chains set the pace)
 #endif
 
 struct FzCtx {                         // one per warp, shared memory
@@ -122,7 +124,7 @@ template <int S, int PC> struct FzL {
     static constexpr int OFF_L = 0;                                        // float2 lead[32*S]
     static constexpr int OFF_T = BLK;                                      // float2 trail[32*S]
     static constexpr int OFF_CW = 2 * BLK;                                 // double cw[16]     carried window sum per phase
-    static constexpr int OFF_TH = OFF_CW + 16 * 8;                         // float  th[FZ_BUF]
+    static constexpr int OFF_TH = OFF_CW + fz_align16(S * 8);              // float  th[FZ_BUF]
     static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                    // float2 selb[FZ_BUF + 2]; [1] = previous sample
     static constexpr int OFF_YH = fz_align16(OFF_SEL + (FZ_BUF + 2) * 8);  // float  yh[PC]   y history, logical order
     static constexpr int OFF_CTX = fz_align16(OFF_YH + PC * 4);
@@ -1271,7 +1273,9 @@ k_fused(const FusedParams prm)
 #define PSKD_FZS_FRONT_MIN_CTAS 6
 #endif
 #ifndef PSKD_FZS_CB_MIN_CTAS
-#define PSKD_FZS_CB_MIN_CTAS 6
+#define PSKD_FZS_CB_MIN_CTAS 6         // 24 warps per SM at 80 registers.  Measured, 512 x 1M coherent 8-PSK: 7 CTAs / 72 registers 0.948 ms,
+                                       // 6 / 80: 0.988, 5 / 96: 1.008 -- but 7 CTAs spill: differential 256 x 4M 1.87 vs 1.78 ms, one
+                                       // channel x 64M (latency-bound) 0.27 vs 0.22 ms
 #endif
 
 template <int S> struct FzsFL {          // per-warp shared memory of the front kernel

@@ -1050,12 +1050,21 @@ k_tp_scan(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, co
     int c = 0;                                             // count at the last symbol processed so far
     {
         int acc = 0;                                       // per-lane partial sums, one warp reduction at the end
-        for (int base = klo + 1; base < khi; base += 128) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int m = base + lane + 32 * q;
-                if (m < khi) acc += classic_dn(__ldg(thg + m), __ldg(thg + m - 1));
-            }
+        // head up to the first 16-byte aligned angle, then 4 angles per lane and load (the scratch rows are shifted so that
+        // packets start aligned, pskd_api.cu), then the tail
+        int m0 = klo + 1;
+        const int a0 = min(khi, (int)(m0 + ((4 - ((reinterpret_cast<uintptr_t>(thg + m0) >> 2) & 3)) & 3)));
+        if (m0 + lane < a0) acc += classic_dn(__ldg(thg + m0 + lane), __ldg(thg + m0 + lane - 1));
+        m0 = a0;
+        const int n4 = (khi - m0) >> 2;                    // whole float4 groups
+        for (int g = lane; g < n4; g += 32) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(thg + m0) + g);
+            const float pv = __ldg(thg + m0 + 4 * g - 1);
+            acc += classic_dn(t.x, pv) + classic_dn(t.y, t.x) + classic_dn(t.z, t.y) + classic_dn(t.w, t.z);
+        }
+        for (int base = m0 + 4 * n4; base < khi; base += 32) {
+            const int m = base + lane;
+            if (m < khi) acc += classic_dn(__ldg(thg + m), __ldg(thg + m - 1));
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1136,14 +1145,19 @@ k_tp_resolve(const ChanDesc* __restrict__ desc, const float* __restrict__ theta,
         }
         int myA = 0, myW = 0;
         const int cnt = min(32, np - base);
-        for (int l = 0; l < cnt; l++) {                       // uniform loop: every lane follows the same recurrence
+        // uniform loop: every lane follows the same recurrence.  Only the level Ad is carried from step to step; the
+        // shuffles do not depend on it, so unrolling lets them run ahead of the dependent DFMA -> F2F -> compare chain
+#pragma unroll 8
+        for (int l = 0; l < 32; l++) {
             const int s_l = __shfl_sync(0xffffffffu, step, l), h_l = __shfl_sync(0xffffffffu, has, l);
             const double e_l = __shfl_sync(0xffffffffu, er, l);
-            const float est_end = (float)fma(PSKD_M_2PI, Ad, e_l);
-            int w = 0;
-            if (h_l && fabsf(est_end) >= wrapThr) w = (int)rintf(est_end * rWrap);
-            if (l == lane) { myA = (int)Ad; myW = w; }
-            Ad += (double)(s_l - M * w);
+            if (l < cnt) {
+                const float est_end = (float)fma(PSKD_M_2PI, Ad, e_l);
+                int w = 0;
+                if (h_l && fabsf(est_end) >= wrapThr) w = (int)rintf(est_end * rWrap);
+                if (l == lane) { myA = (int)Ad; myW = w; }
+                Ad += (double)(s_l - M * w);
+            }
         }
         if (j < np) { pkts[tc.first_slot + j].A = myA; pkts[tc.first_slot + j].w = myW; }
     }
