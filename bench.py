@@ -156,11 +156,20 @@ def measured_peak():
 
 
 def config_of(args, w, world, scaling, nch_global):
-    """the `config` object of the JSON line -- the same keys for both arms"""
+    """the `config` object of the JSON line -- the same keys AND values for both arms (ours and --impl reference)"""
+    mixed = bool(w.get("mixed"))
+    per_gpu = nch_global if (scaling != "strong" or world == 1) else -(-nch_global // world)
+    if scaling == "strong" or world == 1:
+        par = (f"ONE bank of {nch_global} channels partitioned over {world} GPU(s) in contiguous"
+               f"{' cost-balanced' if mixed else ''} channel ranges, no collective")
+    else:
+        par = f"{world} independent banks of {nch_global} channels, one per GPU, no collective"
     return {"workload": args.workload, "description": w["desc"], "channels": nch_global, "samples_per_channel": w["samples"],
             "samplesPerBaud": w.get("S", "8/9/10"), "constelationSize": w.get("M", "2/4/8"), "numAvg": w.get("A", "50/100/200"),
             "phaseAvg": w.get("P", "25/50/100"), "differentialDecoding": w.get("D", "0/1"), "packet_len": PACKET_LEN,
-            "xdelta": XDELTA, "n_gpus": world, "scaling": scaling}
+            "xdelta": XDELTA, "n_gpus": world, "scaling": scaling, "channels_per_gpu": per_gpu, "parallelism": par,
+            "l2": f"inputs (~{per_gpu * w['samples'] * 8 / 1e9:.1f} GB per GPU) far larger than the 126 MB L2; no flush needed",
+            "input": "replayed resident buffer; carrier offsets quantised so that the replay is a continuous stream"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -242,7 +251,9 @@ def run_reference(args, w):
         t_tot += dt
     ms = 1e3 * t_tot / args.steps
     val = ch * n / (ms * 1e-3) / 1e6
-    scaling = "strong" if nch_global > 1 else "replicas"
+    scaling = args.scaling
+    if scaling == "auto":
+        scaling = "strong" if nch_global >= world and nch_global > 1 else "weak"
     sample = (f"{ch} channels (every {max(1, nch_global // ch)}th of the bank) x {n} samples per step "
               f"({'oracle/_ref = unmodified psk_soft.cpp' if kind == 'reference' else 'oracle C port'}), one component per channel, "
               "input synthesised on the host")
@@ -380,8 +391,6 @@ def main():
     ms_total = timed(args.steps)
     t_wall1 = time.time()
     launches = (bank.launch_count - launches0) if bank else 0
-    time.sleep(0.15)
-    sampler.stop()
     ms_step = ms_total / args.steps
     total_samples = (nch_global if (scaling == "strong" or world == 1) else world * nch_global) * n
     value = total_samples / (ms_step * 1e-3) / 1e6
@@ -397,6 +406,9 @@ def main():
         timed(psteps)
         kern = bank.profile_read(reset=True)
         bank.profile_enable(False)
+    t_wall2 = time.time()                                       # the clock samples cover both passes (the same steps, back to back)
+    time.sleep(0.15)
+    sampler.stop()
     stats = bank.stats() if bank else {}
     if kern:
         dom = max(kern, key=lambda k: kern[k][0])
@@ -500,19 +512,13 @@ def main():
                "single_core_value": rate1}
 
     if rank == 0:
-        clocks = sampler.summary(t_wall0, t_wall1)
+        clocks = sampler.summary(t_wall0, t_wall2)
         cfg = config_of(args, w, world, scaling, nch_global)
-        cfg.update({"channels_this_rank": nch,
-                    "l2": f"inputs ({nch * n * 8 / 1e9:.1f} GB on this GPU) far larger than the 126 MB L2; no flush needed",
-                    "parallelism": (f"ONE bank of {nch_global} channels partitioned over {world} GPU(s) in contiguous"
-                                    f"{' cost-balanced' if w.get('mixed') else ''} channel ranges, no collective" if scaling == "strong" or world == 1
-                                    else f"{world} independent banks of {nch_global} channels, one per GPU, no collective"),
-                    "input": "replayed resident buffer; carrier offsets quantised so that the replay is a continuous stream",
-                    "host_affinity": numa})
         line = {"metric": "Msamples/s demodulated", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "f32/f64", "data": "synthetic", "config": cfg,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "run": {"channels_rank0": nch, "host_affinity": numa},
                 "chain": {k: stats.get(k) for k in ("spec_chunks", "spec_misses", "seq_channels", "wraps", "tp_packets")}}
         print(json.dumps(line), flush=True)
     if world > 1:

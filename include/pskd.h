@@ -88,6 +88,9 @@ typedef struct pskd_output {
     size_t   bits_stride;   /* shorts between consecutive channels in bits */
     size_t*  n_symbols;     /* [n_channels] HOST array, filled by the call (may be NULL) */
     size_t*  n_bits;        /* [n_channels] HOST array, filled by the call (may be NULL) */
+    uint8_t* hard;          /* ADDITIONAL output, not a port of the reference: the decided symbol as one byte per symbol, its
+                               bitsPerBaud bits packed LSB first (bit j = bits[k*bitsPerBaud + j]); row stride sym_stride;
+                               NULL skips it.  Never replaces `bits`. */
 } pskd_output;
 
 /* ---- out-port stream metadata the component pushes beside the data (cpp/psk_soft.cpp:393-405):

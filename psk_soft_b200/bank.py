@@ -130,7 +130,7 @@ class Bank:
 
     # -- the hot path ----------------------------------------------------------------------
     def process_raw(self, iq_ptr, iq_stride, n_complex, soft_ptr, bits_ptr, phase_ptr, sidx_ptr, sym_stride,
-                    bits_stride, xdelta=0.01, packet_len=64000, flags=0, sri_mode=1, counts=True):
+                    bits_stride, xdelta=0.01, packet_len=64000, flags=0, sri_mode=1, counts=True, hard_ptr=None):
         """Direct call of pskd_process with raw pointers (device pointers unless FLAG_HOST_BUFFERS)."""
         inp = B.Input()
         inp.iq = iq_ptr
@@ -148,6 +148,7 @@ class Bank:
         inp.flags = int(flags)
         out = B.Output()
         out.soft, out.bits, out.phase, out.sample_index = soft_ptr, bits_ptr, phase_ptr, sidx_ptr
+        out.hard = hard_ptr
         out.sym_stride, out.bits_stride = int(sym_stride), int(bits_stride)
         if counts:
             self._nsym = (C.c_size_t * self.n_channels)()
@@ -175,14 +176,16 @@ class Bank:
         phase = np.zeros((self.n_channels, cap), np.float32)
         sidx = np.zeros((self.n_channels, cap), np.int16)
         bits = np.zeros((self.n_channels, 3 * cap), np.int16)
+        hard = np.zeros((self.n_channels, cap), np.uint8)      # the additional packed hard-symbol output
         flags = B.FLAG_HOST_BUFFERS | (B.FLAG_QUEUE_FLUSHED if flushed else 0)
         rc, ns, nb = self.process_raw(a.ctypes.data if a.size else None, n, ncx, soft.ctypes.data, bits.ctypes.data,
-                                      phase.ctypes.data, sidx.ctypes.data, cap, 3 * cap, xdelta, packet_len, flags, sri_mode)
+                                      phase.ctypes.data, sidx.ctypes.data, cap, 3 * cap, xdelta, packet_len, flags, sri_mode,
+                                      hard_ptr=hard.ctypes.data)
         res = []
         for c in range(self.n_channels):
             k, b = int(ns[c]), int(nb[c])
             res.append(dict(soft=soft[c, :k].copy(), bits=bits[c, :b].copy(), phase=phase[c, :k].copy(),
-                            sidx=sidx[c, :k].copy(), rc=rc))
+                            sidx=sidx[c, :k].copy(), hard=hard[c, :k].copy(), rc=rc))
         return res
 
 

@@ -37,7 +37,7 @@ class Input(C.Structure):
 class Output(C.Structure):
     _fields_ = [("soft", C.c_void_p), ("bits", C.c_void_p), ("phase", C.c_void_p), ("sample_index", C.c_void_p),
                 ("sym_stride", C.c_size_t), ("bits_stride", C.c_size_t),
-                ("n_symbols", C.POINTER(C.c_size_t)), ("n_bits", C.POINTER(C.c_size_t))]
+                ("n_symbols", C.POINTER(C.c_size_t)), ("n_bits", C.POINTER(C.c_size_t)), ("hard", C.c_void_p)]
 
 
 class SriOut(C.Structure):

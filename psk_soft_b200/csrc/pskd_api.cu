@@ -92,7 +92,7 @@ struct pskd_bank {
     float2* d_tail[2] = {nullptr, nullptr}; long long tail_total = 0; int tail_cur = 0;
     DevBuf<float2> sel; DevBuf<float> theta; DevBuf<float> phase_tmp; DevBuf<int16_t> sidx_tmp;
     // host-buffer staging
-    DevBuf<float> st_in; DevBuf<float> st_soft; DevBuf<float> st_phase; DevBuf<int16_t> st_bits; DevBuf<int16_t> st_sidx;
+    DevBuf<float> st_in; DevBuf<float> st_soft; DevBuf<float> st_phase; DevBuf<int16_t> st_bits; DevBuf<int16_t> st_sidx; DevBuf<uint8_t> st_hard;
     unsigned long long launches = 0;
     pskd_stats stats{};
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host-buffer mode: H2D / D2H overlap the kernels slab by slab
@@ -301,7 +301,7 @@ int pskd_destroy(pskd_handle b) {
     cudaFree(b->d_state); cudaFree(b->d_counters); cudaFree(b->d_ring);
     cudaFree(b->d_tail[0]); cudaFree(b->d_tail[1]);
     b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
-    b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release();
+    b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release(); b->st_hard.release();
     b->tp_items.release(); b->tp_chans.release(); b->tp_pkts.release(); b->tp_ends.release();
     b->tp_end_ring.release(); b->tp_start_ring.release(); b->tp_fail.release(); b->tp_slot_flags.release();
     b->prof.destroy();
@@ -645,7 +645,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         fusable[i] = fast && b->fused_mode != 0 && fused_supports(S, A, P) && K < (1LL << 30);
         fzsable[i] = fast && b->fzs_mode != 0 && fzs_supports(S, A, P) && K < (1LL << 30);
         if (d.bpb == 0) any_nobits = true;
-        if ((size_t)K > out->sym_stride && (out->soft || out->phase || out->sample_index))
+        if ((size_t)K > out->sym_stride && (out->soft || out->phase || out->sample_index || out->hard))
             return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld symbols > sym_stride %zu", i, K, out->sym_stride);
         if (out->bits && (size_t)(K * d.bpb) > out->bits_stride)
             return fail(PSKD_ERR_CAPACITY, "channel %d emits %lld bits > bits_stride %zu", i, K * d.bpb, out->bits_stride);
@@ -789,19 +789,21 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     CUDA_TRY(b->sel.reserve((size_t)scr_total + 4));
     CUDA_TRY(b->theta.reserve((size_t)scr_total + 4));
     float* dev_soft = out->soft; float* dev_phase = out->phase; int16_t* dev_bits = out->bits; int16_t* dev_sidx = out->sample_index;
+    uint8_t* dev_hard = out->hard;
     size_t slot_in = 0, slot_sym = 0, slot_bits = 0;          // elements per ring slot
     if (host_bufs) {
         slot_in = 2 * in_stride * slab_ch_max; slot_sym = sym_stride * slab_ch_max; slot_bits = bits_stride * slab_ch_max;
         // growing a staging buffer frees the old one: let every slab in flight (an earlier NO_SYNC call) drain first
         const bool grow = RING * slot_in + 4 > b->st_in.cap || (out->soft && RING * 2 * slot_sym + 4 > b->st_soft.cap) ||
                           (out->phase && RING * slot_sym + 4 > b->st_phase.cap) || (out->bits && RING * slot_bits + 4 > b->st_bits.cap) ||
-                          (out->sample_index && RING * slot_sym + 4 > b->st_sidx.cap);
+                          (out->sample_index && RING * slot_sym + 4 > b->st_sidx.cap) || (out->hard && RING * slot_sym + 4 > b->st_hard.cap);
         if (grow) { CUDA_TRY(cudaStreamSynchronize(b->copy_in)); CUDA_TRY(cudaStreamSynchronize(b->stream)); CUDA_TRY(cudaStreamSynchronize(b->copy_out)); }
         CUDA_TRY(b->st_in.reserve(RING * slot_in + 4));
         if (out->soft) CUDA_TRY(b->st_soft.reserve(RING * 2 * slot_sym + 4));
         if (out->phase) CUDA_TRY(b->st_phase.reserve(RING * slot_sym + 4));
         if (out->bits) CUDA_TRY(b->st_bits.reserve(RING * slot_bits + 4));
         if (out->sample_index) CUDA_TRY(b->st_sidx.reserve(RING * slot_sym + 4));
+        if (out->hard) CUDA_TRY(b->st_hard.reserve(RING * slot_sym + 4));
     }
     const size_t ostride_all = host_bufs ? slot_sym : sym_stride * (size_t)nch;     // elements of a whole-call temporary
     if (!out->phase && any_staged) { CUDA_TRY(b->phase_tmp.reserve(ostride_all + 4)); }
@@ -852,7 +854,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         Ls.Pmax_fast = si.Pmax_fast; Ls.n_fast_channels = si.n_fast; Ls.n_seq_channels = si.n_seq;
         Ls.d_desc = b->d_desc + lo; Ls.h_desc = b->h_desc + lo; Ls.d_state = b->d_state + lo; Ls.d_ring = b->d_ring;
         Ls.d_sel = b->sel.p; Ls.d_theta = b->theta.p; Ls.d_phase_tmp = b->phase_tmp.p;
-        Ls.out_soft = dev_soft; Ls.out_bits = dev_bits; Ls.out_phase = dev_phase; Ls.out_sidx = dev_sidx;
+        Ls.out_soft = dev_soft; Ls.out_bits = dev_bits; Ls.out_phase = dev_phase; Ls.out_sidx = dev_sidx; Ls.out_hard = dev_hard;
         Ls.sri_xdelta = in->sri_xdelta; Ls.d_counters = b->d_counters; Ls.launches = &b->launches; Ls.prof = &b->prof;
         if (si.n_chan > 0) {
             Ls.tp_head_items = b->tp_items.p + si.head0; Ls.tp_n_head = si.n_head;
@@ -940,6 +942,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             dev_phase = out->phase ? b->st_phase.p + (size_t)r * slot_sym : nullptr;
             dev_bits = out->bits ? b->st_bits.p + (size_t)r * slot_bits : nullptr;
             dev_sidx = out->sample_index ? b->st_sidx.p + (size_t)r * slot_sym : b->sidx_tmp.p;
+            dev_hard = out->hard ? b->st_hard.p + (size_t)r * slot_sym : nullptr;
             rc = run_slab(s, lo, hi);
             if (rc != PSKD_OK) return rc;
             CUDA_TRY(cudaEventRecord(b->ev_kern[r], b->stream));
@@ -948,6 +951,7 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
                 if (out->soft) CUDA_TRY(cudaMemcpy2DAsync(out->soft + 2 * out->sym_stride * lo, out->sym_stride * 8, dev_soft, sym_stride * 8, (size_t)Kmax * 8, rows, cudaMemcpyDeviceToHost, b->copy_out));
                 if (out->phase) CUDA_TRY(cudaMemcpy2DAsync(out->phase + out->sym_stride * lo, out->sym_stride * 4, dev_phase, sym_stride * 4, (size_t)Kmax * 4, rows, cudaMemcpyDeviceToHost, b->copy_out));
                 if (out->sample_index) CUDA_TRY(cudaMemcpy2DAsync(out->sample_index + out->sym_stride * lo, out->sym_stride * 2, dev_sidx, sym_stride * 2, (size_t)Kmax * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));
+                if (out->hard) CUDA_TRY(cudaMemcpy2DAsync(out->hard + out->sym_stride * lo, out->sym_stride, dev_hard, sym_stride, (size_t)Kmax, rows, cudaMemcpyDeviceToHost, b->copy_out));
                 if (out->bits) {
                     size_t w = std::min((size_t)Kmax * 3, out->bits_stride);
                     CUDA_TRY(cudaMemcpy2DAsync(out->bits + out->bits_stride * lo, out->bits_stride * 2, dev_bits, bits_stride * 2, w * 2, rows, cudaMemcpyDeviceToHost, b->copy_out));

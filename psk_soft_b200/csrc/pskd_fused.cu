@@ -81,6 +81,7 @@ struct FzCtx {                         // one per warp, shared memory
     const ChanDesc* desc;
     float2* o_soft; float* o_phase; int16_t* o_bits;       // this channel's output rows (or null)
     int16_t* o_sidx;
+    uint8_t* o_hard;                   // optional packed hard symbols
     double sri_xdelta;
     long long tail_len, pkt_len, V;
     unsigned long long wraps0;
@@ -112,6 +113,11 @@ template <int S> struct FzCfg {
     // physical position of logical sample n (= row*S + phase) inside a staged block.  S = 8: rows
     // 8..15 and 24..31 swap places in pairs, which puts the four row groups of one 64-bit read
     // (lane = (phase, group), same row of every group) on disjoint banks.
+    // Measured and rejected (r02): additionally permuting the four 16-byte pieces of a row by bits 1-2 of the row (the
+    // 128-byte XOR swizzle) turns the 16-way bank conflict of the gather of the timing-selected sample (lane = row, 13 of
+    // the kernel's 185 shared-memory wavefronts per chunk) into a 4-way one -- but cp.async's shared-memory writes only
+    // coalesce for contiguous runs: the eight LDGSTS of a chunk went from 53 to 99 wavefronts and the kernel from 12.5 to
+    // 13.6 ms (the shared-memory data pipe is this kernel's busiest unit: 80 % of peak).
     __host__ __device__ static constexpr int phys(int n) { return S == 8 ? (n ^ (((n >> 6) & 1) << 3)) : n; }
 };
 
@@ -143,7 +149,7 @@ struct FusedParams {
     int parts_per_pkt;                 // > 1: a unit is one of these parts of ONE packet (pkts_per_unit == 1)
     int* ticket;                       // unit ticket counter (zeroed before the launch)
     int* done;                         // [n_channels] units completed per channel (zeroed before the launch)
-    float2* out_soft; int16_t* out_bits; float* out_phase; int16_t* out_sidx;
+    float2* out_soft; int16_t* out_bits; float* out_phase; int16_t* out_sidx; uint8_t* out_hard;
     double sri_xdelta;
     DevCounters* counters;
 };
@@ -365,7 +371,7 @@ __device__ __forceinline__ float2 fz_cdiv_fast(float2 n, float2 dn, bool& bad) {
 // the literal path of one symbol: libgcc-style division, library sincosf, checked complex
 // multiply, atan2f slicer -- for the symbols whose fast evaluation raised a flag
 static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float est, int M, int bpb, int diff,
-                                                    float2* c_stage, short* b_stage) {
+                                                    float2* c_stage, short* b_stage, unsigned char* h_stage) {
     float2 x = s;
     if (diff) x = cdiv_f32(s, prev);
     const float pc = phase_correction(est, M, diff != 0);
@@ -373,6 +379,7 @@ static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float
     *c_stage = c;
     const unsigned b = slice_bits(c, bpb);
     for (int j = 0; j < bpb; j++) b_stage[j] = (short)((b >> j) & 1u);
+    *h_stage = (unsigned char)b;
 }
 
 // derotate / differential decode / slice (cpp/psk_soft.cpp:484-566), specialised on bits per symbol and on
@@ -384,8 +391,9 @@ static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float
 // The buffers are addressed from the warp's shared-memory offset (not through generic pointer parameters: those cost
 // ~15 instructions per 32 symbols of address conversion and turn every access into a generic LD / ST).
 template <class L, int BPB, bool DIFF>
-static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const int lane, const int M, const int m) {
+static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const int lane, const int M, const int m, const bool hard) {
     unsigned char* wb = fz_smem + wofs;
+    unsigned char* __restrict__ hst = wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6;                     // packed hard symbols [FZ_B]
     const float*  __restrict__ th     = reinterpret_cast<const float*>(wb + L::OFF_TH);
     const float2* __restrict__ selb   = reinterpret_cast<const float2*>(wb + L::OFF_SEL);
     float2*       __restrict__ cst    = reinterpret_cast<float2*>(wb + L::OFF_ALIAS);              // soft staging [FZ_B]
@@ -414,14 +422,18 @@ static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const in
         if (BPB == 3) {
             const unsigned b = fz_slice8_flag(c, bad);
             bstage[3 * i] = (short)(b & 1u); bstage[3 * i + 1] = (short)((b >> 1) & 1u); bstage[3 * i + 2] = (short)(b >> 2);   // :559-563
+            if (hard) hst[i] = (unsigned char)b;
         } else if (BPB == 1) {
             bstage[i] = (x < 0.0f) ? 1 : 0;                                                       // :512
+            if (hard) hst[i] = (x < 0.0f) ? 1 : 0;
         } else if (BPB == 2) {                                                                    // :523-526 (float -> bool, sic)
-            reinterpret_cast<unsigned*>(bstage)[i] = ((x != 0.0f) != (y != 0.0f) ? 1u : 0u) | ((y != 0.0f) ? 0u : 0x10000u);
+            const unsigned b0 = ((x != 0.0f) != (y != 0.0f)) ? 1u : 0u, b1 = (y != 0.0f) ? 0u : 1u;
+            reinterpret_cast<unsigned*>(bstage)[i] = b0 | (b1 << 16);
+            if (hard) hst[i] = (unsigned char)(b0 | (b1 << 1));
         }
         bad = bad && i < m;
         if (__any_sync(0xffffffffu, bad)) {             // rare: literal evaluation of the flagged symbols
-            if (bad) fz_back_literal(selb[2 + i], selb[1 + i], th[i], M, BPB, DIFF ? 1 : 0, &cst[i], &bstage[i * BPB]);
+            if (bad) fz_back_literal(selb[2 + i], selb[1 + i], th[i], M, BPB, DIFF ? 1 : 0, &cst[i], &bstage[i * BPB], &hst[i]);
         }
     }
 }
@@ -616,15 +628,17 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
     const int lane = fz_lane();
     const int M = cx.M, bpb = cx.bpb, kchain = cx.kchain;
     const bool diff = cx.diff != 0;
+    uint8_t* o_hard = cx.o_hard;
+    const bool hard = o_hard != nullptr && bpb > 0;
     switch (bpb * 2 + (diff ? 1 : 0)) {
-        case 6: fz_back_rolled<L, 3, false>(wofs, lane, M, m); break;
-        case 7: fz_back_rolled<L, 3, true>(wofs, lane, M, m); break;
-        case 4: fz_back_rolled<L, 2, false>(wofs, lane, M, m); break;
-        case 5: fz_back_rolled<L, 2, true>(wofs, lane, M, m); break;
-        case 2: fz_back_rolled<L, 1, false>(wofs, lane, M, m); break;
-        case 3: fz_back_rolled<L, 1, true>(wofs, lane, M, m); break;
-        case 0: fz_back_rolled<L, 0, false>(wofs, lane, M, m); break;
-        default: fz_back_rolled<L, 0, true>(wofs, lane, M, m); break;
+        case 6: fz_back_rolled<L, 3, false>(wofs, lane, M, m, hard); break;
+        case 7: fz_back_rolled<L, 3, true>(wofs, lane, M, m, hard); break;
+        case 4: fz_back_rolled<L, 2, false>(wofs, lane, M, m, hard); break;
+        case 5: fz_back_rolled<L, 2, true>(wofs, lane, M, m, hard); break;
+        case 2: fz_back_rolled<L, 1, false>(wofs, lane, M, m, hard); break;
+        case 3: fz_back_rolled<L, 1, true>(wofs, lane, M, m, hard); break;
+        case 0: fz_back_rolled<L, 0, false>(wofs, lane, M, m, hard); break;
+        default: fz_back_rolled<L, 0, true>(wofs, lane, M, m, hard); break;
     }
     int16_t* o_bits = cx.o_bits;
     __syncwarp();
@@ -676,6 +690,12 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
             } else {
                 for (int t = lane; t < nsh; t += 32) o[t] = bstage[t];
             }
+        }
+        if (hard) {                                       // packed hard symbols, one byte each
+            const unsigned char* hst = wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6;
+            uint8_t* o = o_hard + kchain;
+            if (full && (reinterpret_cast<uintptr_t>(o) & 3) == 0) reinterpret_cast<unsigned*>(o)[lane] = reinterpret_cast<const unsigned*>(hst)[lane];
+            else for (int t = lane; t < m; t += 32) o[t] = hst[t];
         }
     }
     __syncwarp();
@@ -861,7 +881,7 @@ __device__ __forceinline__ void fz_issue(float2* st, const float2* src, int lane
         for (int q = 0; q < C::NQ16; q++) {
             const int f = lane + 32 * q;
             if ((S * 16) % 32 == 0 || f < S * 16) {
-                const int fp = (S == 8) ? ((lane ^ ((q & 1) << 2)) + 32 * q) : f;      // phys() on 16-byte pieces
+                const int fp = C::phys(2 * f) >> 1;                                    // phys() on 16-byte pieces (keeps pairs together)
                 fz_cp_async16(d4 + fp, g4 + 32 * q);
             }
         }
@@ -869,8 +889,7 @@ __device__ __forceinline__ void fz_issue(float2* st, const float2* src, int lane
 #pragma unroll
         for (int q = 0; q < S; q++) {
             const int n = lane + 32 * q;
-            const int np = (S == 8) ? ((lane ^ (((q >> 1) & 1) << 3)) + 32 * q) : n;
-            fz_cp_async8(st + np, src + n);
+            fz_cp_async8(st + C::phys(n), src + n);
         }
     }
 }
@@ -989,6 +1008,7 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
         cx.o_phase = prm.out_phase ? prm.out_phase + sym_off : nullptr;
         cx.o_bits = prm.out_bits ? prm.out_bits + dgp->bits_off : nullptr;
         cx.o_sidx = prm.out_sidx ? prm.out_sidx + sym_off : nullptr;
+        cx.o_hard = prm.out_hard ? prm.out_hard + sym_off : nullptr;
         cx.sri_xdelta = prm.sri_xdelta;
         cx.tail_len = tail_len; cx.pkt_len = pkt_len;
         cx.n_pkts = n_pkts; cx.pk1 = pk1; cx.K = K; cx.A = A; cx.M = dgp->M; cx.P = P; cx.bpb = dgp->bpb; cx.diff = dgp->D;
@@ -1106,10 +1126,13 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
     int16_t* o_sidx = cx.o_sidx;
     double Cw = cwp[wp];
     // lane = (phase, group): where this lane's rows sit in a staged block (even / odd rows, see phys())
-    const int od = (S == 8) ? (wg & 1) : 0;
-    const int ofs_e = (R * wg + od) * S + wp, ofs_o = (R * wg - od) * S + wp;
+    // FzCfg<S>::phys() of (row R*wg + i, phase wp) for the unrolled i: pos[i >> 1][i & 1] (loop-invariant, lane-dependent)
+    int pos[(R + 1) / 2][2];
+#pragma unroll
+    for (int i = 0; i < R; i++) pos[i >> 1][i & 1] = C::phys((R * wg + i) * S + wp);
     // lane = row: where this lane's row sits in the trail block
-    const int rowp = (S == 8) ? (lane ^ ((lane >> 3) & 1)) * S : lane * S;
+    const int rowp = C::phys(lane * S) & ~(S == 8 ? 7 : 0);                 // its row's base ...
+    const int gsw = (S == 8) ? (C::phys(lane * S) & 7) : 0;                 // ... and the permutation of its pieces (phase ^ gsw)
 
     do {
         const int krow = kA + FZ_CH * c;
@@ -1130,13 +1153,11 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
         double Eloc[R];
         double x = 0.0;
         {
-            const float2* le = Lst + ofs_e; const float2* lo = Lst + ofs_o;
-            const float2* te = Tst + ofs_e; const float2* to = Tst + ofs_o;
 #pragma unroll
             for (int i = 0; i < R; i++) {
                 if (G * R == 32 || R * wg + i < 32) {
-                    const float2 a = (i & 1) ? lo[i * S] : le[i * S];
-                    const float2 b = (i & 1) ? to[i * S] : te[i * S];
+                    const float2 a = Lst[pos[i >> 1][i & 1]];
+                    const float2 b = Tst[pos[i >> 1][i & 1]];
                     x = daddr(x, (double)fz_energy(a));                       // :448-451
                     Eloc[i] = x;
                     x = dsubr(x, (double)fz_energy(b));                       // :576
@@ -1190,7 +1211,7 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
             }
             const int idx = ix[0];
             if (o_sidx && lane < nrows) __stcs(o_sidx + krow + lane, (int16_t)idx);        // :466
-            gx = Tst[rowp + idx];
+            gx = Tst[rowp + (idx ^ gsw)];
         }
         __syncwarp();
         if (nfast) {
@@ -1331,9 +1352,12 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
     const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
     const bool m_ok = (M == 2 || M == 4 || M == 8);
     double Cw = cwp[wp];
-    const int od = (S == 8) ? (wg & 1) : 0;
-    const int ofs_e = (R * wg + od) * S + wp, ofs_o = (R * wg - od) * S + wp;
-    const int rowp = (S == 8) ? (lane ^ ((lane >> 3) & 1)) * S : lane * S;
+    // FzCfg<S>::phys() of (row R*wg + i, phase wp) for the unrolled i: pos[i >> 1][i & 1] (loop-invariant, lane-dependent)
+    int pos[(R + 1) / 2][2];
+#pragma unroll
+    for (int i = 0; i < R; i++) pos[i >> 1][i & 1] = C::phys((R * wg + i) * S + wp);
+    const int rowp = C::phys(lane * S) & ~(S == 8 ? 7 : 0);                 // its row's base ...
+    const int gsw = (S == 8) ? (C::phys(lane * S) & 7) : 0;                 // ... and the permutation of its pieces (phase ^ gsw)
 
 #pragma unroll 1
     for (int c = 0; c < nchunks; c++) {
@@ -1353,13 +1377,11 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
         double Eloc[R];
         double x = 0.0;
         {
-            const float2* le = Lst + ofs_e; const float2* lo = Lst + ofs_o;
-            const float2* te = Tst + ofs_e; const float2* to = Tst + ofs_o;
 #pragma unroll
             for (int i = 0; i < R; i++) {
                 if (G * R == 32 || R * wg + i < 32) {
-                    const float2 a = (i & 1) ? lo[i * S] : le[i * S];
-                    const float2 b = (i & 1) ? to[i * S] : te[i * S];
+                    const float2 a = Lst[pos[i >> 1][i & 1]];
+                    const float2 b = Tst[pos[i >> 1][i & 1]];
                     x = daddr(x, (double)fz_energy(a));                       // :448-451
                     Eloc[i] = x;
                     x = dsubr(x, (double)fz_energy(b));                       // :576
@@ -1410,7 +1432,7 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
             }
             const int idx = ix[0];
             if (lane < nrows) __stcs(o_sidx + krow + lane, (int16_t)idx);                  // :466
-            gx = Tst[rowp + idx];
+            gx = Tst[rowp + (idx ^ gsw)];
         }
         __syncwarp();
         if (nfast) {
@@ -1543,7 +1565,7 @@ template <int PC> struct FzsCbL {        // per-warp shared memory of the chain 
 struct FzsCbParams {
     const ChanDesc* desc; ChanState* state; float* ring_base; int n_channels;
     const float2* sel; const float* theta;
-    float2* out_soft; int16_t* out_bits; float* out_phase;
+    float2* out_soft; int16_t* out_bits; float* out_phase; uint8_t* out_hard;
     double sri_xdelta; DevCounters* counters;
     TpCtl tp;                          // items: one unit per item; else one unit per channel (all its packets, from state[ch])
     int n_units; int* ticket;
@@ -1639,6 +1661,7 @@ static __device__ __noinline__ bool fzs_cb_begin(const FzsCbParams& prm, const u
         cx.o_phase = prm.out_phase ? prm.out_phase + sym_off : nullptr;
         cx.o_bits = prm.out_bits ? prm.out_bits + dgp->bits_off : nullptr;
         cx.o_sidx = nullptr;
+        cx.o_hard = prm.out_hard ? prm.out_hard + sym_off : nullptr;
         cx.sri_xdelta = prm.sri_xdelta;
         cx.tail_len = tail_len; cx.pkt_len = pkt_len;
         cx.n_pkts = n_pkts; cx.pk1 = pk_b; cx.K = K; cx.A = A; cx.M = M; cx.P = P; cx.bpb = dgp->bpb; cx.diff = dgp->D;
@@ -1755,7 +1778,7 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     p.pkts_per_unit = f.pkts_per_unit; p.parts_per_pkt = f.parts_per_pkt;
     p.n_units = f.n_list * f.units_per_channel;
     p.ticket = f.d_ticket; p.done = f.d_done;
-    p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_sidx = c.out_sidx;
+    p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_sidx = c.out_sidx; p.out_hard = c.out_hard;
     p.sri_xdelta = c.sri_xdelta;
     p.counters = c.d_counters;
     static const size_t pad = getenv("PSKD_FZ_PAD_SMEM") ? (size_t)atoi(getenv("PSKD_FZ_PAD_SMEM")) : 0;   // tuning: lowers occupancy
@@ -1845,7 +1868,7 @@ static cudaError_t launch_fzs_cb_t(const LaunchCtx& c, const TpCtl& tp, int n_un
     FzsCbParams p{};
     p.desc = c.d_desc; p.state = c.d_state; p.ring_base = c.d_ring; p.n_channels = c.n_channels;
     p.sel = c.d_sel; p.theta = c.d_theta;
-    p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase;
+    p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_hard = c.out_hard;
     p.sri_xdelta = c.sri_xdelta; p.counters = c.d_counters;
     p.tp = tp;
     p.n_units = n_units;

@@ -198,6 +198,7 @@ struct LaunchCtx {
     float* d_theta;          // scratch: M-th power angle per symbol
     float* d_phase_tmp;      // scratch phase when the caller passes no phase buffer
     float* out_soft; int16_t* out_bits; float* out_phase; int16_t* out_sidx;
+    uint8_t* out_hard;       // optional packed hard symbols (one byte per symbol), or null
     double sri_xdelta;
     DevCounters* d_counters;
     unsigned long long* launches;   // host counter

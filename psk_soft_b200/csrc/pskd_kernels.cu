@@ -496,7 +496,7 @@ cudaError_t launch_chain_seq(const LaunchCtx& c) {
 __global__ void __launch_bounds__(256)
 k_back(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ state,
        const float2* __restrict__ sel, const float* __restrict__ phase,
-       float2* __restrict__ out_soft, int16_t* __restrict__ out_bits)
+       float2* __restrict__ out_soft, int16_t* __restrict__ out_bits, uint8_t* __restrict__ out_hard)
 {
     const ChanDesc& d = desc[blockIdx.y];
     if (d.flags & (CH_FAST | CH_FUSED)) return; // k_chain_par / k_fused derotate and slice their own channels
@@ -512,23 +512,26 @@ k_back(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ state,
     float pc = phase_correction(est, d.M, d.D != 0);
     float2 c = derotate(sample, pc);
     if (out_soft) out_soft[d.sym_off + k] = c;
-    if (out_bits && d.bpb) {
+    if ((out_bits || out_hard) && d.bpb) {
         unsigned b = slice_bits(c, d.bpb);
-        int16_t* o = out_bits + d.bits_off + k * d.bpb;
-        for (int j = 0; j < d.bpb; j++) o[j] = (int16_t)((b >> j) & 1u);
+        if (out_bits) {
+            int16_t* o = out_bits + d.bits_off + k * d.bpb;
+            for (int j = 0; j < d.bpb; j++) o[j] = (int16_t)((b >> j) & 1u);
+        }
+        if (out_hard) out_hard[d.sym_off + k] = (uint8_t)b;
     }
 }
 
 cudaError_t launch_back(const LaunchCtx& c) {
     if (c.Kmax <= 0) return cudaSuccess;
-    if (!c.out_soft && !c.out_bits) return cudaSuccess;
+    if (!c.out_soft && !c.out_bits && !c.out_hard) return cudaSuccess;
     if (c.n_seq_channels == 0) return cudaSuccess;
     dim3 grid((unsigned)((c.Kmax + 255) / 256), (unsigned)c.n_channels);
     const float* phase = c.out_phase ? c.out_phase : c.d_phase_tmp;
     double ab = 0.0;
     if (c.prof->enabled) for (int i = 0; i < c.n_channels; i++) { const ChanDesc& d = c.h_desc[i]; if (!(d.flags & (CH_FAST | CH_FUSED))) ab += alg_bytes_back(d); }
     c.prof->begin(KID_BACK, c.stream, ab);
-    k_back<<<grid, 256, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
+    k_back<<<grid, 256, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits, c.out_hard);
     c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
@@ -965,7 +968,7 @@ constexpr int BP_TILE = BP_THREADS * BP_V;
 __global__ void __launch_bounds__(BP_THREADS)
 k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ state,
            const float2* __restrict__ sel, const float* __restrict__ phase,
-           float2* __restrict__ out_soft, int16_t* __restrict__ out_bits)
+           float2* __restrict__ out_soft, int16_t* __restrict__ out_bits, uint8_t* __restrict__ out_hard)
 {
     const ChanDesc& d = desc[blockIdx.y];
     if (!(d.flags & CH_FAST) || (d.flags & (CH_FUSED | CH_FZS))) return;
@@ -1009,6 +1012,7 @@ k_back_par(const ChanDesc* __restrict__ desc, const ChanState* __restrict__ stat
             else if (bpb == 2) b = slice_bits(c, 2);
             short* o = sb + kl * bpb;
             for (int j = 0; j < bpb; j++) o[j] = (short)((b >> j) & 1u);
+            if (out_hard && bpb) out_hard[d.sym_off + k] = (uint8_t)b;
         }
     }
     if (!out_bits || !bpb) return;
@@ -1379,10 +1383,10 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
         e = chain_round(t3, c.n_channels, tp_legacy > 0, tp_fzs > 0);
         if (e != cudaSuccess) return e;
     }
-    if (n_legacy > 0 && (c.out_soft || c.out_bits) && c.Kmax > 0) {
+    if (n_legacy > 0 && (c.out_soft || c.out_bits || c.out_hard) && c.Kmax > 0) {
         dim3 grid((unsigned)((c.Kmax + BP_TILE - 1) / BP_TILE), (unsigned)c.n_channels);
         c.prof->begin(KID_BACK_PAR, c.stream, ab_back);
-        k_back_par<<<grid, BP_THREADS, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits);
+        k_back_par<<<grid, BP_THREADS, 0, c.stream>>>(c.d_desc, c.d_state, c.d_sel, phase, (float2*)c.out_soft, c.out_bits, c.out_hard);
         c.prof->end(c.stream);
         (*c.launches)++;
         e = cudaGetLastError();

@@ -51,6 +51,15 @@ def assert_parity(got, ref, differential=False, tag="", check_first_bits=True):
         bpb = len(rb) // len(ref["sidx"])
         gb, rb = gb[bpb:], rb[bpb:]
     assert np.array_equal(gb, rb), f"{tag}: bits differ at {np.nonzero(gb != rb)[0][:8]} of {len(rb)}"
+    if "hard" in got and len(ref["sidx"]) and len(ref["bits"]):
+        # the additional packed output: one byte per symbol = its bits, LSB first (checked against the REFERENCE's bits)
+        bpb = len(ref["bits"]) // len(ref["sidx"])
+        packed = (ref["bits"].reshape(-1, bpb).astype(np.uint8) << np.arange(bpb, dtype=np.uint8)).sum(axis=1).astype(np.uint8)
+        gh = got["hard"]
+        if "hard_mask" in got:
+            gh = np.where(got["hard_mask"], packed, gh)
+        s1 = 1 if (differential and not check_first_bits) else 0
+        assert np.array_equal(gh[s1:], packed[s1:]), f"{tag}: packed hard symbols differ at {np.nonzero(gh != packed)[0][:8]}"
     bad, rel = float_close(got["phase"], ref["phase"])
     assert not bad.any(), f"{tag}: phase differs at {np.nonzero(bad)[0][:8]} max rel {np.nanmax(rel):.3e}"
     s0 = 1 if differential else 0

@@ -40,7 +40,7 @@ def test_struct_layouts_match_header():
     from psk_soft_b200 import binding as B
     assert ctypes.sizeof(B.Props) == 16       # uint16, uint32, uint16, uint16, uint8, uint8 with natural alignment
     assert B.Props.numAvg.offset == 4 and B.Props.differentialDecoding.offset == 12
-    assert ctypes.sizeof(B.Input) == 64 and ctypes.sizeof(B.Output) == 64
+    assert ctypes.sizeof(B.Input) == 64 and ctypes.sizeof(B.Output) == 72
     assert ctypes.sizeof(B.KernelTime) == 56 and ctypes.sizeof(B.Synth) == 32
 
 

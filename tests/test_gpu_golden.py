@@ -262,3 +262,76 @@ def test_randomized_reconfiguration_scripts(seed, oracle_built):
         diff = bool(dev.differentialDecoding)
         assert_parity(got, ref, differential=False if np.isfinite(ref["soft"]).all() else diff,
                       tag=f"seed {seed} step {step} n {n} {ch} xdelta {xdelta} flushed {flushed}")
+
+
+def test_host_buffer_slab_ring_and_async_calls(oracle_built, monkeypatch):
+    """host-buffer calls cut into MANY slabs (PSKD_SLAB_MB=1: one or two channels per slab, more slabs than ring slots, each slab
+    with its own time-parallel plan), synchronous and pipelined (PSKD_FLAG_NO_SYNC + pskd_sync, two calls in flight with their
+    own output buffers) -- every channel of every call against the oracle"""
+    import psk_soft_b200 as pk
+    from psk_soft_b200 import binding as B
+    monkeypatch.setenv("PSKD_SLAB_MB", "1")
+    rs = np.random.RandomState(12)
+    nch, n = 20, 64000
+    props, iqs = [], []
+    for c in range(nch):
+        S = int(rs.choice([8, 10])); M = int(rs.choice([2, 4, 8])); D = int(rs.randint(0, 2))
+        props.append(dict(samplesPerBaud=S, constelationSize=M, numAvg=int(rs.choice([50, 100])), phaseAvg=int(rs.choice([25, 50])), differentialDecoding=D))
+        iqs.append(siggen.gen_shaped(2 * n, S, M, seed=300 + c, sigma=0.03, freq=float(rs.uniform(-2e-5, 2e-5)), timing_shift=c % S))
+    iqs = np.stack(iqs)
+    # (a) synchronous calls
+    bank = pk.Bank(nch, props)
+    orcs = [oracle_built.OracleComponent(**p) for p in props]
+    for a, b in ((0, n), (n, 2 * n)):
+        got = bank.process_host(iqs[:, a:b].copy(), xdelta=0.01, packet_len=4000)
+        for c in range(nch):
+            ref = orcs[c].demod(iqs[c, a:b], packet_len=4000, xdelta=0.01)
+            d = bool(props[c]["differentialDecoding"])
+            assert_parity(got[c], ref, differential=d if a == 0 else (False if np.isfinite(ref["soft"]).all() else d), tag=f"sync call {a}:{b} ch{c}")
+    if os.environ.get("PSKD_TP") == "1" and os.environ.get("PSKD_FUSED") == "0":
+        assert bank.stats()["tp_packets"] > 0             # every slab ran its own time-parallel plan
+    # (b) two pipelined calls, one sync at the end
+    bank2 = pk.Bank(nch, props)
+    cap = n // 8 + 16
+    outs = []
+    bufs = [np.ascontiguousarray(iqs[:, :n]), np.ascontiguousarray(iqs[:, n:])]
+    for j in range(2):
+        o = dict(soft=np.zeros((nch, cap), np.complex64), phase=np.zeros((nch, cap), np.float32), sidx=np.zeros((nch, cap), np.int16),
+                 bits=np.zeros((nch, 3 * cap), np.int16), hard=np.zeros((nch, cap), np.uint8))
+        rc, ns, nb = bank2.process_raw(bufs[j].ctypes.data, n, n, o["soft"].ctypes.data, o["bits"].ctypes.data, o["phase"].ctypes.data,
+                                       o["sidx"].ctypes.data, cap, 3 * cap, xdelta=0.01, packet_len=4000,
+                                       flags=B.FLAG_HOST_BUFFERS | B.FLAG_NO_SYNC, hard_ptr=o["hard"].ctypes.data)
+        assert rc == 0
+        o["ns"], o["nb"] = ns, nb
+        outs.append(o)
+    bank2.sync()
+    orcs = [oracle_built.OracleComponent(**p) for p in props]
+    for j, o in enumerate(outs):
+        for c in range(nch):
+            k, b = int(o["ns"][c]), int(o["nb"][c])
+            got = dict(soft=o["soft"][c, :k], phase=o["phase"][c, :k], sidx=o["sidx"][c, :k], bits=o["bits"][c, :b], hard=o["hard"][c, :k])
+            ref = orcs[c].demod(bufs[j][c], packet_len=4000, xdelta=0.01)
+            d = bool(props[c]["differentialDecoding"])
+            assert_parity(got, ref, differential=d if j == 0 else (False if np.isfinite(ref["soft"]).all() else d), tag=f"pipelined call {j} ch{c}")
+
+
+def test_bank_with_one_stalled_channel(oracle_built):
+    """a window shrink on ONE channel of a bank: that channel stalls (and recovers) while its neighbours keep emitting"""
+    import psk_soft_b200 as pk
+    props = [dict(samplesPerBaud=8, constelationSize=8, numAvg=100, phaseAvg=50) for _ in range(3)]
+    iqs = np.stack([siggen.gen_shaped(90000, 8, 8, seed=500 + c, sigma=0.03, freq=1e-5 * (c - 1), timing_shift=c) for c in range(3)])
+    bank = pk.Bank(3, props)
+    orcs = [oracle_built.OracleComponent(**p) for p in props]
+    script = [(0, 30000, {}), (30000, 30400, dict(numAvg=40)), (30400, 31000, {}), (31000, 60000, dict(numAvg=250)), (60000, 90000, {})]
+    for a, b, ch in script:
+        if ch:
+            bank.set_props(1, **ch)
+            orcs[1].configure(**ch)
+        got = bank.process_host(iqs[:, a:b].copy(), xdelta=0.01, packet_len=8000)
+        for c in range(3):
+            ref = orcs[c].demod(iqs[c, a:b], packet_len=8000, xdelta=0.01)
+            assert_parity(got[c], ref, tag=f"{a}:{b} ch{c} {ch}")
+            if c == 1 and a in (30000, 30400):
+                assert len(ref["sidx"]) == 0          # stalled
+            else:
+                assert len(ref["sidx"]) > 0

@@ -220,6 +220,7 @@ def test_randomized_configurations(seed, path, oracle_built, monkeypatch):
                     if bpb:
                         gb = g["bits"].copy().reshape(-1, bpb); gb[zero] = ref["bits"].reshape(-1, bpb)[zero]
                         g["bits"] = gb.reshape(-1)
+                        g["hard_mask"] = zero
             assert_parity(g, ref, differential=bool(props[c]["differentialDecoding"]),
                           tag=f"seed {seed} ch{c} {props[c]} pkt {pkt} call {a}:{b}")
     print(f"seed {seed} {path}: {masked_total[0]} zero-sample symbols masked")

@@ -43,9 +43,11 @@ def _bank_run(pk, torch, table, n, seed, packet_len, pn=0.0, sigma=0.02, freq_ma
         o = dict(soft=torch.zeros((nch, cap, 2), dtype=torch.float32, device="cuda"),
                  phase=torch.zeros((nch, cap), dtype=torch.float32, device="cuda"),
                  sidx=torch.zeros((nch, cap), dtype=torch.int16, device="cuda"),
-                 bits=torch.zeros((nch, cap * 3), dtype=torch.int16, device="cuda"))
+                 bits=torch.zeros((nch, cap * 3), dtype=torch.int16, device="cuda"),
+                 hard=torch.zeros((nch, cap), dtype=torch.uint8, device="cuda"))
         rc, ns, nb = bank.process_raw(iq.data_ptr(), n, n, o["soft"].data_ptr(), o["bits"].data_ptr(), o["phase"].data_ptr(),
-                                      o["sidx"].data_ptr(), cap, cap * 3, xdelta=0.01, packet_len=packet_len)
+                                      o["sidx"].data_ptr(), cap, cap * 3, xdelta=0.01, packet_len=packet_len,
+                                      hard_ptr=o["hard"].data_ptr())
         assert rc == 0
         o["ns"], o["nb"] = ns, nb
         outs.append(o)
@@ -56,7 +58,7 @@ def _bank_run(pk, torch, table, n, seed, packet_len, pn=0.0, sigma=0.02, freq_ma
 def _channel(o, c):
     k, b = int(o["ns"][c]), int(o["nb"][c])
     return dict(soft=o["soft"][c, :k].cpu().numpy().view(np.complex64).reshape(-1), phase=o["phase"][c, :k].cpu().numpy(),
-                sidx=o["sidx"][c, :k].cpu().numpy(), bits=o["bits"][c, :b].cpu().numpy())
+                sidx=o["sidx"][c, :k].cpu().numpy(), bits=o["bits"][c, :b].cpu().numpy(), hard=o["hard"][c, :k].cpu().numpy())
 
 
 def _check_sampled(oracle, iq, outs, table, rows, packet_len, tag):

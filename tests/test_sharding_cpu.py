@@ -60,3 +60,33 @@ def test_two_rank_gloo_sharding():
         assert p.exitcode == 0
     assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == 4099
     assert tmax == 13.0 and units == 4099.0
+
+
+def test_bench_bank_tables_and_partitions():
+    """bench.py's bank description and its strong-scaling partition (host logic only): the mixed bank of configs[4] is
+    sorted by (samplesPerBaud, constelationSize), its cost-balanced ranges tile it exactly once with near-equal cost, and
+    the algorithmic bytes follow SURVEY.md 8d."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w5, w0 = bench.WORKLOADS["config5"], bench.WORKLOADS["bank8psk"]
+    t5 = bench.channel_table(w5)
+    assert len(t5) == 8192
+    keys = [(p["samplesPerBaud"], p["constelationSize"]) for p in t5]
+    assert keys == sorted(keys) and {k[0] for k in keys} == {8, 9, 10} and {k[1] for k in keys} == {2, 4, 8}
+    assert {p["numAvg"] for p in t5} == {50, 100, 200} and {p["phaseAvg"] for p in t5} == {25, 50, 100}
+    assert t5 == bench.channel_table(w5)                      # seeded: every rank builds the same table
+    costs = [bench.channel_cost(p, w5["samples"]) for p in t5]
+    for world in (2, 4, 8):
+        r = balanced_ranges(costs, world)
+        assert r[0][0] == 0 and r[-1][1] == 8192 and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+        sums = [sum(costs[lo:hi]) for lo, hi in r]
+        assert max(sums) <= 1.02 * sum(costs) / world
+    t0 = bench.channel_table(w0)
+    assert len(t0) == 4096 and all(p == t0[0] for p in t0)
+    # 8 N + K (8 + 4 + 2 + 2 b) per channel, K = N / S in steady state
+    assert bench.algorithmic_bytes(t0[:1], 1_000_000) == 8_000_000 + 125_000 * (14 + 6)
+    assert bench.algorithmic_bytes(t0, 1_000_000) == 43_008_000_000
+    assert bench.sample_rows(4096, 512)[:3] == [0, 8, 16] and len(set(bench.sample_rows(8192, 512))) == 512
