@@ -519,7 +519,7 @@ def main():
                 "dtype": "f32/f64", "data": "synthetic", "config": cfg,
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "run": {"channels_rank0": nch, "host_affinity": numa},
-                "chain": {k: stats.get(k) for k in ("spec_chunks", "spec_misses", "seq_channels", "wraps", "tp_packets")}}
+                "chain": {k: stats.get(k) for k in ("spec_chunks", "spec_misses", "seq_channels", "wraps", "tp_packets", "tp_repaired")}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

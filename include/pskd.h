@@ -112,6 +112,8 @@ typedef struct pskd_stats {
     uint64_t spec_misses;        /* chunks whose speculation failed verification and were re-run exactly */
     uint64_t seq_channels;       /* channel-calls that took the sequential (non-speculative) chain */
     uint64_t tp_packets;         /* emulated packets whose phase chain ran time-parallel and whose hand-over was proven */
+    uint64_t tp_repaired;        /* channel-calls whose time-parallel plan needed the repair round (a hand-over was not proven:
+                                    the classic unwrap count differs from the reference's rule somewhere) */
 } pskd_stats;
 
 typedef struct pskd_bank* pskd_handle;

@@ -47,7 +47,7 @@ class SriOut(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("symbols_out", "samples_in", "packets", "wraps", "spec_chunks",
-                                          "spec_misses", "seq_channels", "tp_packets")]
+                                          "spec_misses", "seq_channels", "tp_packets", "tp_repaired")]
 
 
 class KernelTime(C.Structure):

@@ -399,7 +399,7 @@ int pskd_get_stats(pskd_handle b, pskd_stats* st) {
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     *st = b->stats;
     st->wraps = c.wraps; st->spec_chunks = c.spec_chunks; st->spec_misses = c.spec_misses; st->seq_channels = c.seq_channels;
-    st->tp_packets = c.tp_packets;
+    st->tp_packets = c.tp_packets; st->tp_repaired = c.tp_repaired;
     return PSKD_OK;
 }
 

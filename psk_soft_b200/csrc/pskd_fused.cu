@@ -103,6 +103,10 @@ struct FzCtx {                         // one per warp, shared memory
 };
 
 constexpr int fz_align16(int x) { return (x + 15) & ~15; }
+// A warp's region is a whole number of 128-byte lines: its staged blocks then start on a line, which cp.async's
+// shared-memory writes need to coalesce (a region of 9424 instead of 9472 bytes cost 53 -> 93 LDGSTS wavefronts per chunk
+// and 12.5 -> 13.7 ms per launch).
+constexpr int fz_align128(int x) { return (x + 127) & ~127; }
 
 template <int S> struct FzCfg {
     static constexpr int G = 32 / S;                         // row groups (lane = g*S + p)
@@ -113,11 +117,11 @@ template <int S> struct FzCfg {
     // physical position of logical sample n (= row*S + phase) inside a staged block.  S = 8: rows
     // 8..15 and 24..31 swap places in pairs, which puts the four row groups of one 64-bit read
     // (lane = (phase, group), same row of every group) on disjoint banks.
-    // Measured and rejected (r02): additionally permuting the four 16-byte pieces of a row by bits 1-2 of the row (the
-    // 128-byte XOR swizzle) turns the 16-way bank conflict of the gather of the timing-selected sample (lane = row, 13 of
-    // the kernel's 185 shared-memory wavefronts per chunk) into a 4-way one -- but cp.async's shared-memory writes only
-    // coalesce for contiguous runs: the eight LDGSTS of a chunk went from 53 to 99 wavefronts and the kernel from 12.5 to
-    // 13.6 ms (the shared-memory data pipe is this kernel's busiest unit: 80 % of peak).
+    // Measured and rejected (r02, profiles/r02_summary.md): additionally permuting the four 16-byte pieces of a row by bits
+    // 1-2 of the row (the 128-byte XOR swizzle) turns the 16-way bank conflict of the gather of the timing-selected sample
+    // (lane = row, 13 of the kernel's 185 shared-memory wavefronts per chunk) into a 4-way one: -6 % wavefronts, but the
+    // eight lane-dependent block positions it needs cost 20 more integer instructions per chunk at 96 registers: 13.1 vs
+    // 13.3 ms with them, against 12.5 ms for this layout with its two base pointers and immediate offsets.
     __host__ __device__ static constexpr int phys(int n) { return S == 8 ? (n ^ (((n >> 6) & 1) << 3)) : n; }
 };
 
@@ -138,7 +142,8 @@ template <int S, int PC> struct FzL {
     static constexpr int OFF_ALIAS = OFF_CZ + fz_align16((PC + 1) * 8);
     static constexpr int E_BYTES = 32 * C::ES * 8;                         // front stage: window sums [32][ES]
     static constexpr int C_BYTES = FZ_B * 8 + FZ_B * 4 + (FZ_B + 4) * 4;   // chain stage: prefix block, y block, est block
-    static constexpr int BYTES = OFF_ALIAS + fz_align16(E_BYTES > C_BYTES ? E_BYTES : C_BYTES);
+    static constexpr int BYTES = fz_align128(OFF_ALIAS + fz_align16(E_BYTES > C_BYTES ? E_BYTES : C_BYTES));
+    static_assert(BYTES % 128 == 0 && OFF_T % 128 == 0, "staged blocks must start on a 128-byte line");
 };
 
 struct FusedParams {
@@ -154,7 +159,7 @@ struct FusedParams {
     DevCounters* counters;
 };
 
-extern __shared__ __align__(16) unsigned char fz_smem[];
+extern __shared__ __align__(128) unsigned char fz_smem[];
 
 __device__ __forceinline__ void fz_prefetch_line(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -169,7 +174,11 @@ __device__ __forceinline__ int fz_lane() {
 }
 __device__ __forceinline__ void fz_cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+#ifdef PSKD_FZ_CPASYNC_CA
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");     // through L1 (experiment: 14.1 vs 12.8 ms on the bench bank, off)
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
 }
 __device__ __forceinline__ void fz_cp_async8(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -370,8 +379,16 @@ __device__ __forceinline__ float2 fz_cdiv_fast(float2 n, float2 dn, bool& bad) {
 
 // the literal path of one symbol: libgcc-style division, library sincosf, checked complex
 // multiply, atan2f slicer -- for the symbols whose fast evaluation raised a flag
-static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float est, int M, int bpb, int diff,
-                                                    float2* c_stage, short* b_stage, unsigned char* h_stage) {
+template <class L>
+static __device__ __noinline__ void fz_back_literal(const unsigned wofs, const int i, int M, int bpb, int diff) {
+    unsigned char* wb = fz_smem + wofs;                  // (offsets, not pointers: see the note at fz_normalize_ring_w)
+    const float*  th   = reinterpret_cast<const float*>(wb + L::OFF_TH);
+    const float2* selb = reinterpret_cast<const float2*>(wb + L::OFF_SEL);
+    float2* c_stage = reinterpret_cast<float2*>(wb + L::OFF_ALIAS) + i;
+    short*  b_stage = reinterpret_cast<short*>(wb + L::OFF_ALIAS + FZ_B * 8) + i * bpb;
+    unsigned char* h_stage = wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6 + i;
+    const float2 s = selb[2 + i], prev = selb[1 + i];
+    const float est = th[i];
     float2 x = s;
     if (diff) x = cdiv_f32(s, prev);
     const float pc = phase_correction(est, M, diff != 0);
@@ -390,8 +407,9 @@ static __device__ __noinline__ void fz_back_literal(float2 s, float2 prev, float
 // warps of a scheduler): four trips through ~70 instructions beat one trip through ~250.
 // The buffers are addressed from the warp's shared-memory offset (not through generic pointer parameters: those cost
 // ~15 instructions per 32 symbols of address conversion and turn every access into a generic LD / ST).
-template <class L, int BPB, bool DIFF>
-static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const int lane, const int M, const int m, const bool hard) {
+template <class L, int BPB, bool DIFF, bool HARD>
+static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const int lane, const int M, const int m) {
+    constexpr bool hard = HARD;          // the additional packed output is compiled out of the loop nobody asked it of
     unsigned char* wb = fz_smem + wofs;
     unsigned char* __restrict__ hst = wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6;                     // packed hard symbols [FZ_B]
     const float*  __restrict__ th     = reinterpret_cast<const float*>(wb + L::OFF_TH);
@@ -433,7 +451,7 @@ static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const in
         }
         bad = bad && i < m;
         if (__any_sync(0xffffffffu, bad)) {             // rare: literal evaluation of the flagged symbols
-            if (bad) fz_back_literal(selb[2 + i], selb[1 + i], th[i], M, BPB, DIFF ? 1 : 0, &cst[i], &bstage[i * BPB], &hst[i]);
+            if (bad) fz_back_literal<L>(wofs, i, M, BPB, DIFF ? 1 : 0);
         }
     }
 }
@@ -630,15 +648,26 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
     const bool diff = cx.diff != 0;
     uint8_t* o_hard = cx.o_hard;
     const bool hard = o_hard != nullptr && bpb > 0;
-    switch (bpb * 2 + (diff ? 1 : 0)) {
-        case 6: fz_back_rolled<L, 3, false>(wofs, lane, M, m, hard); break;
-        case 7: fz_back_rolled<L, 3, true>(wofs, lane, M, m, hard); break;
-        case 4: fz_back_rolled<L, 2, false>(wofs, lane, M, m, hard); break;
-        case 5: fz_back_rolled<L, 2, true>(wofs, lane, M, m, hard); break;
-        case 2: fz_back_rolled<L, 1, false>(wofs, lane, M, m, hard); break;
-        case 3: fz_back_rolled<L, 1, true>(wofs, lane, M, m, hard); break;
-        case 0: fz_back_rolled<L, 0, false>(wofs, lane, M, m, hard); break;
-        default: fz_back_rolled<L, 0, true>(wofs, lane, M, m, hard); break;
+    if (!hard) {
+        switch (bpb * 2 + (diff ? 1 : 0)) {
+            case 6: fz_back_rolled<L, 3, false, false>(wofs, lane, M, m); break;
+            case 7: fz_back_rolled<L, 3, true, false>(wofs, lane, M, m); break;
+            case 4: fz_back_rolled<L, 2, false, false>(wofs, lane, M, m); break;
+            case 5: fz_back_rolled<L, 2, true, false>(wofs, lane, M, m); break;
+            case 2: fz_back_rolled<L, 1, false, false>(wofs, lane, M, m); break;
+            case 3: fz_back_rolled<L, 1, true, false>(wofs, lane, M, m); break;
+            case 0: fz_back_rolled<L, 0, false, false>(wofs, lane, M, m); break;
+            default: fz_back_rolled<L, 0, true, false>(wofs, lane, M, m); break;
+        }
+    } else {
+        switch (bpb * 2 + (diff ? 1 : 0)) {
+            case 6: fz_back_rolled<L, 3, false, true>(wofs, lane, M, m); break;
+            case 7: fz_back_rolled<L, 3, true, true>(wofs, lane, M, m); break;
+            case 4: fz_back_rolled<L, 2, false, true>(wofs, lane, M, m); break;
+            case 5: fz_back_rolled<L, 2, true, true>(wofs, lane, M, m); break;
+            case 2: fz_back_rolled<L, 1, false, true>(wofs, lane, M, m); break;
+            default: fz_back_rolled<L, 1, true, true>(wofs, lane, M, m); break;
+        }
     }
     int16_t* o_bits = cx.o_bits;
     __syncwarp();
@@ -875,14 +904,21 @@ template <int S, bool A16>
 __device__ __forceinline__ void fz_issue(float2* st, const float2* src, int lane) {
     using C = FzCfg<S>;
     if (A16) {
-        const float4* g4 = reinterpret_cast<const float4*>(src) + lane;
+        const float4* g4 = reinterpret_cast<const float4*>(src);
         float4* d4 = reinterpret_cast<float4*>(st);
 #pragma unroll
         for (int q = 0; q < C::NQ16; q++) {
             const int f = lane + 32 * q;
             if ((S * 16) % 32 == 0 || f < S * 16) {
                 const int fp = C::phys(2 * f) >> 1;                                    // phys() on 16-byte pieces (keeps pairs together)
-                fz_cp_async16(d4 + fp, g4 + 32 * q);
+#ifdef PSKD_FZ_ISSUE_SRC
+                // the permutation is applied on the SOURCE side (phys() is an involution): the lanes of one LDGSTS write
+                // consecutive 16-byte pieces, which is what its shared-memory writes coalesce on; the global side still
+                // touches the same sectors.  Experiment, off: 185 -> 180 shared-memory wavefronts per chunk, 12.81 vs 12.77 ms
+                fz_cp_async16(d4 + f, g4 + fp);
+#else
+                fz_cp_async16(d4 + fp, g4 + f);
+#endif
             }
         }
     } else {
@@ -1126,13 +1162,10 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
     int16_t* o_sidx = cx.o_sidx;
     double Cw = cwp[wp];
     // lane = (phase, group): where this lane's rows sit in a staged block (even / odd rows, see phys())
-    // FzCfg<S>::phys() of (row R*wg + i, phase wp) for the unrolled i: pos[i >> 1][i & 1] (loop-invariant, lane-dependent)
-    int pos[(R + 1) / 2][2];
-#pragma unroll
-    for (int i = 0; i < R; i++) pos[i >> 1][i & 1] = C::phys((R * wg + i) * S + wp);
+    const int od = (S == 8) ? (wg & 1) : 0;
+    const int ofs_e = (R * wg + od) * S + wp, ofs_o = (R * wg - od) * S + wp;
     // lane = row: where this lane's row sits in the trail block
-    const int rowp = C::phys(lane * S) & ~(S == 8 ? 7 : 0);                 // its row's base ...
-    const int gsw = (S == 8) ? (C::phys(lane * S) & 7) : 0;                 // ... and the permutation of its pieces (phase ^ gsw)
+    const int rowp = (S == 8) ? (lane ^ ((lane >> 3) & 1)) * S : lane * S;
 
     do {
         const int krow = kA + FZ_CH * c;
@@ -1153,11 +1186,13 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
         double Eloc[R];
         double x = 0.0;
         {
+            const float2* le = Lst + ofs_e; const float2* lo = Lst + ofs_o;
+            const float2* te = Tst + ofs_e; const float2* to = Tst + ofs_o;
 #pragma unroll
             for (int i = 0; i < R; i++) {
                 if (G * R == 32 || R * wg + i < 32) {
-                    const float2 a = Lst[pos[i >> 1][i & 1]];
-                    const float2 b = Tst[pos[i >> 1][i & 1]];
+                    const float2 a = (i & 1) ? lo[i * S] : le[i * S];
+                    const float2 b = (i & 1) ? to[i * S] : te[i * S];
                     x = daddr(x, (double)fz_energy(a));                       // :448-451
                     Eloc[i] = x;
                     x = dsubr(x, (double)fz_energy(b));                       // :576
@@ -1211,7 +1246,7 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
             }
             const int idx = ix[0];
             if (o_sidx && lane < nrows) __stcs(o_sidx + krow + lane, (int16_t)idx);        // :466
-            gx = Tst[rowp + (idx ^ gsw)];
+            gx = Tst[rowp + idx];
         }
         __syncwarp();
         if (nfast) {
@@ -1306,7 +1341,8 @@ template <int S> struct FzsFL {          // per-warp shared memory of the front 
     static constexpr int OFF_T = BLK;                  // float2 trail[32*S]
     static constexpr int OFF_E = 2 * BLK;              // double e[32][ES] window sums
     static constexpr int OFF_CW = OFF_E + 32 * C::ES * 8;   // double cw[16]
-    static constexpr int BYTES = OFF_CW + 16 * 8;
+    static constexpr int BYTES = fz_align128(OFF_CW + 16 * 8);
+    static_assert(BYTES % 128 == 0 && OFF_T % 128 == 0, "staged blocks must start on a 128-byte line");
 };
 
 struct FzsFrontParams {
@@ -1352,12 +1388,9 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
     const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
     const bool m_ok = (M == 2 || M == 4 || M == 8);
     double Cw = cwp[wp];
-    // FzCfg<S>::phys() of (row R*wg + i, phase wp) for the unrolled i: pos[i >> 1][i & 1] (loop-invariant, lane-dependent)
-    int pos[(R + 1) / 2][2];
-#pragma unroll
-    for (int i = 0; i < R; i++) pos[i >> 1][i & 1] = C::phys((R * wg + i) * S + wp);
-    const int rowp = C::phys(lane * S) & ~(S == 8 ? 7 : 0);                 // its row's base ...
-    const int gsw = (S == 8) ? (C::phys(lane * S) & 7) : 0;                 // ... and the permutation of its pieces (phase ^ gsw)
+    const int od = (S == 8) ? (wg & 1) : 0;
+    const int ofs_e = (R * wg + od) * S + wp, ofs_o = (R * wg - od) * S + wp;
+    const int rowp = (S == 8) ? (lane ^ ((lane >> 3) & 1)) * S : lane * S;
 
 #pragma unroll 1
     for (int c = 0; c < nchunks; c++) {
@@ -1377,11 +1410,13 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
         double Eloc[R];
         double x = 0.0;
         {
+            const float2* le = Lst + ofs_e; const float2* lo = Lst + ofs_o;
+            const float2* te = Tst + ofs_e; const float2* to = Tst + ofs_o;
 #pragma unroll
             for (int i = 0; i < R; i++) {
                 if (G * R == 32 || R * wg + i < 32) {
-                    const float2 a = Lst[pos[i >> 1][i & 1]];
-                    const float2 b = Tst[pos[i >> 1][i & 1]];
+                    const float2 a = (i & 1) ? lo[i * S] : le[i * S];
+                    const float2 b = (i & 1) ? to[i * S] : te[i * S];
                     x = daddr(x, (double)fz_energy(a));                       // :448-451
                     Eloc[i] = x;
                     x = dsubr(x, (double)fz_energy(b));                       // :576
@@ -1432,7 +1467,7 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
             }
             const int idx = ix[0];
             if (lane < nrows) __stcs(o_sidx + krow + lane, (int16_t)idx);                  // :466
-            gx = Tst[rowp + (idx ^ gsw)];
+            gx = Tst[rowp + idx];
         }
         __syncwarp();
         if (nfast) {
@@ -1559,7 +1594,7 @@ template <int PC> struct FzsCbL {        // per-warp shared memory of the chain 
     static constexpr int OFF_CZ = fz_align16(OFF_CTX + (int)sizeof(FzCtx)); // double cz[PC + 1], ends where ALIAS starts
     static constexpr int OFF_ALIAS = OFF_CZ + fz_align16((PC + 1) * 8);
     static constexpr int C_BYTES = FZ_B * 8 + FZ_B * 4 + (FZ_B + 4) * 4;    // prefix block, y block, est block; back: soft + bits staging
-    static constexpr int BYTES = OFF_ALIAS + fz_align16(C_BYTES);
+    static constexpr int BYTES = fz_align128(OFF_ALIAS + fz_align16(C_BYTES));
 };
 
 struct FzsCbParams {

@@ -51,7 +51,7 @@ struct ChanState {
 };
 
 struct DevCounters {
-    unsigned long long wraps, spec_chunks, spec_misses, seq_channels, tp_packets;
+    unsigned long long wraps, spec_chunks, spec_misses, seq_channels, tp_packets, tp_repaired;
 };
 
 // first call-local output symbol whose emission sample lies at or after input position x

@@ -1204,7 +1204,7 @@ k_tp_check(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, c
 // its predecessor's exact end record, and the later packets from re-synthesised rings; k_tp_check then proves the
 // new hand-overs.  A channel that fails again goes to the sequential chain.
 __global__ void __launch_bounds__(128)
-k_tp_fix(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, const TpCtl tp)
+k_tp_fix(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, const TpCtl tp, DevCounters* counters)
 {
     const int lane = threadIdx.x & 31;
     const int ci = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -1231,6 +1231,7 @@ k_tp_fix(const ChanDesc* __restrict__ desc, const float* __restrict__ theta, con
     __syncwarp();
     if (lane != 0) return;
     *tp.any_rerun = 1;
+    atomicAdd(&counters->tp_repaired, 1ULL);
     const float* thg = theta + d.scr_off;
     const int M = d.M;
     const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)M));
@@ -1362,7 +1363,7 @@ cudaError_t launch_chain_par(const LaunchCtx& c) {
         static const int rounds = getenv("PSKD_TP_ROUNDS") ? atoi(getenv("PSKD_TP_ROUNDS")) : 1;
         for (int r = 0; r < rounds && tp_fzs > 0; r++) {
             c.prof->begin(KID_TP, c.stream);
-            k_tp_fix<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2);
+            k_tp_fix<<<(c.tp_n_chans + 3) / 4, 128, 0, c.stream>>>(c.d_desc, c.d_theta, t2, c.d_counters);
             c.prof->end(c.stream);
             (*c.launches)++;
             TpCtl t2r = t2; t2r.rerun = 1;

@@ -224,3 +224,35 @@ def test_randomized_configurations(seed, path, oracle_built, monkeypatch):
             assert_parity(g, ref, differential=bool(props[c]["differentialDecoding"]),
                           tag=f"seed {seed} ch{c} {props[c]} pkt {pkt} call {a}:{b}")
     print(f"seed {seed} {path}: {masked_total[0]} zero-sample symbols masked")
+
+
+def test_time_parallel_repair_round(oracle_built, monkeypatch):
+    """phase steps of about pi in the M-th power phase in the middle of a stream: the classic sample-to-sample unwrap count
+    and the reference's unwrap-against-the-fit rule part ways there, so the levels the time-parallel plan resolved from the
+    classic counts are off by one from that packet on, and the hand-over proof fails.  The repair round (k_tp_fix: exact
+    advances instead of classic ones, restart from the proven predecessor's exact end record) must bring every channel home
+    without the whole-channel sequential fallback -- and the result must be the reference's."""
+    import psk_soft_b200 as pk
+    monkeypatch.setenv("PSKD_FUSED", "0")
+    monkeypatch.setenv("PSKD_TP", "1")
+    rs = np.random.RandomState(77)
+    nch, n, S, M = 48, 160000, 8, 8
+    props = dict(samplesPerBaud=S, constelationSize=M, numAvg=100, phaseAvg=50, differentialDecoding=0)
+    iqs = []
+    for c in range(nch):
+        cut = int(rs.randint(3, 8)) * 16000 + int(rs.randint(2000, 14000))            # somewhere inside a packet
+        step = (np.pi + float(rs.uniform(-0.35, 0.35))) / M * (1 if c % 2 else -1)       # ~ +-pi after the M-th power
+        a = siggen.gen_shaped(n, S, M, seed=900 + c, sigma=0.02, freq=1e-5 * ((c % 5) - 2), timing_shift=c % S)
+        ph = np.ones(n, np.complex64); ph[cut:] = np.exp(1j * step)
+        iqs.append((a * ph).astype(np.complex64))
+    iqs = np.stack(iqs)
+    bank = pk.Bank(nch, props)
+    got = bank.process_host(iqs, xdelta=0.01, packet_len=16000)
+    st = bank.stats()
+    print("stats", st)
+    for c in range(nch):
+        ref = oracle_built.OracleComponent(**props).demod(iqs[c], packet_len=16000, xdelta=0.01)
+        assert_parity(got[c], ref, tag=f"phase step, channel {c}")
+    assert st["tp_packets"] > 0
+    assert st["tp_repaired"] + st["seq_channels"] > 0, st         # the steps really broke some hand-overs ...
+    assert st["seq_channels"] <= st["tp_repaired"], st            # ... and the repair round fixed (most of) them
