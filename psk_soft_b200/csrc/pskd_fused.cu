@@ -108,6 +108,14 @@ constexpr int fz_align16(int x) { return (x + 15) & ~15; }
 // and 12.5 -> 13.7 ms per launch).
 constexpr int fz_align128(int x) { return (x + 127) & ~127; }
 
+// The block buffer keeps the timing-selected samples split into real parts and imaginary parts, selx[FZ_SELN] and
+// sely[FZ_SELN] (entry 2 + i = buffered symbol i, entry 1 = the sample before them, for the differential decoder):
+// two adjacent symbols' real (imaginary) parts are then ONE aligned 64-bit read = one packed f32x2 operand of the
+// per-block stages, with no register shuffling.
+constexpr int FZ_SELN = FZ_BUF + 2;
+__device__ __forceinline__ float2 fz_sel_get(const float* selx, int e) { return make_float2(selx[e], selx[FZ_SELN + e]); }
+__device__ __forceinline__ void fz_sel_put(float* selx, int e, float2 v) { selx[e] = v.x; selx[FZ_SELN + e] = v.y; }
+
 template <int S> struct FzCfg {
     static constexpr int G = 32 / S;                         // row groups (lane = g*S + p)
     static constexpr int R = (32 + G - 1) / G;               // rows per group
@@ -135,7 +143,7 @@ template <int S, int PC> struct FzL {
     static constexpr int OFF_T = BLK;                                      // float2 trail[32*S]
     static constexpr int OFF_CW = 2 * BLK;                                 // double cw[16]     carried window sum per phase
     static constexpr int OFF_TH = OFF_CW + fz_align16(S * 8);              // float  th[FZ_BUF]
-    static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                    // float2 selb[FZ_BUF + 2]; [1] = previous sample
+    static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                    // float selx[FZ_SELN], sely[FZ_SELN]; [1] = previous sample
     static constexpr int OFF_YH = fz_align16(OFF_SEL + (FZ_BUF + 2) * 8);  // float  yh[PC]   y history, logical order
     static constexpr int OFF_CTX = fz_align16(OFF_YH + PC * 4);
     static constexpr int OFF_CZ = fz_align16(OFF_CTX + (int)sizeof(FzCtx));// double cz[PC + 1], ends where ALIAS starts
@@ -198,6 +206,23 @@ __device__ __forceinline__ float fz_energy(float2 v) {
         : "=f"(px), "=f"(py) : "f"(v.x), "f"(v.y));
     return faddr(px, py);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Packed single precision (Blackwell f32x2: one FMUL2 / FADD2 / FFMA2 does the operation on both
+// halves of a 64-bit register pair, each half rounded to nearest exactly like the scalar
+// instruction).  The per-symbol stages that run once per block put TWO symbols in a lane with
+// these: half the issue slots for the same arithmetic.
+// ptxas contracts mul.rn.f32x2 + add/sub.rn.f32x2 into one FFMA2 (it does not for the scalar forms) and folds an
+// fma by +1 back into that, so sums and differences of products that the reference rounds separately are written
+// as a subtraction through an fma by -1 (a sum a + b as a - (-b)).
+// ---------------------------------------------------------------------------------------------
+typedef unsigned long long fz_p2;
+__device__ __forceinline__ fz_p2 p2_make(float lo, float hi) { return ((fz_p2)__float_as_uint(hi) << 32) | (fz_p2)__float_as_uint(lo); }
+__device__ __forceinline__ fz_p2 p2_dup(float c) { return p2_make(c, c); }
+__device__ __forceinline__ void p2_get(fz_p2 v, float& lo, float& hi) { lo = __uint_as_float((unsigned)v); hi = __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ fz_p2 p2_mul(fz_p2 a, fz_p2 b) { fz_p2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ fz_p2 p2_fma(fz_p2 a, fz_p2 b, fz_p2 c) { fz_p2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ fz_p2 p2_sub(fz_p2 a, fz_p2 b) { return p2_fma(b, p2_dup(-1.0f), a); }    // f32(a - b)
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
@@ -307,59 +332,41 @@ __device__ __forceinline__ int fz_unwrap_count(float est_prev, float theta, bool
     return __double2loint(t);
 }
 
-static __device__ __noinline__ unsigned fz_slice8_slow(float cx_, float cy_) { return slice_bits(make_float2(cx_, cy_), 3); }
-__device__ __forceinline__ unsigned fz_slice8(float2 c) {
-    const float a = fabsf(c.x), b = fabsf(c.y);
-    const float T = 0.41421356237309503f;       // tan(pi/8)
-    const float sum = a + b;
-    const float d1 = b - T * a, d2 = a - T * b;
-    const float g = 1.0e-5f * sum;
-    if (!(sum > 0.0f) || !(sum < 3.0e38f) || fabsf(d1) <= g || fabsf(d2) <= g) return fz_slice8_slow(c.x, c.y);
-    if (d1 < 0.0f) return (c.x > 0.0f) ? 0u : 4u;
-    if (d2 < 0.0f) return (c.y > 0.0f) ? 2u : 6u;
-    return (c.x > 0.0f) ? ((c.y > 0.0f) ? 1u : 7u) : ((c.y > 0.0f) ? 3u : 5u);
-}
-
-static __device__ __noinline__ float2 fz_cdiv(float2 n, float2 d) { return cdiv_f32(n, d); }
-
 // ---------------------------------------------------------------------------------------------
-// sincosf for the derotation phasor (cpp/psk_soft.cpp:499, std::polar(1.0f, pc)).  Three-term
-// Cody-Waite reduction by pi/2 and the Cephes single-precision kernels: |error| <= 1e-7 for
-// |pc| < 1e4 (glibc's and CUDA's sincosf are "about an ulp" functions as well; the soft output's
-// tolerance is 1e-4).  Larger / non-finite arguments take the library call.
+// The derotation phasor (cpp/psk_soft.cpp:499, std::polar(1.0f, pc)) of two symbols at once: Cody-Waite
+// reduction by 2 pi in packed arithmetic, then the hardware's sine / cosine (MUFU, |error| <= 2^-21.4 on
+// [-pi, pi]): |error| <= 6e-7 on the phasor, i.e. on the soft decisions relative to their magnitude
+// (tolerance 1e-4; glibc's and CUDA's sincosf are "about an ulp" functions); a decision that close to a
+// slicer boundary is inside the slicer's guard band (1e-5) and is redone literally.  |pc| >= 1e4 or
+// non-finite arguments take the library call.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fz_sincos(float x, float& sn, float& cs, bool& bad) {
-    bad = bad || !(fabsf(x) < 1.0e4f);
-    const float t = fmaf(x, 0.63661977236758134f, 12582912.0f);      // x * 2/pi, rounded to an integer in the low bits
-    const int q = __float_as_int(t);
-    const float j = t - 12582912.0f;
-    float r = fmaf(-j, 1.5707962513e+0f, x);
-    r = fmaf(-j, 7.5497894159e-8f, r);
-    r = fmaf(-j, 5.3903029534e-15f, r);
-    const float r2 = r * r;
-    float ps = fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f);
-    ps = fmaf(ps, r2, -1.6666654611e-1f);
-    const float s0 = fmaf(r * r2, ps, r);
-    float pc = fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f);
-    pc = fmaf(pc, r2, 4.166664568298827e-2f);
-    const float c0 = fmaf(r2 * r2, pc, fmaf(-0.5f, r2, 1.0f));
-    const float ss = (q & 1) ? c0 : s0, cc = (q & 1) ? s0 : c0;
-    sn = (q & 2) ? -ss : ss;
-    cs = ((q + 1) & 2) ? -cc : cc;
+__device__ __forceinline__ void fz_sincos2(fz_p2 X, fz_p2& SN, fz_p2& CS, bool& badA, bool& badB) {
+    float xa, xb;
+    p2_get(X, xa, xb);
+    badA = badA || !(fabsf(xa) < 1.0e4f);
+    badB = badB || !(fabsf(xb) < 1.0e4f);
+    const fz_p2 T = p2_fma(X, p2_dup(0.15915494309189535f), p2_dup(12582912.0f));      // x / 2pi, rounded to an integer in the low bits
+    const fz_p2 K = p2_fma(T, p2_dup(1.0f), p2_dup(-12582912.0f));
+    fz_p2 R = p2_fma(K, p2_dup(-6.2831854820251465f), X);                               // 2 pi = 6.2831854820251465 - 1.7484555e-7
+    R = p2_fma(K, p2_dup(1.7484555e-7f), R);
+    float ra, rb;
+    p2_get(R, ra, rb);
+    SN = p2_make(__sinf(ra), __sinf(rb));
+    CS = p2_make(__cosf(ra), __cosf(rb));
 }
 
 // 8-PSK slicer (cpp/psk_soft.cpp:547-563) as a sector test against the rays at odd multiples of
 // pi/8; inside a guard band of the rays (or for zero / non-finite input) `bad` asks for the literal
-// atan2f -> /pi*4 -> roundf path.
-__device__ __forceinline__ unsigned fz_slice8_flag(float2 c, bool& bad) {
-    const float a = fabsf(c.x), b = fabsf(c.y);
+// atan2f -> /pi*4 -> roundf path.  ONE guard comparison: zero input (d1 = d2 = g = 0), NaN and infinity
+// (g or both d are NaN / inf) all fail min(|d1|, |d2|) > g.
+__device__ __forceinline__ unsigned fz_slice8_guard(float x, float y, bool& bad) {
+    const float a = fabsf(x), b = fabsf(y);
     const float T = 0.41421356237309503f;       // tan(pi/8)
-    const float sum = a + b;
     const float d1 = b - T * a, d2 = a - T * b;
-    const float g = 1.0e-5f * sum;
-    bad = bad || !(sum > 0.0f) || !(sum < 3.0e38f) || fabsf(d1) <= g || fabsf(d2) <= g;
-    const unsigned quad = (c.x > 0.0f) ? ((c.y > 0.0f) ? 1u : 7u) : ((c.y > 0.0f) ? 3u : 5u);
-    const unsigned ax = (c.x > 0.0f) ? 0u : 4u, ay = (c.y > 0.0f) ? 2u : 6u;
+    const float g = 1.0e-5f * (a + b);
+    bad = bad || !(fminf(fabsf(d1), fabsf(d2)) > g);
+    const unsigned quad = (x > 0.0f) ? ((y > 0.0f) ? 1u : 7u) : ((y > 0.0f) ? 3u : 5u);
+    const unsigned ax = (x > 0.0f) ? 0u : 4u, ay = (y > 0.0f) ? 2u : 6u;
     return (d1 < 0.0f) ? ax : ((d2 < 0.0f) ? ay : quad);
 }
 
@@ -383,11 +390,11 @@ template <class L>
 static __device__ __noinline__ void fz_back_literal(const unsigned wofs, const int i, int M, int bpb, int diff) {
     unsigned char* wb = fz_smem + wofs;                  // (offsets, not pointers: see the note at fz_normalize_ring_w)
     const float*  th   = reinterpret_cast<const float*>(wb + L::OFF_TH);
-    const float2* selb = reinterpret_cast<const float2*>(wb + L::OFF_SEL);
+    const float* selx = reinterpret_cast<const float*>(wb + L::OFF_SEL);
     float2* c_stage = reinterpret_cast<float2*>(wb + L::OFF_ALIAS) + i;
     short*  b_stage = reinterpret_cast<short*>(wb + L::OFF_ALIAS + FZ_B * 8) + i * bpb;
     unsigned char* h_stage = wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6 + i;
-    const float2 s = selb[2 + i], prev = selb[1 + i];
+    const float2 s = fz_sel_get(selx, 2 + i), prev = fz_sel_get(selx, 1 + i);
     const float est = th[i];
     float2 x = s;
     if (diff) x = cdiv_f32(s, prev);
@@ -401,57 +408,88 @@ static __device__ __noinline__ void fz_back_literal(const unsigned wofs, const i
 
 // derotate / differential decode / slice (cpp/psk_soft.cpp:484-566), specialised on bits per symbol and on
 // differential decoding.  QPSK <=> BPB == 2 (constelationSize 4).  Flagged symbols take fz_back_literal.
-// A ROLLED loop: trip t handles symbol 32*t + lane (inputs and outputs go through shared memory,
-// conflict-free).  The block's code is executed once per 128 symbols, so its cost is
-// dominated by instruction fetch (the L0 instruction cache holds ~380 instructions and is shared by the
-// warps of a scheduler): four trips through ~70 instructions beat one trip through ~250.
+// TWO adjacent symbols per lane (symbols 2j and 2j + 1, j = 32 * trip + lane): the loads are 64-bit reads of the two
+// samples' real parts, imaginary parts and estimates, the phasor / derotation arithmetic is packed (FMUL2 / FFMA2), the
+// phasor comes from the hardware sine / cosine after a Cody-Waite reduction (fz_sincos2), and the results leave in one
+// 128-bit store (soft) and 32-bit stores (bits): 90 instructions per 64 symbols where the one-symbol-per-lane form took 168.
+// A ROLLED loop, two trips per 128-symbol block: the code runs once per block, so its cost is dominated by
+// instruction fetch (unrolling the two trips: 13.1 vs 12.6 ms per launch).
 // The buffers are addressed from the warp's shared-memory offset (not through generic pointer parameters: those cost
 // ~15 instructions per 32 symbols of address conversion and turn every access into a generic LD / ST).
 template <class L, int BPB, bool DIFF, bool HARD>
-static __device__ __noinline__ void fz_back_rolled(const unsigned wofs, const int lane, const int M, const int m) {
-    constexpr bool hard = HARD;          // the additional packed output is compiled out of the loop nobody asked it of
+static __device__ __noinline__ void fz_back_pairs(const unsigned wofs, const int lane, const int M, const int m) {
     unsigned char* wb = fz_smem + wofs;
-    unsigned char* __restrict__ hst = wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6;                     // packed hard symbols [FZ_B]
-    const float*  __restrict__ th     = reinterpret_cast<const float*>(wb + L::OFF_TH);
-    const float2* __restrict__ selb   = reinterpret_cast<const float2*>(wb + L::OFF_SEL);
-    float2*       __restrict__ cst    = reinterpret_cast<float2*>(wb + L::OFF_ALIAS);              // soft staging [FZ_B]
-    short*        __restrict__ bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS + FZ_B * 8);    // bits staging [FZ_B * 3]
-    const float inv_m = 1.0f / (float)M;
+    const float2* __restrict__ th2  = reinterpret_cast<const float2*>(wb + L::OFF_TH);
+    const float*  __restrict__ selx = reinterpret_cast<const float*>(wb + L::OFF_SEL);
+    const float2* __restrict__ sx2  = reinterpret_cast<const float2*>(selx + 2);                   // real parts of symbols 2j, 2j + 1
+    const float2* __restrict__ sy2  = reinterpret_cast<const float2*>(selx + FZ_SELN + 2);         // imaginary parts
+    float4*   __restrict__ cst4 = reinterpret_cast<float4*>(wb + L::OFF_ALIAS);                    // soft staging [FZ_B]
+    unsigned* __restrict__ bst  = reinterpret_cast<unsigned*>(wb + L::OFF_ALIAS + FZ_B * 8);       // bits staging [FZ_B * 3] int16
+    unsigned short* __restrict__ hst2 = reinterpret_cast<unsigned short*>(wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6);   // packed hard symbols
+    const float ninv_m = -1.0f / (float)M;
     const bool inexact = (BPB == 0 && (M & (M - 1)) != 0);                 // -est/M not an exact multiply
-#ifdef PSKD_FZ_BACK_UNROLL2
-#pragma unroll 2
-#else
+    const int npairs = (m + 1) >> 1;
 #pragma unroll 1
-#endif
-    for (int i = lane; i < ((m + 31) & ~31); i += 32) {
-        bool bad = inexact;
-        float2 s = selb[2 + i];
-        float pc = 0.0f;
-        if (DIFF) s = fz_cdiv_fast(s, selb[1 + i], bad);                                          // :488
-        else pc = fmulr(-th[i], inv_m);                                                           // :494 (exact for M = 2^n)
-        if (BPB == 2) pc = __double2float_rn(daddr((double)pc, PSKD_M_PI_4));                     // :497-498
-        float sn, cs;
-        fz_sincos(pc, sn, cs, bad);                                                               // :499
-        const float x = fsubr(fmulr(s.x, cs), fmulr(s.y, sn));                                    // :500-501, unfused
-        const float y = faddr(fmulr(s.x, sn), fmulr(s.y, cs));
-        bad = bad || !(fabsf(x) + fabsf(y) < 3.0e38f);                                            // NaN / inf: __mulsc3 recovery decides
-        const float2 c = make_float2(x, y);
-        cst[i] = c;
-        if (BPB == 3) {
-            const unsigned b = fz_slice8_flag(c, bad);
-            bstage[3 * i] = (short)(b & 1u); bstage[3 * i + 1] = (short)((b >> 1) & 1u); bstage[3 * i + 2] = (short)(b >> 2);   // :559-563
-            if (hard) hst[i] = (unsigned char)b;
-        } else if (BPB == 1) {
-            bstage[i] = (x < 0.0f) ? 1 : 0;                                                       // :512
-            if (hard) hst[i] = (x < 0.0f) ? 1 : 0;
-        } else if (BPB == 2) {                                                                    // :523-526 (float -> bool, sic)
-            const unsigned b0 = ((x != 0.0f) != (y != 0.0f)) ? 1u : 0u, b1 = (y != 0.0f) ? 0u : 1u;
-            reinterpret_cast<unsigned*>(bstage)[i] = b0 | (b1 << 16);
-            if (hard) hst[i] = (unsigned char)(b0 | (b1 << 1));
+    for (int j = lane; j < ((npairs + 31) & ~31); j += 32) {
+        bool badA = inexact, badB = inexact;
+        const float2 vx = sx2[j], vy = sy2[j];
+        float2 sA = make_float2(vx.x, vy.x), sB = make_float2(vx.y, vy.y);
+        fz_p2 SN, CS;
+        if (DIFF) {
+            const float2 pA = fz_sel_get(selx, 1 + 2 * j);
+            const float2 rawA = sA;
+            sA = fz_cdiv_fast(rawA, pA, badA);                                                     // :488
+            sB = fz_cdiv_fast(sB, rawA, badB);
+            // pc = 0 (+ pi/4 for QPSK, :497-498): the phasor is a constant
+            SN = (BPB == 2) ? p2_dup(0.7071067966408575f) : p2_dup(0.0f);
+            CS = (BPB == 2) ? p2_dup(0.7071067657322372f) : p2_dup(1.0f);
+        } else {
+            const float2 e2 = th2[j];
+            fz_p2 PCV = p2_mul(p2_make(e2.x, e2.y), p2_dup(ninv_m));                               // :494 (exact for M = 2^n)
+            if (BPB == 2) {                                                                        // :497-498
+                float pa, pb;
+                p2_get(PCV, pa, pb);
+                PCV = p2_make(__double2float_rn(daddr((double)pa, PSKD_M_PI_4)), __double2float_rn(daddr((double)pb, PSKD_M_PI_4)));
+            }
+            fz_sincos2(PCV, SN, CS, badA, badB);                                                   // :499
         }
-        bad = bad && i < m;
-        if (__any_sync(0xffffffffu, bad)) {             // rare: literal evaluation of the flagged symbols
-            if (bad) fz_back_literal<L>(wofs, i, M, BPB, DIFF ? 1 : 0);
+        const fz_p2 X = p2_make(sA.x, sB.x), Y = p2_make(sA.y, sB.y);
+        const fz_p2 XO = p2_sub(p2_mul(X, CS), p2_mul(Y, SN));                                     // :500-501, unfused
+        const fz_p2 YO = p2_sub(p2_mul(X, SN), p2_mul(p2_mul(Y, p2_dup(-1.0f)), CS));              // xs - (-(y cs)): stays unfused
+        float xA, xB, yA, yB;
+        p2_get(XO, xA, xB);
+        p2_get(YO, yA, yB);
+        if (BPB != 3) {                                                                            // NaN / inf: __mulsc3 recovery decides
+            badA = badA || !(fabsf(xA) + fabsf(yA) < 3.0e38f);                                     // (8-PSK: the slicer's guard test covers it)
+            badB = badB || !(fabsf(xB) + fabsf(yB) < 3.0e38f);
+        }
+        cst4[j] = make_float4(xA, yA, xB, yB);
+        if (BPB == 3) {
+            const unsigned bA = fz_slice8_guard(xA, yA, badA), bB = fz_slice8_guard(xB, yB, badB);
+            // one int16 per bit, LSB first (:559-563): b * 0x40008001 puts bit 0 at 0, bit 1 at 16, bit 2 at 32
+            const unsigned long long wA = (unsigned long long)bA * 0x40008001ull, wB = (unsigned long long)bB * 0x40008001ull;
+            const unsigned loA = (unsigned)wA & 0x00010001u, hiA = (unsigned)(wA >> 32) & 1u;
+            const unsigned loB = (unsigned)wB & 0x00010001u, hiB = (unsigned)(wB >> 32) & 1u;
+            bst[3 * j] = loA;
+            bst[3 * j + 1] = hiA | (loB << 16);
+            bst[3 * j + 2] = (loB >> 16) | (hiB << 16);
+            if (HARD) hst2[j] = (unsigned short)(bA | (bB << 8));
+        } else if (BPB == 1) {
+            const unsigned bA = (xA < 0.0f) ? 1u : 0u, bB = (xB < 0.0f) ? 1u : 0u;                 // :512
+            bst[j] = bA | (bB << 16);
+            if (HARD) hst2[j] = (unsigned short)(bA | (bB << 8));
+        } else if (BPB == 2) {                                                                     // :523-526 (float -> bool, sic)
+            const unsigned a0 = ((xA != 0.0f) != (yA != 0.0f)) ? 1u : 0u, a1 = (yA != 0.0f) ? 0u : 1u;
+            const unsigned b0 = ((xB != 0.0f) != (yB != 0.0f)) ? 1u : 0u, b1 = (yB != 0.0f) ? 0u : 1u;
+            reinterpret_cast<uint2*>(bst)[j] = make_uint2(a0 | (a1 << 16), b0 | (b1 << 16));
+            if (HARD) hst2[j] = (unsigned short)((a0 | (a1 << 1)) | ((b0 | (b1 << 1)) << 8));
+        }
+        const int iA = 2 * j;
+        badA = badA && iA < m;
+        badB = badB && iA + 1 < m;
+        if (__any_sync(0xffffffffu, badA || badB)) {    // rare: literal evaluation of the flagged symbols
+            if (badA) fz_back_literal<L>(wofs, iA, M, BPB, DIFF ? 1 : 0);
+            if (badB) fz_back_literal<L>(wofs, iA + 1, M, BPB, DIFF ? 1 : 0);
         }
     }
 }
@@ -639,7 +677,7 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
 {
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     float2* cst  = reinterpret_cast<float2*>(wb + L::OFF_ALIAS);              // soft staging [FZ_B]
     short* bstage = reinterpret_cast<short*>(wb + L::OFF_ALIAS + FZ_B * 8);   // bits staging [FZ_B * 3]
@@ -650,23 +688,23 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
     const bool hard = o_hard != nullptr && bpb > 0;
     if (!hard) {
         switch (bpb * 2 + (diff ? 1 : 0)) {
-            case 6: fz_back_rolled<L, 3, false, false>(wofs, lane, M, m); break;
-            case 7: fz_back_rolled<L, 3, true, false>(wofs, lane, M, m); break;
-            case 4: fz_back_rolled<L, 2, false, false>(wofs, lane, M, m); break;
-            case 5: fz_back_rolled<L, 2, true, false>(wofs, lane, M, m); break;
-            case 2: fz_back_rolled<L, 1, false, false>(wofs, lane, M, m); break;
-            case 3: fz_back_rolled<L, 1, true, false>(wofs, lane, M, m); break;
-            case 0: fz_back_rolled<L, 0, false, false>(wofs, lane, M, m); break;
-            default: fz_back_rolled<L, 0, true, false>(wofs, lane, M, m); break;
+            case 6: fz_back_pairs<L, 3, false, false>(wofs, lane, M, m); break;
+            case 7: fz_back_pairs<L, 3, true, false>(wofs, lane, M, m); break;
+            case 4: fz_back_pairs<L, 2, false, false>(wofs, lane, M, m); break;
+            case 5: fz_back_pairs<L, 2, true, false>(wofs, lane, M, m); break;
+            case 2: fz_back_pairs<L, 1, false, false>(wofs, lane, M, m); break;
+            case 3: fz_back_pairs<L, 1, true, false>(wofs, lane, M, m); break;
+            case 0: fz_back_pairs<L, 0, false, false>(wofs, lane, M, m); break;
+            default: fz_back_pairs<L, 0, true, false>(wofs, lane, M, m); break;
         }
     } else {
         switch (bpb * 2 + (diff ? 1 : 0)) {
-            case 6: fz_back_rolled<L, 3, false, true>(wofs, lane, M, m); break;
-            case 7: fz_back_rolled<L, 3, true, true>(wofs, lane, M, m); break;
-            case 4: fz_back_rolled<L, 2, false, true>(wofs, lane, M, m); break;
-            case 5: fz_back_rolled<L, 2, true, true>(wofs, lane, M, m); break;
-            case 2: fz_back_rolled<L, 1, false, true>(wofs, lane, M, m); break;
-            default: fz_back_rolled<L, 1, true, true>(wofs, lane, M, m); break;
+            case 6: fz_back_pairs<L, 3, false, true>(wofs, lane, M, m); break;
+            case 7: fz_back_pairs<L, 3, true, true>(wofs, lane, M, m); break;
+            case 4: fz_back_pairs<L, 2, false, true>(wofs, lane, M, m); break;
+            case 5: fz_back_pairs<L, 2, true, true>(wofs, lane, M, m); break;
+            case 2: fz_back_pairs<L, 1, false, true>(wofs, lane, M, m); break;
+            default: fz_back_pairs<L, 1, true, true>(wofs, lane, M, m); break;
         }
     }
     int16_t* o_bits = cx.o_bits;
@@ -777,7 +815,7 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
 {
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     const int lane = fz_lane();
@@ -807,7 +845,7 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
             m = 1048576 - cnt;                                                      // stop at the re-sum point
         }
         if (!fast) m = min(m, max(1, P - pts));                                     // fill-up runs sequentially
-        const float2 prev_new = selb[2 + m - 1];
+        const float2 prev_new = fz_sel_get(selx, 2 + m - 1);
         bool done = false;
         if (fast) done = fz_chain_fast<L>(wofs, m);
         if (!done) fz_chain_slow<L>(wofs, m);
@@ -818,12 +856,12 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
         for (int base = 0; base < left; base += 32) {
             const int i = base + lane;
             float tv = 0.f; float2 sv2 = make_float2(0.f, 0.f);
-            if (i < left) { tv = th[m + i]; sv2 = selb[2 + m + i]; }
+            if (i < left) { tv = th[m + i]; sv2 = fz_sel_get(selx, 2 + m + i); }
             __syncwarp();
-            if (i < left) { th[i] = tv; selb[2 + i] = sv2; }
+            if (i < left) { th[i] = tv; fz_sel_put(selx, 2 + i, sv2); }
             __syncwarp();
         }
-        if (lane == 0) { selb[1] = prev_new; cx.nbuf = left; cx.kchain = kchain + m; }
+        if (lane == 0) { fz_sel_put(selx, 1, prev_new); cx.nbuf = left; cx.kchain = kchain + m; }
         __syncwarp();
     }
 }
@@ -880,14 +918,14 @@ __device__ __forceinline__ float fz_theta(float2 s, int M, bool& bad) {
 #endif
 }
 // literal path for the lanes that asked for it: th[i] = atan2f(pow(sel[i], M)) with the library call
-static __device__ __noinline__ void fz_theta_fixup(float* th, const float2* sel, int i, unsigned M) {
-    const float2 z = cpow_unsigned(sel[i], M);
+static __device__ __noinline__ void fz_theta_fixup(float* th, float2 sel, int i, unsigned M) {
+    const float2 z = cpow_unsigned(sel, M);
     th[i] = atan2f(z.y, z.x);
 }
 
 template <class L> static __device__ __noinline__ void fz_theta_fixup_w(const unsigned wofs, int i, unsigned M) {
     unsigned char* wb = fz_smem + wofs;
-    fz_theta_fixup(reinterpret_cast<float*>(wb + L::OFF_TH), reinterpret_cast<const float2*>(wb + L::OFF_SEL) + 2, i, M);
+    fz_theta_fixup(reinterpret_cast<float*>(wb + L::OFF_TH), fz_sel_get(reinterpret_cast<const float*>(wb + L::OFF_SEL), 2 + i), i, M);
 }
 
 __device__ __forceinline__ void fz_prefetch_l2(const void* p, unsigned bytes) {
@@ -964,7 +1002,7 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
     unsigned char* wb = fz_smem + wofs;
     float2* Lst  = reinterpret_cast<float2*>(wb + L::OFF_L);
     float2* Tst  = reinterpret_cast<float2*>(wb + L::OFF_T);
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
@@ -1061,7 +1099,7 @@ static __device__ __noinline__ int fz_unit_begin(const FusedParams& prm, const u
     for (int j = lane; j < P; j += 32) yh[j] = __ldcg(gring + j);
     __syncwarp();
     if (lane == 0) {
-        cx.wraps0 = cx.st.wraps; selb[1] = cx.st.last;
+        cx.wraps0 = cx.st.wraps; fz_sel_put(selx, 1, cx.st.last);
         if (!start_mid) fz_prologue(cx, yh);
         else if (cx.st.fit.pts == cx.st.fit.n && cx.st.fit.pts > 1) cx.fc = fit_const(cx.st.fit);
     }
@@ -1098,7 +1136,7 @@ static __device__ __noinline__ void fz_unit_end(const FusedParams& prm, const un
 {
     using L = FzL<S, PC>;
     unsigned char* wb = fz_smem + wofs;
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     const int lane = threadIdx.x & 31;
@@ -1108,7 +1146,7 @@ static __device__ __noinline__ void fz_unit_end(const FusedParams& prm, const un
         fz_normalize_ring(yh, reinterpret_cast<float*>(wb + L::OFF_ALIAS), cx.st.fit, P, lane);
     for (int j = lane; j < P; j += 32) __stcg(gring + j, yh[j]);
     if (lane == 0) {
-        if (cx.diff && cx.kB > cx.kA) cx.st.last = selb[1];                               // :489
+        if (cx.diff && cx.kB > cx.kA) cx.st.last = fz_sel_get(selx, 1);                   // :489
         const int4* src = reinterpret_cast<const int4*>(&cx.st);
         int4* dst = reinterpret_cast<int4*>(prm.state + ch);
 #pragma unroll
@@ -1144,7 +1182,7 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
     float2* Lst  = reinterpret_cast<float2*>(wb + L::OFF_L);
     float2* Tst  = reinterpret_cast<float2*>(wb + L::OFF_T);
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
     double* ebuf = reinterpret_cast<double*>(wb + L::OFF_ALIAS);       // [32][ES] window sums
@@ -1261,12 +1299,14 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
         inflight = nfast;
 
         // ---- M-th power angle (:474), append to the block buffer ---------------------------------------
+        // (forming the angles of a whole block in a packed two-symbols-per-lane stage saves 22 instructions per chunk
+        // and costs time: 12.95 vs 12.75 ms -- here the angle's dependent chain overlaps the rest of the loop body)
         bool bad = false;
         const float thv = fz_theta(gx, M, bad);
         bad = (bad || !m_ok) && lane < nrows;
         if (lane < nrows) {
             th[nbuf + lane] = thv;
-            selb[2 + nbuf + lane] = gx;
+            fz_sel_put(selx, 2 + nbuf + lane, gx);
         }
         if (__any_sync(0xffffffffu, bad)) {            // rare: literal angle for odd inputs / other M
             __syncwarp();
@@ -1282,8 +1322,11 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int S, int PC>
-__global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZ_MIN_CTAS)
+// CT = resident CTAs per SM the register allocation aims at: 5 (96 registers) is the faster code per warp, 6 (80 registers,
+// 24 warps per SM) hides more latency and wins once a launch has enough channels to keep all of those warps busy
+// (launch_fused_t decides).
+template <int S, int PC, int CT>
+__global__ void __launch_bounds__(FZ_WARPS * 32, CT)
 k_fused(const FusedParams prm)
 {
     using L = FzL<S, PC>;
@@ -1489,7 +1532,7 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
         }
         if (__any_sync(0xffffffffu, bad)) {            // rare: literal angle for odd inputs / other M
             __syncwarp();
-            if (bad) fz_theta_fixup(o_th, o_sel, krow + lane, (unsigned)M);
+            if (bad) fz_theta_fixup(o_th, gx, krow + lane, (unsigned)M);
         }
     }
     __syncwarp();
@@ -1588,7 +1631,7 @@ template <int PC> struct FzsCbL {        // per-warp shared memory of the chain 
     static constexpr int S_STATIC = 0;
     static constexpr bool TRACK_N = true;                                   // exact first / last unwrap counts into the end record
     static constexpr int OFF_TH = 0;                                        // float  th[FZ_BUF]
-    static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                     // float2 selb[FZ_BUF + 2]; [1] = previous sample
+    static constexpr int OFF_SEL = OFF_TH + FZ_BUF * 4;                     // float selx[FZ_SELN], sely[FZ_SELN]; [1] = previous sample
     static constexpr int OFF_YH = fz_align16(OFF_SEL + (FZ_BUF + 2) * 8);   // float  yh[PC]
     static constexpr int OFF_CTX = fz_align16(OFF_YH + PC * 4);
     static constexpr int OFF_CZ = fz_align16(OFF_CTX + (int)sizeof(FzCtx)); // double cz[PC + 1], ends where ALIAS starts
@@ -1612,7 +1655,7 @@ static __device__ __noinline__ bool fzs_cb_begin(const FzsCbParams& prm, const u
 {
     using L = FzsCbL<PC>;
     unsigned char* wb = fz_smem + wofs;
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
     float*  yh   = reinterpret_cast<float*>(wb + L::OFF_YH);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     const int lane = threadIdx.x & 31;
@@ -1708,7 +1751,7 @@ static __device__ __noinline__ bool fzs_cb_begin(const FzsCbParams& prm, const u
         cx.est_start_used = cx.st.est;
         cx.n_first = 0; cx.n_last = 0; cx.have_first = 0; cx.est_pre = cx.st.est;
         cx.wraps0 = cx.st.wraps;
-        selb[1] = (k_begin > 0) ? prm.sel[dgp->scr_off + k_begin - 1] : cx.st.last;         // :486-489
+        fz_sel_put(selx, 1, (k_begin > 0) ? prm.sel[dgp->scr_off + k_begin - 1] : cx.st.last);     // :486-489
         if (pk_a < pk_b) fz_prologue(cx, yh);
     }
     __syncwarp();
@@ -1759,7 +1802,7 @@ k_fzs_cb(const FzsCbParams prm)
     const unsigned wofs = (threadIdx.x >> 5) * (unsigned)L::BYTES;
     unsigned char* wb = fz_smem + wofs;
     float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
-    float2* selb = reinterpret_cast<float2*>(wb + L::OFF_SEL);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
     FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     if (prm.tp.rerun && *prm.tp.any_rerun == 0) return;       // a repair round nobody asked for
 
@@ -1785,13 +1828,15 @@ k_fzs_cb(const FzsCbParams prm)
                 const float4 s0 = __ldg(reinterpret_cast<const float4*>(selg + k0) + lane);
                 const float4 s1 = __ldg(reinterpret_cast<const float4*>(selg + k0) + 32 + lane);
                 reinterpret_cast<float4*>(th)[lane] = t4;
-                reinterpret_cast<float4*>(selb + 2)[lane] = s0;
-                reinterpret_cast<float4*>(selb + 2)[32 + lane] = s1;
+                float2* sx2 = reinterpret_cast<float2*>(selx + 2);
+                float2* sy2 = reinterpret_cast<float2*>(selx + FZ_SELN + 2);
+                sx2[lane] = make_float2(s0.x, s0.z);      sy2[lane] = make_float2(s0.y, s0.w);
+                sx2[32 + lane] = make_float2(s1.x, s1.z); sy2[32 + lane] = make_float2(s1.y, s1.w);
             } else {
 #pragma unroll
                 for (int q = 0; q < FZ_B / 32; q++) {
                     const int i = lane + 32 * q;
-                    if (i < need) { th[nbuf + i] = __ldg(thg + k0 + i); selb[2 + nbuf + i] = __ldg(selg + k0 + i); }
+                    if (i < need) { th[nbuf + i] = __ldg(thg + k0 + i); fz_sel_put(selx, 2 + nbuf + i, __ldg(selg + k0 + i)); }
                 }
             }
             if (lane == 0) cx.nbuf = want;
@@ -1804,6 +1849,27 @@ k_fzs_cb(const FzsCbParams prm)
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+template <int S, int PC, int CT>
+static cudaError_t launch_fused_ct(const LaunchCtx& c, const FusedLaunch& f, const FusedParams& p, double alg_bytes) {
+    using L = FzL<S, PC>;
+    static const size_t pad = getenv("PSKD_FZ_PAD_SMEM") ? (size_t)atoi(getenv("PSKD_FZ_PAD_SMEM")) : 0;   // tuning: lowers occupancy
+    static const int carve = getenv("PSKD_FZ_CARVEOUT") ? atoi(getenv("PSKD_FZ_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;   // tuning: % of the maximum
+    const size_t smem = (size_t)L::BYTES * FZ_WARPS + pad;
+    static KernelCfg cfg;                       // per device (function attributes and occupancy are per device)
+    int ctas_per_sm = 0, n_sm = 0;
+    cudaError_t e = cfg.ensure(k_fused<S, PC, CT>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm, carve);
+    if (e != cudaSuccess) return e;
+    int grid = n_sm * ctas_per_sm;
+    if (f.grid_share > 0.0 && f.grid_share < 1.0) grid = (int)(grid * f.grid_share + 0.999);   // co-resident launches share the SMs
+    const int need = (p.n_units + FZ_WARPS - 1) / FZ_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    c.prof->begin(S == 8 ? KID_FUSED : S == 9 ? KID_FUSED_S9 : S == 10 ? KID_FUSED_S10 : KID_FUSED_S16, c.stream, alg_bytes);
+    k_fused<S, PC, CT><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
+    c.prof->end(c.stream);
+    (*c.launches)++;
+    return cudaGetLastError();
+}
 template <int S, int PC>
 static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     using L = FzL<S, PC>;
@@ -1816,26 +1882,24 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     p.out_soft = (float2*)c.out_soft; p.out_bits = c.out_bits; p.out_phase = c.out_phase; p.out_sidx = c.out_sidx; p.out_hard = c.out_hard;
     p.sri_xdelta = c.sri_xdelta;
     p.counters = c.d_counters;
-    static const size_t pad = getenv("PSKD_FZ_PAD_SMEM") ? (size_t)atoi(getenv("PSKD_FZ_PAD_SMEM")) : 0;   // tuning: lowers occupancy
-    static const int carve = getenv("PSKD_FZ_CARVEOUT") ? atoi(getenv("PSKD_FZ_CARVEOUT")) : (int)cudaSharedmemCarveoutMaxShared;   // tuning: % of the maximum
-    const size_t smem = (size_t)L::BYTES * FZ_WARPS + pad;
-    static KernelCfg cfg;                       // per device (function attributes and occupancy are per device)
-    int ctas_per_sm = 0, n_sm = 0;
-    cudaError_t e = cfg.ensure(k_fused<S, PC>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm, carve);
-    if (e != cudaSuccess) return e;
-    int grid = n_sm * ctas_per_sm;
-    if (f.grid_share > 0.0 && f.grid_share < 1.0) grid = (int)(grid * f.grid_share + 0.999);   // co-resident launches share the SMs
-    const int need = (p.n_units + FZ_WARPS - 1) / FZ_WARPS;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
     double ab = 0.0;
     if (c.prof->enabled && f.h_list)
         for (int i = 0; i < f.n_list; i++) { const ChanDesc& d = c.h_desc[f.h_list[i]]; ab += alg_bytes_front(d) + alg_bytes_chain(d) + alg_bytes_back(d); }
-    c.prof->begin(S == 8 ? KID_FUSED : S == 9 ? KID_FUSED_S9 : S == 10 ? KID_FUSED_S10 : KID_FUSED_S16, c.stream, ab);
-    k_fused<S, PC><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
-    c.prof->end(c.stream);
-    (*c.launches)++;
-    return cudaGetLastError();
+    // 6 CTAs per SM when the launch's channels fill them (every channel is one sequential chain of units: with fewer channels
+    // than resident warps the extra warps idle and the 80-register code is the slower one per warp).  Measured on the bench bank:
+    // 4096 channels 12.2 vs 12.5 ms with 6, 3600 channels (48 more than the 3552 resident warps) 11.2 vs 11.1, 3072 channels 10.5 vs
+    // 9.5 ms: six from 1.1 x the resident warps on.
+    static const int force_ct = getenv("PSKD_FZ_CTAS") ? atoi(getenv("PSKD_FZ_CTAS")) : 0;          // tuning: 5 or 6
+    int n_sm = 0, dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    constexpr bool fits6 = ((size_t)L::BYTES * FZ_WARPS + 1024) * 6 <= 228 * 1024;               // shared memory of six CTAs (S = 8 only)
+    if constexpr (fits6) {
+        const bool six = force_ct ? (force_ct >= 6) : (f.n_list * 10 >= n_sm * 6 * FZ_WARPS * 11 && !(f.grid_share > 0.0 && f.grid_share < 1.0));
+        if (six) return launch_fused_ct<S, PC, 6>(c, f, p, ab);
+    }
+    return launch_fused_ct<S, PC, PSKD_FZ_MIN_CTAS>(c, f, p, ab);
 }
 
 // ---- staged path through the fused kernel's stages ---------------------------------------------
