@@ -115,11 +115,9 @@ struct pskd_bank {
     int* d_done = nullptr;     // [n_channels] units completed per channel in the current call
     int* d_ticket = nullptr;   // [16 slabs x 4 samplesPerBaud values] unit ticket counters of k_fused, then FZS_TICKETS for the k_fzs_* launches
     int fzs_ticket_next = 0;
-    int fzs_uni_mode = 0;      // (experimental, off: measured slower) the staged path's time-parallel channels as ONE task kernel (k_fzs_uni): PSKD_FZS_UNI=0 off, 1 auto, 2 whenever possible
     int fzs_mode = 1;          // staged path through the fused kernel's stages (k_fzs_front + k_fzs_cb) where a channel qualifies (PSKD_FZS=0: legacy staged kernels)
     int tp_mode = -1;          // time-parallel chain of the staged path: -1 auto (few channels, many packets), 0 never, 1 whenever possible (PSKD_TP)
     DevBuf<TpItem> tp_items; DevBuf<TpChan> tp_chans; DevBuf<TpPacket> tp_pkts; DevBuf<TpEnd> tp_ends;
-    DevBuf<int2> uni_tasks; DevBuf<int> uni_ctr;       // task kernel k_fzs_uni: task list, per-channel progress counters
     DevBuf<float> tp_end_ring, tp_start_ring; DevBuf<int> tp_fail, tp_slot_flags;
     Profiler prof;
 };
@@ -243,7 +241,6 @@ int pskd_create(pskd_handle* out, int device, int n_channels, const pskd_props* 
     if (const char* e = getenv("PSKD_TP_MAX")) b->tp_max_channels = std::max(1, atoi(e));
     if (const char* e = getenv("PSKD_TP")) b->tp_mode = (strcmp(e, "auto") == 0) ? -1 : atoi(e) != 0;
     if (const char* e = getenv("PSKD_FZS")) b->fzs_mode = atoi(e) != 0;
-    if (const char* e = getenv("PSKD_FZS_UNI")) b->fzs_uni_mode = atoi(e);
     cudaError_t e;
 #define CT(expr) do { e = (expr); if (e != cudaSuccess) { int rc = fail(e == cudaErrorMemoryAllocation ? PSKD_ERR_NOMEM : PSKD_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e)); pskd_destroy(b); return rc; } } while (0)
     CT(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
@@ -306,7 +303,6 @@ int pskd_destroy(pskd_handle b) {
     b->sel.release(); b->theta.release(); b->phase_tmp.release(); b->sidx_tmp.release();
     b->st_in.release(); b->st_soft.release(); b->st_phase.release(); b->st_bits.release(); b->st_sidx.release(); b->st_hard.release();
     b->tp_items.release(); b->tp_chans.release(); b->tp_pkts.release(); b->tp_ends.release();
-    b->uni_tasks.release(); b->uni_ctr.release();
     b->tp_end_ring.release(); b->tp_start_ring.release(); b->tp_fail.release(); b->tp_slot_flags.release();
     b->prof.destroy();
     for (int i = 0; i < RING; i++) for (cudaEvent_t e : {b->ev_h2d[i], b->ev_kern[i], b->ev_d2h[i]}) if (e) cudaEventDestroy(e);
@@ -718,7 +714,6 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
     std::vector<TpItem> tp_heads, tp_items;
     std::vector<TpChan> tp_chans;
     int tp_slots = 0, tp_records = 0, tp_Pmax = 1;
-    size_t uni_bound = 0;                  // upper bound of a slab's task list (k_fzs_uni)
     static const bool headless_ok = !(getenv("PSKD_TP_HEADLESS") && atoi(getenv("PSKD_TP_HEADLESS")) == 0);
     bool any_staged = false;
     for (int s = 0; s < n_slabs; s++) {
@@ -774,15 +769,13 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
                 if (d.flags & CH_FZS) si.tp_fzs++;
                 const int has_head = headless ? 0 : 1;
                 const int cr = i - lo;                                         // slab-relative channel
-                const int cidx = (int)tp_chans.size() - si.chan0;              // slab-relative index of the channel's TpChan
                 tp_chans.push_back(TpChan{cr, j0, d.n_pkts, tp_records, tp_slots, has_head});
-                if (has_head) tp_heads.push_back(TpItem{cr, 0, j0, 0, -1, tp_records, -1, cidx});
+                if (has_head) tp_heads.push_back(TpItem{cr, 0, j0, 0, -1, tp_records, -1, 0});
                 for (int j = j0; j < d.n_pkts; j++) {
                     const int rec = tp_records + has_head + (j - j0);
                     const int kind = (j == j0) ? (has_head ? 2 : 0) : 1;
-                    tp_items.push_back(TpItem{cr, j, j + 1, kind, has_head ? tp_records : -1, rec, tp_slots + (j - j0), cidx});
+                    tp_items.push_back(TpItem{cr, j, j + 1, kind, has_head ? tp_records : -1, rec, tp_slots + (j - j0), 0});
                 }
-                uni_bound += (size_t)(d.K / 1024 + 2) + 2 * (size_t)(d.n_pkts - j0);
                 tp_records += has_head + (d.n_pkts - j0);
                 tp_slots += d.n_pkts - j0;
                 si.n_slot += d.n_pkts - j0;
@@ -843,8 +836,6 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
         CUDA_TRY(b->tp_start_ring.reserve((size_t)tp_records * tp_stride));
         CUDA_TRY(b->tp_fail.reserve((size_t)nch));
         CUDA_TRY(b->tp_slot_flags.reserve(2 * (size_t)tp_slots + 4));
-        CUDA_TRY(b->uni_tasks.reserve(uni_bound + 4));
-        CUDA_TRY(b->uni_ctr.reserve(3 * (size_t)nch + 4));
         // pageable sources: the copies are staged before the calls return
         CUDA_TRY(cudaMemcpyAsync(b->tp_items.p, tp_heads.data(), sizeof(TpItem) * tp_heads.size(), cudaMemcpyHostToDevice, b->stream));
         CUDA_TRY(cudaMemcpyAsync(b->tp_items.p + tp_heads.size(), tp_items.data(), sizeof(TpItem) * tp_items.size(), cudaMemcpyHostToDevice, b->stream));
@@ -874,13 +865,9 @@ int pskd_process(pskd_handle b, const pskd_input* in, pskd_output* out) {
             Ls.tp_slot_fail = b->tp_slot_flags.p; Ls.tp_slot_run = b->tp_slot_flags.p + tp_slots;
             Ls.tp_any_rerun = b->tp_slot_flags.p + 2 * (size_t)tp_slots;
             Ls.tp_n_chans_fzs = si.tp_fzs;
-            Ls.h_tp_items = tp_items.data() + si.item0; Ls.h_tp_chans = tp_chans.data() + si.chan0;
-            Ls.d_uni_tasks = b->uni_tasks.p; Ls.uni_tasks_cap = b->uni_tasks.cap; Ls.d_uni_ctr = b->uni_ctr.p;
         }
         Ls.n_fzs_channels = si.n_fzs; Ls.Pmax_fzs = si.Pmax_fzs; Ls.S_mask_fzs = si.S_mask_fzs; Ls.Kmax_fzs = si.Kmax_fzs;
         Ls.d_fzs_ticket = b->d_ticket + FUSED_TICKETS; Ls.fzs_ticket_next = &b->fzs_ticket_next; Ls.fzs_ticket_cap = FZS_TICKETS;
-        Ls.fzs_uni_mode = b->fzs_uni_mode;
-        Ls.fzs_uni = fzs_uni_eligible(Ls);
         // A mixed bank has one fused launch per samples-per-symbol class that is large enough: the first on the bank's stream,
         // the others on aux streams, so that one class's tail (few warps left) overlaps the next class's start.
         int n_seg = 0, seg_total = 0, seg_count = 0;

@@ -36,9 +36,7 @@
 // shared memory.
 #include "pskd_internal.h"
 #include "pskd_device.cuh"
-#include "pskd_tp.cuh"
 #include <cstdlib>
-#include <vector>
 
 namespace pskd {
 
@@ -1540,25 +1538,34 @@ static __device__ __forceinline__ void fzs_front_chunks(unsigned char* wb, const
     __syncwarp();
 }
 
-// one front unit: segment `seg` of channel `ch` (rows [seg * seg_syms, +seg_syms) of its symbols)
 template <int S>
-static __device__ __forceinline__ void fzs_front_unit(const FzsFrontParams& prm, unsigned char* wb, const int lane, const int ch, const int seg)
+__global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZS_FRONT_MIN_CTAS)
+k_fzs_front(const FzsFrontParams prm)
 {
     using C = FzCfg<S>;
     using L = FzsFL<S>;
     constexpr int G = C::G, ES = C::ES, CHS = C::CHS;
+    const int lane = fz_lane();
+    unsigned char* wb = fz_smem + (threadIdx.x >> 5) * (unsigned)L::BYTES;
     float2* Lst  = reinterpret_cast<float2*>(wb + L::OFF_L);
     float2* Tst  = reinterpret_cast<float2*>(wb + L::OFF_T);
     double* cwp  = reinterpret_cast<double*>(wb + L::OFF_CW);
     double* ebuf = reinterpret_cast<double*>(wb + L::OFF_E);
     const bool wact = lane < G * S;
     const int wg = wact ? lane / S : 0, wp = wact ? lane - (lane / S) * S : 0;
-    {
+
+    for (;;) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(prm.ticket, 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= prm.n_units) break;
+        const int seg = u / prm.n_channels;
+        const int ch = u - seg * prm.n_channels;
         const ChanDesc* dgp = prm.desc + ch;
-        if (!(dgp->flags & CH_FZS) || dgp->S != S) return;
+        if (!(dgp->flags & CH_FZS) || dgp->S != S) continue;
         const int K = (int)dgp->K;
         const int kA = seg * prm.seg_syms;
-        if (kA >= K) return;
+        if (kA >= K) continue;
         const int kB = min(K, kA + prm.seg_syms);
         const int A = dgp->A, lag = A - 1;
         const long long tail_len = dgp->tail_len;
@@ -1616,23 +1623,6 @@ static __device__ __forceinline__ void fzs_front_unit(const FzsFrontParams& prm,
         float2* o_sel = prm.sel + dgp->scr_off;
         if (a16) fzs_front_chunks<S, true>(wb, lane, kA, kB, lag, c_lo, c_hi, nchunks, pre0, dgp->M, in_mt, tailp, tail_len, V, o_sidx, o_th, o_sel);
         else     fzs_front_chunks<S, false>(wb, lane, kA, kB, lag, c_lo, c_hi, nchunks, pre0, dgp->M, in_mt, tailp, tail_len, V, o_sidx, o_th, o_sel);
-    }
-}
-
-template <int S>
-__global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZS_FRONT_MIN_CTAS)
-k_fzs_front(const FzsFrontParams prm)
-{
-    using L = FzsFL<S>;
-    const int lane = fz_lane();
-    unsigned char* wb = fz_smem + (threadIdx.x >> 5) * (unsigned)L::BYTES;
-    for (;;) {
-        int u = 0;
-        if (lane == 0) u = atomicAdd(prm.ticket, 1);
-        u = __shfl_sync(0xffffffffu, u, 0);
-        if (u >= prm.n_units) break;
-        const int seg = u / prm.n_channels;
-        fzs_front_unit<S>(prm, wb, lane, u - seg * prm.n_channels, seg);
     }
 }
 
@@ -1710,7 +1700,7 @@ static __device__ __noinline__ bool fzs_cb_begin(const FzsCbParams& prm, const u
     } else {
         // synthesised start of packet pk_a (see k_chain_par): the history ring the previous packet leaves behind,
         // from the resolved integers: y = f32(theta + 2pi(c + A)), then the packet-end shift f32(y - w*wrapValue)
-        const TpPacket pp = tp_ld_pkt(tp.pkts + pkt_slot - 1);
+        const TpPacket pp = tp.pkts[pkt_slot - 1];
         const float wrapValue = __double2float_rn(dmulr(PSKD_M_2PI, (double)M));
         const float shift = fmulr((float)pp.w, wrapValue);
         int carry = 0;
@@ -1719,7 +1709,7 @@ static __device__ __noinline__ bool fzs_cb_begin(const FzsCbParams& prm, const u
             int dn = 0;
             float t = 0.0f;
             const bool in = m >= k_begin - P;
-            if (in) { t = __ldcg(thg + m); dn = -__float2int_rn((t - __ldcg(thg + m - 1)) * 0.15915494309189535f); }
+            if (in) { t = __ldg(thg + m); dn = -__float2int_rn((t - __ldg(thg + m - 1)) * 0.15915494309189535f); }
             const int incl = warp_scan_int(dn, lane);
             if (in) {
                 const int c = pp.cEnd - (carry + incl - dn);
@@ -1761,7 +1751,7 @@ static __device__ __noinline__ bool fzs_cb_begin(const FzsCbParams& prm, const u
         cx.est_start_used = cx.st.est;
         cx.n_first = 0; cx.n_last = 0; cx.have_first = 0; cx.est_pre = cx.st.est;
         cx.wraps0 = cx.st.wraps;
-        fz_sel_put(selx, 1, (k_begin > 0) ? __ldcg(prm.sel + dgp->scr_off + k_begin - 1) : cx.st.last);     // :486-489
+        fz_sel_put(selx, 1, (k_begin > 0) ? prm.sel[dgp->scr_off + k_begin - 1] : cx.st.last);     // :486-489
         if (pk_a < pk_b) fz_prologue(cx, yh);
     }
     __syncwarp();
@@ -1803,50 +1793,6 @@ static __device__ __noinline__ void fzs_cb_end(const FzsCbParams& prm, const uns
     __syncwarp();
 }
 
-// one chain + back unit (fzs_cb_begin: an item of the time-parallel plan, or a whole channel)
-template <int PC>
-static __device__ __forceinline__ void fzs_cb_unit(const FzsCbParams& prm, const unsigned wofs, const int lane, const int u)
-{
-    using L = FzsCbL<PC>;
-    unsigned char* wb = fz_smem + wofs;
-    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
-    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
-    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
-    if (!fzs_cb_begin<PC>(prm, wofs, u)) return;
-    const float* thg = prm.theta + cx.desc->scr_off;
-    const float2* selg = prm.sel + cx.desc->scr_off;
-    for (;;) {
-        fz_drain<L>(wofs);
-        if (cx.unit_done) break;
-        // the next block of (angle, sample) pairs from the scratch, appended to the block buffer (ld.global.cg: in the
-        // task kernel the front units of the same launch wrote them, pskd_tp.cuh)
-        const int nbuf = cx.nbuf, kchain = cx.kchain, k0 = kchain + nbuf;
-        const int want = min(FZ_B, cx.pk_hi - kchain);
-        const int need = want - nbuf;
-        __syncwarp();
-        if (nbuf == 0 && need == FZ_B && ((reinterpret_cast<uintptr_t>(thg + k0) | reinterpret_cast<uintptr_t>(selg + k0)) & 15) == 0) {
-            // a full block at an aligned position (every block of a packet but its first and last)
-            const float4 t4 = __ldcg(reinterpret_cast<const float4*>(thg + k0) + lane);
-            const float4 s0 = __ldcg(reinterpret_cast<const float4*>(selg + k0) + lane);
-            const float4 s1 = __ldcg(reinterpret_cast<const float4*>(selg + k0) + 32 + lane);
-            reinterpret_cast<float4*>(th)[lane] = t4;
-            float2* sx2 = reinterpret_cast<float2*>(selx + 2);
-            float2* sy2 = reinterpret_cast<float2*>(selx + FZ_SELN + 2);
-            sx2[lane] = make_float2(s0.x, s0.z);      sy2[lane] = make_float2(s0.y, s0.w);
-            sx2[32 + lane] = make_float2(s1.x, s1.z); sy2[32 + lane] = make_float2(s1.y, s1.w);
-        } else {
-#pragma unroll
-            for (int q = 0; q < FZ_B / 32; q++) {
-                const int i = lane + 32 * q;
-                if (i < need) { th[nbuf + i] = __ldcg(thg + k0 + i); fz_sel_put(selx, 2 + nbuf + i, __ldcg(selg + k0 + i)); }
-            }
-        }
-        if (lane == 0) cx.nbuf = want;
-        __syncwarp();
-    }
-    fzs_cb_end<PC>(prm, wofs);
-}
-
 template <int PC>
 __global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZS_CB_MIN_CTAS)
 k_fzs_cb(const FzsCbParams prm)
@@ -1854,13 +1800,49 @@ k_fzs_cb(const FzsCbParams prm)
     using L = FzsCbL<PC>;
     const int lane = fz_lane();
     const unsigned wofs = (threadIdx.x >> 5) * (unsigned)L::BYTES;
+    unsigned char* wb = fz_smem + wofs;
+    float*  th   = reinterpret_cast<float*>(wb + L::OFF_TH);
+    float*  selx = reinterpret_cast<float*>(wb + L::OFF_SEL);
+    FzCtx&  cx   = *reinterpret_cast<FzCtx*>(wb + L::OFF_CTX);
     if (prm.tp.rerun && *prm.tp.any_rerun == 0) return;       // a repair round nobody asked for
+
     for (;;) {
         int u = 0;
         if (lane == 0) u = atomicAdd(prm.ticket, 1);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= prm.n_units) break;
-        fzs_cb_unit<PC>(prm, wofs, lane, u);
+        if (!fzs_cb_begin<PC>(prm, wofs, u)) continue;
+        const float* thg = prm.theta + cx.desc->scr_off;
+        const float2* selg = prm.sel + cx.desc->scr_off;
+        for (;;) {
+            fz_drain<L>(wofs);
+            if (cx.unit_done) break;
+            // the next block of (angle, sample) pairs from the scratch, appended to the block buffer
+            const int nbuf = cx.nbuf, kchain = cx.kchain, k0 = kchain + nbuf;
+            const int want = min(FZ_B, cx.pk_hi - kchain);
+            const int need = want - nbuf;
+            __syncwarp();
+            if (nbuf == 0 && need == FZ_B && ((reinterpret_cast<uintptr_t>(thg + k0) | reinterpret_cast<uintptr_t>(selg + k0)) & 15) == 0) {
+                // a full block at an aligned position (every block of a packet but its first and last)
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(thg + k0) + lane);
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(selg + k0) + lane);
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(selg + k0) + 32 + lane);
+                reinterpret_cast<float4*>(th)[lane] = t4;
+                float2* sx2 = reinterpret_cast<float2*>(selx + 2);
+                float2* sy2 = reinterpret_cast<float2*>(selx + FZ_SELN + 2);
+                sx2[lane] = make_float2(s0.x, s0.z);      sy2[lane] = make_float2(s0.y, s0.w);
+                sx2[32 + lane] = make_float2(s1.x, s1.z); sy2[32 + lane] = make_float2(s1.y, s1.w);
+            } else {
+#pragma unroll
+                for (int q = 0; q < FZ_B / 32; q++) {
+                    const int i = lane + 32 * q;
+                    if (i < need) { th[nbuf + i] = __ldg(thg + k0 + i); fz_sel_put(selx, 2 + nbuf + i, __ldg(selg + k0 + i)); }
+                }
+            }
+            if (lane == 0) cx.nbuf = want;
+            __syncwarp();
+        }
+        fzs_cb_end<PC>(prm, wofs);
     }
 }
 
@@ -1965,7 +1947,7 @@ static cudaError_t launch_fzs_front_t(const LaunchCtx& c) {
 }
 
 cudaError_t launch_fzs_front(const LaunchCtx& c) {
-    if (c.n_fzs_channels == 0 || c.Kmax_fzs <= 0 || c.fzs_uni) return cudaSuccess;    // (fzs_uni: the task kernel runs the front units)
+    if (c.n_fzs_channels == 0 || c.Kmax_fzs <= 0) return cudaSuccess;
     cudaError_t e = cudaSuccess;
     if (c.S_mask_fzs & (1ull << 8))  { e = launch_fzs_front_t<8>(c);  if (e != cudaSuccess) return e; }
     if (c.S_mask_fzs & (1ull << 9))  { e = launch_fzs_front_t<9>(c);  if (e != cudaSuccess) return e; }
@@ -2001,222 +1983,6 @@ static cudaError_t launch_fzs_cb_t(const LaunchCtx& c, const TpCtl& tp, int n_un
     c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
-}
-
-// =============================================================================================
-// k_fzs_uni<S,PC>: the time-parallel staged path as ONE persistent task kernel.  Run as two launches, the front
-// stage (HBM-bound) and the chain + back stage (latency-bound) leave the other resource idle in turn; here a
-// host-built task list interleaves
-//   F  front unit (fzs_front_unit: a segment of one channel),
-//   S  scan of one packet (tp_scan_item) -- the warp that completes a channel's last scan also resolves the
-//      channel (tp_resolve_chan),
-//   C  chain + back unit of one packet (fzs_cb_unit),
-// so that an SM works on both halves at once.  Warps take tasks in list order from a ticket counter.  A task
-// whose inputs are not there yet (S: all front units of its channel; C: its channel resolved) waits on a counter:
-// the list puts every task AFTER the tasks it depends on, so whatever a warp waits for is held by a running warp
-// (or done) -- no dependence on co-residency beyond the persistent grid, the argument of k_fused's unit order.
-// The list also keeps a distance (in tasks) between a task and its dependencies so that the wait is normally over
-// before it starts.  A wait that times out (it cannot, short of a fault) marks the channel failed: the sequential
-// re-run of k_tp_check / the fallback round then computes it.
-// =============================================================================================
-#ifndef PSKD_FZS_UNI_MIN_CTAS
-#define PSKD_FZS_UNI_MIN_CTAS 6
-#endif
-struct FzsUniParams {
-    FzsFrontParams f;                  // (its ticket is unused)
-    FzsCbParams c;                     // c.tp.items / chans / pkts: the plan; (its ticket and n_units are unused)
-    const int2* tasks; int n_tasks;    // x: 0 F, 1 S, 2 C; y: F: seg * n_channels + ch, S / C: item index
-    int* ticket;
-    int* f_done; int* s_done; int* resolved;       // [n_channels], zeroed before the launch
-};
-__device__ __forceinline__ int atom_add_release(int* p, int v) {
-    int o;
-    asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
-    return o;
-}
-__device__ __forceinline__ int atom_add_acq_rel(int* p, int v) {
-    int o;
-    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
-    return o;
-}
-// lane 0 polls until *p >= target; the shuffle hands the outcome (and the acquire's ordering) to the warp
-__device__ __forceinline__ bool uni_wait(const int* p, const int target, const int lane) {
-    int ok = 1;
-    if (lane == 0) {
-        int spins = 0;
-        while (ld_acquire(p) < target) {
-            __nanosleep(256);
-            if (++spins > (1 << 21)) { ok = 0; break; }
-        }
-    }
-    return __shfl_sync(0xffffffffu, ok, 0) != 0;
-}
-
-template <int S, int PC>
-__global__ void __launch_bounds__(FZ_WARPS * 32, PSKD_FZS_UNI_MIN_CTAS)
-k_fzs_uni(const FzsUniParams prm)
-{
-    constexpr unsigned BYTES = FzsFL<S>::BYTES > FzsCbL<PC>::BYTES ? FzsFL<S>::BYTES : FzsCbL<PC>::BYTES;
-    static_assert(BYTES % 128 == 0, "per-warp regions are whole 128-byte lines");
-    const int lane = fz_lane();
-    const unsigned wofs = (threadIdx.x >> 5) * BYTES;
-    unsigned char* wb = fz_smem + wofs;
-    const TpCtl& tp = prm.c.tp;
-    for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(prm.ticket, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= prm.n_tasks) break;
-        const int2 task = prm.tasks[t];
-        if (task.x == 0) {
-            const int seg = task.y / prm.f.n_channels, ch = task.y - seg * prm.f.n_channels;
-            fzs_front_unit<S>(prm.f, wb, lane, ch, seg);
-            __syncwarp();
-            if (lane == 0) (void)atom_add_release(prm.f_done + ch, 1);
-        } else if (task.x == 1) {
-            const TpItem it = tp.items[task.y];
-            const TpChan tc = tp.chans[it.chan];
-            const int K = (int)prm.c.desc[it.ch].K;
-            const int nF = (K + prm.f.seg_syms - 1) / prm.f.seg_syms;
-            if (!uni_wait(prm.f_done + it.ch, nF, lane)) { if (lane == 0) tp.fail[it.ch] = 1; continue; }
-            tp_scan_item(prm.c.desc, prm.c.theta, it, tp.pkts, lane);
-            __syncwarp();
-            int last = 0;
-            if (lane == 0) last = (atom_add_acq_rel(prm.s_done + it.ch, 1) == tc.n_pkts - tc.pkt0 - 1) ? 1 : 0;
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last) {                                  // every packet of the channel is scanned: its levels and wraps
-                tp_resolve_chan(prm.c.desc, prm.c.theta, tc, tp.pkts, tp.ends, prm.c.state, lane);
-                __syncwarp();
-                if (lane == 0) st_release(prm.resolved + it.ch, 1);
-            }
-        } else {
-            const int ch = tp.items[task.y].ch;
-            if (!uni_wait(prm.resolved + ch, 1, lane)) { if (lane == 0) tp.fail[ch] = 1; continue; }
-            fzs_cb_unit<PC>(prm.c, wofs, lane, task.y);
-        }
-        __syncwarp();
-    }
-}
-
-// does this slab's staged work go through the task kernel?  Every CH_FZS channel must be a head-less time-parallel
-// channel, nothing time-parallel may belong to the legacy kernels, and there must be enough front work for a steady
-// state (a few waves of units); PSKD_FZS_UNI=0 (read at pskd_create) switches it off, 2 drops the size condition.
-bool fzs_uni_eligible(const LaunchCtx& c) {
-    const int mode = c.fzs_uni_mode;
-    if (mode == 0 || c.n_fzs_channels <= 0 || c.tp_n_chans <= 0 || c.tp_n_head != 0) return false;
-    if (c.tp_n_chans_fzs != c.tp_n_chans || c.n_fzs_channels != c.tp_n_chans_fzs) return false;
-    if (!c.h_tp_items || !c.h_tp_chans || !c.d_uni_tasks || !c.d_uni_ctr) return false;
-    int dev = 0, n_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
-    const long long slots = (long long)n_sm * PSKD_FZS_UNI_MIN_CTAS * FZ_WARPS;
-    return mode >= 2 || c.Kmax_fzs * c.n_fzs_channels >= 3 * 1024 * slots;
-}
-
-template <int S, int PC>
-static cudaError_t launch_fzs_uni_t(const LaunchCtx& c, const TpCtl& tp, double alg_bytes) {
-    constexpr size_t BYTES = FzsFL<S>::BYTES > FzsCbL<PC>::BYTES ? FzsFL<S>::BYTES : FzsCbL<PC>::BYTES;
-    const size_t smem = BYTES * FZ_WARPS;
-    static KernelCfg cfg;
-    int ctas_per_sm = 0, n_sm = 0;
-    cudaError_t e = cfg.ensure(k_fzs_uni<S, PC>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm);
-    if (e != cudaSuccess) return e;
-    const long long slots = (long long)n_sm * ctas_per_sm * FZ_WARPS;
-    // the channels of this samples-per-symbol class, in plan order; their items follow each other in the item array
-    struct Chan { int ch, np, item0, nF; };
-    std::vector<Chan> chans;
-    long long k_total = 0;
-    {
-        int item0 = 0;
-        for (int ci = 0; ci < c.tp_n_chans; ci++) {
-            const TpChan& tc = c.h_tp_chans[ci];
-            const int np = tc.n_pkts - tc.pkt0;
-            const ChanDesc& d = c.h_desc[tc.ch];
-            if ((d.flags & CH_FZS) && d.S == S && d.K > 0) { chans.push_back(Chan{tc.ch, np, item0, 0}); k_total += d.K; }
-            item0 += np;
-        }
-    }
-    if (chans.empty()) return cudaSuccess;
-    FzsUniParams p{};
-    p.f.desc = c.d_desc; p.f.n_channels = c.n_channels;
-    static const int seg_env = getenv("PSKD_FZS_SEG") ? atoi(getenv("PSKD_FZS_SEG")) : 0;
-    long long seg = seg_env > 0 ? seg_env : k_total / (8 * slots);
-    seg = (seg + 31) & ~31LL;
-    if (seg < 1024) seg = 1024;
-    if (seg > 8192 && seg_env <= 0) seg = 8192;
-    p.f.seg_syms = (int)seg;
-    p.f.sel = c.d_sel; p.f.theta = c.d_theta; p.f.out_sidx = c.out_sidx;
-    p.c.desc = c.d_desc; p.c.state = c.d_state; p.c.ring_base = c.d_ring; p.c.n_channels = c.n_channels;
-    p.c.sel = c.d_sel; p.c.theta = c.d_theta;
-    p.c.out_soft = (float2*)c.out_soft; p.c.out_bits = c.out_bits; p.c.out_phase = c.out_phase; p.c.out_hard = c.out_hard;
-    p.c.sri_xdelta = c.sri_xdelta; p.c.counters = c.d_counters;
-    p.c.tp = tp;
-    // ---- the task list: front units channel after channel; a channel's scans at least lagF tasks after its last front
-    // unit, its chain units at least lagS tasks after its last scan (released tasks go first: they finish channels)
-    static const int lag_env = getenv("PSKD_FZS_UNI_LAG") ? atoi(getenv("PSKD_FZS_UNI_LAG")) : 0;       // tuning: % of the resident warps
-    const long long lagF = slots * (lag_env > 0 ? lag_env : 125) / 100, lagS = slots / 4;
-    std::vector<int2> tasks;
-    {
-        long long n_front = 0;
-        for (Chan& ch : chans) { ch.nF = (int)((c.h_desc[ch.ch].K + seg - 1) / seg); n_front += ch.nF; }
-        long long n_items = 0;
-        for (const Chan& ch : chans) n_items += ch.np;
-        const long long total = n_front + 2 * n_items;
-        if (total > (long long)c.uni_tasks_cap || total > 0x7fffffffLL) return cudaErrorInvalidValue;
-        tasks.reserve((size_t)total);
-        struct Rel { long long pos; int chan; };
-        std::vector<Rel> sq, cq;                         // channels whose scans / chain units wait for their release position
-        size_t sh = 0, ch_ = 0;                          // heads of the two queues
-        int s_next = 0, c_next = 0;                      // next packet of the queue's head channel
-        size_t fc = 0; int fs = 0;                       // next front unit: channel fc, segment fs
-        while ((long long)tasks.size() < total) {
-            const long long pos = (long long)tasks.size();
-            const bool f_left = fc < chans.size();
-            if (ch_ < cq.size() && (cq[ch_].pos <= pos || (!f_left && sh >= sq.size()))) {
-                const Chan& k = chans[cq[ch_].chan];
-                tasks.push_back(make_int2(2, k.item0 + c_next));
-                if (++c_next == k.np) { c_next = 0; ch_++; }
-            } else if (sh < sq.size() && (sq[sh].pos <= pos || !f_left)) {
-                const Chan& k = chans[sq[sh].chan];
-                tasks.push_back(make_int2(1, k.item0 + s_next));
-                if (++s_next == k.np) { cq.push_back(Rel{pos + 1 + lagS, sq[sh].chan}); s_next = 0; sh++; }
-            } else if (f_left) {
-                const Chan& k = chans[fc];
-                tasks.push_back(make_int2(0, fs * c.n_channels + k.ch));
-                if (++fs == k.nF) { sq.push_back(Rel{pos + 1 + lagF, (int)fc}); fs = 0; fc++; }
-            } else break;                                // (cannot happen: every channel passes through both queues)
-        }
-        if ((long long)tasks.size() != total) return cudaErrorInvalidValue;
-    }
-    p.tasks = c.d_uni_tasks; p.n_tasks = (int)tasks.size();
-    p.ticket = fzs_take_ticket(c);
-    if (!p.ticket) return cudaErrorInvalidValue;
-    p.f_done = c.d_uni_ctr; p.s_done = c.d_uni_ctr + c.n_channels; p.resolved = c.d_uni_ctr + 2 * (size_t)c.n_channels;
-    e = cudaMemcpyAsync(c.d_uni_tasks, tasks.data(), sizeof(int2) * tasks.size(), cudaMemcpyHostToDevice, c.stream);   // pageable: staged before the call returns
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(c.d_uni_ctr, 0, sizeof(int) * 3 * (size_t)c.n_channels, c.stream);
-    if (e != cudaSuccess) return e;
-    int grid = n_sm * ctas_per_sm;
-    const int need = (p.n_tasks + FZ_WARPS - 1) / FZ_WARPS;
-    if (grid > need) grid = need;
-    if (grid < 1) grid = 1;
-    c.prof->begin(KID_FZS_UNI, c.stream, alg_bytes);
-    k_fzs_uni<S, PC><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
-    c.prof->end(c.stream);
-    (*c.launches)++;
-    return cudaGetLastError();
-}
-
-// the task kernel over the slab's time-parallel channels, one launch per samples-per-symbol class
-cudaError_t launch_fzs_uni(const LaunchCtx& c, const TpCtl& tp, double alg_bytes) {
-    cudaError_t e = cudaSuccess;
-    int n_classes = 0;
-    for (int s : {8, 9, 10, 16}) if (c.S_mask_fzs & (1ull << s)) n_classes++;
-    const double ab = n_classes > 0 ? alg_bytes / n_classes : 0.0;     // (profiling: the classes share one kernel id)
-    const bool small = c.Pmax_fzs <= 52;
-#define PSKD_UNI(SV) if (e == cudaSuccess && (c.S_mask_fzs & (1ull << SV))) e = small ? launch_fzs_uni_t<SV, 52>(c, tp, ab) : launch_fzs_uni_t<SV, 128>(c, tp, ab);
-    PSKD_UNI(8) PSKD_UNI(9) PSKD_UNI(10) PSKD_UNI(16)
-#undef PSKD_UNI
-    return e;
 }
 
 // one launch of the chain + back kernel: tp.items != null -> one unit per item, else one unit per channel

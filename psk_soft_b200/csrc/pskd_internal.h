@@ -82,7 +82,7 @@ struct TpItem {            // one warp of work for k_chain_par
     int src;               // kind 2: end record to start from; kind 1: end record holding the channel's fit constants (< 0: state[ch])
     int dst;               // end record this item writes
     int pkt_slot;          // index of packet pk_a in the TpPacket array
-    int chan;              // index of the channel's TpChan (slab-relative, like ch)
+    int pad;
 };
 struct TpPacket {          // per (channel, packet) of the time-parallel range
     int cEnd;              // classic unwrap count at the packet's last symbol, relative to its first symbol
@@ -125,7 +125,7 @@ struct TpCtl {
 };
 
 // ---- optional per-kernel event timing --------------------------------------------------------
-enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_FUSED, KID_TP, KID_FZS_FRONT, KID_FZS_CB, KID_FUSED_S9, KID_FUSED_S10, KID_FUSED_S16, KID_FZS_UNI, KID_COUNT };
+enum KernelId { KID_FRONT = 0, KID_CHAIN_SEQ, KID_CHAIN_PAR, KID_BACK_PAR, KID_CHAIN_EXACT, KID_BACK, KID_FINISH, KID_FUSED, KID_TP, KID_FZS_FRONT, KID_FZS_CB, KID_FUSED_S9, KID_FUSED_S10, KID_FUSED_S16, KID_COUNT };
 struct Profiler {
     bool enabled = false;
     struct Pair { cudaEvent_t a, b; int kid; };
@@ -217,12 +217,6 @@ struct LaunchCtx {
     int* d_fzs_ticket;       // zeroed ticket counters for this call's k_fzs_* launches
     int* fzs_ticket_next;    // host-side index of the next unused counter
     int fzs_ticket_cap;
-    // task kernel k_fzs_uni (front units, packet scans and chain units of the time-parallel channels in ONE launch)
-    int fzs_uni_mode;        // PSKD_FZS_UNI at pskd_create: 0 off, 1 when there is enough work for a steady state, 2 whenever possible
-    bool fzs_uni;            // this slab takes it (fzs_uni_eligible)
-    const TpItem* h_tp_items; const TpChan* h_tp_chans;      // host mirrors of tp_items / tp_chans
-    int2* d_uni_tasks; size_t uni_tasks_cap;                 // task list, rebuilt per launch
-    int* d_uni_ctr;          // [3 * n_channels] front units done / packets scanned / resolved, zeroed per launch
 };
 
 // one launch of the fused kernel: the CH_FUSED channels of one samplesPerBaud value
@@ -248,8 +242,6 @@ cudaError_t launch_fused(const LaunchCtx& c, const FusedLaunch& f);
 
 cudaError_t launch_fzs_front(const LaunchCtx& c);
 cudaError_t launch_fzs_cb(const LaunchCtx& c, const TpCtl& tp, int n_units, double alg_bytes = 0.0);
-bool fzs_uni_eligible(const LaunchCtx& c);
-cudaError_t launch_fzs_uni(const LaunchCtx& c, const TpCtl& tp, double alg_bytes = 0.0);
 bool fzs_supports(int S, int A, int P);
 
 cudaError_t launch_front(const LaunchCtx& c);

@@ -9,16 +9,14 @@ from parity import assert_parity
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["fused", "staged", "tp", "uni", "legacy"], autouse=True)
+@pytest.fixture(params=["fused", "staged", "tp", "legacy"], autouse=True)
 def fused_mode(request, monkeypatch):
     """every test of this module runs through the fused kernel, the staged kernels (k_fzs_front +
-    k_fzs_cb), the staged kernels with the time-parallel chain as two launches and as the task kernel
-    k_fzs_uni (every call whose channels carry a full history), and the legacy staged kernels
+    k_fzs_cb), the staged kernels with the time-parallel chain, and the legacy staged kernels
     (PSKD_FZS=0: k_front_t + k_chain_par + k_back_par, time-parallel chain on)"""
     monkeypatch.setenv("PSKD_FUSED", "1" if request.param == "fused" else "0")
-    monkeypatch.setenv("PSKD_TP", "1" if request.param in ("tp", "uni", "legacy") else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if request.param in ("tp", "legacy") else "0")
     monkeypatch.setenv("PSKD_FZS", "0" if request.param == "legacy" else "1")
-    monkeypatch.setenv("PSKD_FZS_UNI", "2" if request.param == "uni" else "0")
     return request.param
 
 

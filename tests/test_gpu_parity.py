@@ -23,7 +23,7 @@ CASES = [
 ]
 
 
-@pytest.fixture(params=["fused", "tp", "uni", "par", "seq", "legacy_tp", "legacy_par"])
+@pytest.fixture(params=["fused", "tp", "par", "seq", "legacy_tp", "legacy_par"])
 def chain_mode(request, monkeypatch):
     """run every case through the fused kernel (where the configuration qualifies), the staged
     kernels (k_fzs_front + k_fzs_cb where the configuration qualifies) with the time-parallel chain
@@ -33,9 +33,8 @@ def chain_mode(request, monkeypatch):
     mode = request.param
     monkeypatch.setenv("PSKD_CHAIN", "seq" if mode == "seq" else "par")
     monkeypatch.setenv("PSKD_FUSED", "1" if mode == "fused" else "0")
-    monkeypatch.setenv("PSKD_TP", "1" if mode in ("tp", "uni", "legacy_tp") else "0")
+    monkeypatch.setenv("PSKD_TP", "1" if mode in ("tp", "legacy_tp") else "0")
     monkeypatch.setenv("PSKD_FZS", "0" if mode.startswith("legacy") else "1")
-    monkeypatch.setenv("PSKD_FZS_UNI", "2" if mode == "uni" else "0")      # the time-parallel chain as the task kernel k_fzs_uni
     return mode
 
 
@@ -257,41 +256,3 @@ def test_time_parallel_repair_round(oracle_built, monkeypatch):
     assert st["tp_packets"] > 0
     assert st["tp_repaired"] + st["seq_channels"] > 0, st         # the steps really broke some hand-overs ...
     assert st["seq_channels"] <= st["tp_repaired"], st            # ... and the repair round fixed (most of) them
-
-
-@pytest.mark.parametrize("cfg", [dict(S=8, M=8, D=0), dict(S=10, M=2, D=0), dict(S=9, M=4, D=1)], ids=lambda c: f"S{c['S']}M{c['M']}D{c['D']}")
-def test_task_kernel_stream(cfg, oracle_built, monkeypatch):
-    """the time-parallel staged path as ONE task kernel (k_fzs_uni: front units, packet scans, resolves and chain units
-    interleaved in a launch): a stream fed in three calls -- the first builds the history (sequential heads, two launches),
-    the others are head-less and must go through the task kernel -- with phase steps of about pi in some channels, so that
-    the repair round runs behind it as well.  Result: the reference's."""
-    import psk_soft_b200 as pk
-    monkeypatch.setenv("PSKD_FUSED", "0")
-    monkeypatch.setenv("PSKD_TP", "1")
-    monkeypatch.setenv("PSKD_FZS_UNI", "2")
-    rs = np.random.RandomState(5)
-    S, M, D = cfg["S"], cfg["M"], cfg["D"]
-    nch, n, pkt = 40, 3 * 96000, 12000
-    props = dict(samplesPerBaud=S, constelationSize=M, numAvg=60, phaseAvg=40, differentialDecoding=D)
-    iqs = []
-    for c in range(nch):
-        a = siggen.gen_shaped(n, S, M, seed=300 + c, sigma=0.03, freq=2e-5 * ((c % 7) - 3), timing_shift=c % S)
-        if c % 4 == 0:                                                                  # a level slip for the repair round
-            cut = 96000 + int(rs.randint(1, 7)) * pkt + int(rs.randint(1000, 11000))
-            ph = np.ones(n, np.complex64); ph[cut:] = np.exp(1j * (np.pi + float(rs.uniform(-0.3, 0.3))) / M)
-            a = (a * ph).astype(np.complex64)
-        iqs.append(a)
-    iqs = np.stack(iqs)
-    bank = pk.Bank(nch, props)
-    bank.profile_enable(True)
-    parts = [bank.process_host(iqs[:, k * 96000:(k + 1) * 96000], xdelta=0.01, packet_len=pkt) for k in range(3)]
-    prof = bank.profile_read()
-    st = bank.stats()
-    print("stats", st, {k: v[1] for k, v in prof.items() if v[1]})
-    assert prof.get("k_fzs_uni", (0, 0, 0))[1] >= 2, prof          # the two head-less calls took the task kernel
-    for c in range(nch):
-        comp = oracle_built.OracleComponent(**props)
-        for k in range(3):
-            ref = comp.demod(iqs[c, k * 96000:(k + 1) * 96000], packet_len=pkt, xdelta=0.01)
-            assert_parity(parts[k][c], ref, tag=f"task kernel, channel {c}, call {k}")
-    assert st["tp_packets"] > 0
