@@ -1824,6 +1824,14 @@ k_fzs_cb(const FzsCbParams prm)
             __syncwarp();
             if (nbuf == 0 && need == FZ_B && ((reinterpret_cast<uintptr_t>(thg + k0) | reinterpret_cast<uintptr_t>(selg + k0)) & 15) == 0) {
                 // a full block at an aligned position (every block of a packet but its first and last)
+#ifndef PSKD_FZS_CB_NO_PF
+                // the block after it towards L2 (the scratch of a large call has left L2 by the time the chain reads it: an
+                // HBM round trip per block otherwise, a fifth of this kernel's stall cycles)
+                if (lane == 0 && k0 + 2 * FZ_B <= cx.pk_hi) {
+                    fz_prefetch_l2(thg + k0 + FZ_B, FZ_B * 4u);
+                    fz_prefetch_l2(selg + k0 + FZ_B, FZ_B * 8u);
+                }
+#endif
                 const float4 t4 = __ldg(reinterpret_cast<const float4*>(thg + k0) + lane);
                 const float4 s0 = __ldg(reinterpret_cast<const float4*>(selg + k0) + lane);
                 const float4 s1 = __ldg(reinterpret_cast<const float4*>(selg + k0) + 32 + lane);
