@@ -83,42 +83,90 @@ def channel_cost(p, samples):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+    """SM clock, board power and clock-event reasons while the timed region runs (B200_PROFILING.md): NVML every 5 ms
+    (nvidia-smi's fastest loop, 100 ms, sees a 0.1 - 0.3 s timed region two or three times), `nvidia-smi -lms 100` when
+    pynvml is missing.  Also reads NVML's energy counter, so the line can say what a step costs in joules: on this board
+    the fused kernel runs into the 1000 W power cap after a few steps (tools/probe/step_trace.py) and its step time then
+    follows the clock the cap leaves it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, period=0.005):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.period = period
+        self.rows = []                 # (time, sm_mhz, watts, set of reasons)
+        self.sm_max = None
         self.proc = None
+        self.go = True
+        self.nv = self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index(pynvml, gpu_index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:              # noqa: BLE001  (no pynvml / no NVML: nvidia-smi below)
+            self.nv = self.h = None
+
+    @staticmethod
+    def _nvml_index(nv, cuda_index):
+        """NVML enumerates every board; CUDA only those in CUDA_VISIBLE_DEVICES"""
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "").strip()
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if cuda_index < len(ids) and ids[cuda_index].isdigit():
+                return int(ids[cuda_index])
+        return cuda_index
+
+    def energy_j(self):
+        try:
+            return self.nv.nvmlDeviceGetTotalEnergyConsumption(self.h) / 1e3 if self.nv else None
+        except Exception:              # noqa: BLE001
+            return None
 
     def run(self):
+        if self.nv:
+            nv, h = self.nv, self.h
+            reasons_of = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while self.go:
+                try:
+                    r = int(reasons_of(h))
+                    self.rows.append((time.time(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                      nv.nvmlDeviceGetPowerUsage(h) / 1e3, {n for n, b in self.BITS if r & b}))
+                except Exception:      # noqa: BLE001
+                    pass
+                time.sleep(self.period)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
-        except Exception:
+                r = [x.strip() for x in line.split(",")]
+                if len(r) >= 9:
+                    self.sm_max = float(r[2])
+                    self.rows.append((time.time(), float(r[1]), float(r[3]),
+                                      {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9])
+                                       if v.lower().startswith("active")}))
+        except Exception:              # noqa: BLE001
             pass
 
     def stop(self):
+        self.go = False
         if self.proc:
             self.proc.terminate()
 
     def summary(self, t0, t1):
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or \
-               [r for (_, r) in self.rows if len(r) >= 9]
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in rows)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (neither NVML nor nvidia-smi)"]}
+        sm = sorted(r[1] for r in rows)
         reasons = set()
         for r in rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
-                "samples": len(rows), "reasons": sorted(reasons)}
+            reasons |= r[3]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "sm_mhz_min": sm[0], "power_w_max": max(r[2] for r in rows),
+                "samples": len(rows), "source": "NVML, every 5 ms" if self.nv else "nvidia-smi -lms 100", "reasons": sorted(reasons)}
 
 
 def bind_to_gpu_numa_node(torch, dev):
@@ -388,26 +436,35 @@ def main():
     time.sleep(0.3)
     launches0 = bank.launch_count if bank else 0
     t_wall0 = time.time()
+    e_j0 = sampler.energy_j()
     ms_total = timed(args.steps)
+    e_j1 = sampler.energy_j()
     t_wall1 = time.time()
     launches = (bank.launch_count - launches0) if bank else 0
     ms_step = ms_total / args.steps
     total_samples = (nch_global if (scaling == "strong" or world == 1) else world * nch_global) * n
     value = total_samples / (ms_step * 1e-3) / 1e6
 
-    # ---- pass 2: per-kernel split with CUDA events around every launch (not part of `value`) --------------
+    # ---- pass 2: the same K steps again with CUDA events around every launch (per-kernel split; not part of `value`).
+    # Same protocol as pass 1 -- a 0.3 s pause, then K steps back to back: the board's power management makes the
+    # step time depend on how long the GPU has been under load (tools/probe/step_trace.py), so a kernel time taken
+    # from fewer steps, or right behind pass 1, is not the time of the steps `value` was measured on.
     peak, peak_src = measured_peak()
     roof = None
     kern = {}
+    ms_step2 = None
+    psteps = args.steps
+    t_wall2 = t_wall2b = t_wall1
     if bank:
         bank.profile_read(reset=True)
         bank.profile_enable(True)
-        psteps = max(1, min(args.steps, 3))
-        timed(psteps)
+        time.sleep(0.3)
+        t_wall2 = time.time()
+        ms_step2 = timed(psteps) / psteps
+        t_wall2b = time.time()
         kern = bank.profile_read(reset=True)
         bank.profile_enable(False)
-    t_wall2 = time.time()                                       # the clock samples cover both passes (the same steps, back to back)
-    time.sleep(0.15)
+    time.sleep(0.05)
     sampler.stop()
     stats = bank.stats() if bank else {}
     if kern:
@@ -426,10 +483,10 @@ def main():
             traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_dom / max(n_dom, 1),
-                "ms_per_launch": ms_launch, "launches_per_step": lps,
+                "ms_per_launch": ms_launch, "launches_per_step": lps, "ms_per_step_profiled_pass": ms_step2,
                 "note": "achieved = algorithmic bytes (SURVEY 8d, split per stage) of the channels this kernel served / its "
-                        "CUDA-event time, both from a second pass with events around every launch (rank 0's shard); `value` "
-                        "is measured without them",
+                        "CUDA-event time, both from a second pass of the same K steps with events around every launch (rank 0's "
+                        "shard); `value` is measured without them",
                 "kernel_ms_per_step": {k: v[0] / psteps for k, v in kern.items()},
                 "kernel_gbs": {k: (v[2] / v[0] / 1e6 if v[0] > 0 and v[2] > 0 else None) for k, v in kern.items()},
                 "whole_path": {"algorithmic_bytes_per_step": abytes_step,
@@ -512,7 +569,12 @@ def main():
                "single_core_value": rate1}
 
     if rank == 0:
-        clocks = sampler.summary(t_wall0, t_wall2)
+        clocks = sampler.summary(t_wall0, t_wall1)              # the timed region of `value`
+        clocks["profiled_pass"] = {k: v for k, v in sampler.summary(t_wall2, t_wall2b).items()
+                                   if k in ("sm_mhz", "sm_mhz_min", "power_w_max", "samples", "reasons")}
+        if e_j0 is not None and e_j1 is not None:
+            clocks["joule_per_step"] = (e_j1 - e_j0) / args.steps
+            clocks["watt_avg"] = (e_j1 - e_j0) / max(t_wall1 - t_wall0, 1e-9)
         cfg = config_of(args, w, world, scaling, nch_global)
         line = {"metric": "Msamples/s demodulated", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
