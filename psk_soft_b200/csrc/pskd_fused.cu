@@ -426,7 +426,7 @@ static __device__ __noinline__ void fz_back_pairs(const unsigned wofs, const int
     float4*   __restrict__ cst4 = reinterpret_cast<float4*>(wb + L::OFF_ALIAS);                    // soft staging [FZ_B]
     unsigned* __restrict__ bst  = reinterpret_cast<unsigned*>(wb + L::OFF_ALIAS + FZ_B * 8);       // bits staging [FZ_B * 3] int16
     unsigned short* __restrict__ hst2 = reinterpret_cast<unsigned short*>(wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6);   // packed hard symbols
-    const float ninv_m = -1.0f / (float)M;
+    const float ninv_m = (M == 8) ? -0.125f : (M == 4) ? -0.25f : (M == 2) ? -0.5f : -1.0f / (float)M;   // (the same floats, without the division)
     const bool inexact = (BPB == 0 && (M & (M - 1)) != 0);                 // -est/M not an exact multiply
     const int npairs = (m + 1) >> 1;
 #pragma unroll 1
@@ -597,9 +597,12 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
                 el[v] = fit_eval_fast(fc, Ys[v], Xl[v], nullptr, nullptr);   // :135-162
             }
         }
-        Yv = Ys[0]; Xv = Xl[0];
+        if (m == FZ_B) { Yv = Ys[3]; Xv = Xl[3]; }           // a full block ends on the owner lane's last symbol
+        else {
+            Yv = Ys[0]; Xv = Xl[0];
 #pragma unroll
-        for (int v = 1; v < 4; v++) if (v == (last & 3)) { Yv = Ys[v]; Xv = Xl[v]; }
+            for (int v = 1; v < 4; v++) if (v == (last & 3)) { Yv = Ys[v]; Xv = Xl[v]; }
+        }
         // verify every predicted n against the reference's rule (:477) with est_{i-1}
         const float eprev = __shfl_up_sync(0xffffffffu, el[3], 1);
         int mymis = 0x7fffffff, mydelta = 0;
@@ -612,6 +615,11 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
 #pragma unroll
                 for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count_slow((v == 0) ? eprev : el[v - 1], tl[v]);
             }
+            // the usual outcome -- every count agrees -- costs one vote; only a disagreement pays for locating its first symbol
+            bool differs = false;
+#pragma unroll
+            for (int v = 0; v < 4; v++) differs = differs || (nt[v] != nloc[v] && i0 + v < m && (v > 0 || lane > 0));
+            if (!__any_sync(0xffffffffu, differs)) { done = true; break; }
 #pragma unroll
             for (int v = 3; v >= 0; v--) {
                 const int i = i0 + v;
@@ -639,9 +647,12 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
         cx.st.est = fit_eval_fast(fc, Yv, Xv, &mm, &bb);
         f.ySum = Yv; f.xySum = Xv; f.m = mm; f.b = bb; f.count += m;
         if (L::TRACK_N) {                      // the verified (= the reference's) count of the block's last symbol
-            int nl = nloc[0];
+            int nl = nloc[3];
+            if (m != FZ_B) {
+                nl = nloc[0];
 #pragma unroll
-            for (int v = 1; v < 4; v++) if (v == (last & 3)) nl = nloc[v];
+                for (int v = 1; v < 4; v++) if (v == (last & 3)) nl = nloc[v];
+            }
             cx.n_last = nl;
         }
     }
@@ -654,6 +665,19 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
     }
     __syncwarp();
     // new history = last P of (history ++ block): shift the prefix and the values by m
+    if (m > P) {
+        // every full block: the new history comes from the block alone, and what is read (the block's prefix sums and
+        // values) does not overlap what is written (the history areas): no read-all-then-write passes
+        const double* src = czblk + (m - P - 1);             // src[j] = cz[m + j]
+        const float* ysrc = yblk + (m - P);
+        const double czm_b = src[0];
+        for (int j = lane; j <= P; j += 32) {
+            cz[j] = dsubr(src[j], czm_b);
+            if (j < P) yh[j] = ysrc[j];
+        }
+        __syncwarp();
+        return true;
+    }
     const double czm = cz[m];
     for (int base = 0; base <= P; base += 32) {
         const int j = base + lane;
