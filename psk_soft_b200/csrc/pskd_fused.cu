@@ -597,16 +597,29 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
                 el[v] = fit_eval_fast(fc, Ys[v], Xl[v], nullptr, nullptr);   // :135-162
             }
         }
-        if (m == FZ_B) { Yv = Ys[3]; Xv = Xl[3]; }           // a full block ends on the owner lane's last symbol
-        else {
-            Yv = Ys[0]; Xv = Xl[0];
-#pragma unroll
-            for (int v = 1; v < 4; v++) if (v == (last & 3)) { Yv = Ys[v]; Xv = Xl[v]; }
+        Yv = Ys[3]; Xv = Xl[3];                               // a full block ends on the owner lane's last symbol
+        if (m != FZ_B) {                                      // (overriding assignments, not Ys[last & 3]: an index the compiler
+            const int lv = last & 3;                          // cannot resolve puts the arrays into local memory on the hot path)
+            if (lv < 3) { Yv = Ys[2]; Xv = Xl[2]; }
+            if (lv < 2) { Yv = Ys[1]; Xv = Xl[1]; }
+            if (lv < 1) { Yv = Ys[0]; Xv = Xl[0]; }
         }
         // verify every predicted n against the reference's rule (:477) with est_{i-1}
         const float eprev = __shfl_up_sync(0xffffffffu, el[3], 1);
         int mymis = 0x7fffffff, mydelta = 0;
         {
+            // the usual outcome -- every predicted count is the reference's -- is established without forming the counts:
+            // |(est_{i-1} - theta_i) / 2pi - n_i| < 0.4999999 means round() of that quotient is n_i, and not by a hair (the
+            // quotient by multiplication is within 1e-15 of the divided one).  One vote; only a count that is off, or next
+            // to a half-integer, pays for the exact counts and for locating the first symbol that disagrees.
+            bool differs = false;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const double dlt = dsubr((double)((v == 0) ? eprev : el[v - 1]), (double)tl[v]);       // exact
+                const double dq = dsubr(dmulr(dlt, 0.15915494309189535), (double)nloc[v]);
+                differs = differs || (!(fabs(dq) < 0.4999999) && i0 + v < m && (v > 0 || lane > 0));
+            }
+            if (!__any_sync(0xffffffffu, differs)) { done = true; break; }
             int nt[4];
             bool knife = false;
 #pragma unroll
@@ -615,11 +628,6 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
 #pragma unroll
                 for (int v = 0; v < 4; v++) nt[v] = fz_unwrap_count_slow((v == 0) ? eprev : el[v - 1], tl[v]);
             }
-            // the usual outcome -- every count agrees -- costs one vote; only a disagreement pays for locating its first symbol
-            bool differs = false;
-#pragma unroll
-            for (int v = 0; v < 4; v++) differs = differs || (nt[v] != nloc[v] && i0 + v < m && (v > 0 || lane > 0));
-            if (!__any_sync(0xffffffffu, differs)) { done = true; break; }
 #pragma unroll
             for (int v = 3; v >= 0; v--) {
                 const int i = i0 + v;
@@ -649,9 +657,10 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
         if (L::TRACK_N) {                      // the verified (= the reference's) count of the block's last symbol
             int nl = nloc[3];
             if (m != FZ_B) {
-                nl = nloc[0];
-#pragma unroll
-                for (int v = 1; v < 4; v++) if (v == (last & 3)) nl = nloc[v];
+                const int lv = last & 3;
+                if (lv < 3) nl = nloc[2];
+                if (lv < 2) nl = nloc[1];
+                if (lv < 1) nl = nloc[0];
             }
             cx.n_last = nl;
         }
@@ -869,12 +878,12 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
             m = 1048576 - cnt;                                                      // stop at the re-sum point
         }
         if (!fast) m = min(m, max(1, P - pts));                                     // fill-up runs sequentially
-        const float2 prev_new = fz_sel_get(selx, 2 + m - 1);
         bool done = false;
         if (fast) done = fz_chain_fast<L>(wofs, m);
         if (!done) fz_chain_slow<L>(wofs, m);
         if (lane == 0) cx.blocks++;
         fz_back_block<L>(wofs, m);
+        const float2 prev_new = fz_sel_get(selx, 2 + m - 1);       // (the stages above leave the samples alone)
         // ---- drop the consumed symbols from the buffer ------------------------------------------------
         const int left = nbuf - m;
         for (int base = 0; base < left; base += 32) {
@@ -887,6 +896,7 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
         }
         if (lane == 0) { fz_sel_put(selx, 1, prev_new); cx.nbuf = left; cx.kchain = kchain + m; }
         __syncwarp();
+        if (left == 0 && m < rem) break;      // buffer empty, packet not exhausted: the next block has to be collected first
     }
 }
 
