@@ -85,7 +85,7 @@ def channel_cost(p, samples):
 class ClockSampler(threading.Thread):
     """SM clock, board power and clock-event reasons while the timed region runs (B200_PROFILING.md): NVML every 5 ms
     (nvidia-smi's fastest loop, 100 ms, sees a 0.1 - 0.3 s timed region two or three times), `nvidia-smi -lms 100` when
-    pynvml is missing.  Also reads NVML's energy counter, so the line can say what a step costs in joules: on this board
+    pynvml is missing.  Also reads NVML's energy counter (reported for timed regions of a second or more): on this board
     the fused kernel runs into the 1000 W power cap after a few steps (tools/probe/step_trace.py) and its step time then
     follows the clock the cap leaves it."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -572,7 +572,9 @@ def main():
         clocks = sampler.summary(t_wall0, t_wall1)              # the timed region of `value`
         clocks["profiled_pass"] = {k: v for k, v in sampler.summary(t_wall2, t_wall2b).items()
                                    if k in ("sm_mhz", "sm_mhz_min", "power_w_max", "samples", "reasons")}
-        if e_j0 is not None and e_j1 is not None:
+        if e_j0 is not None and e_j1 is not None and t_wall1 - t_wall0 >= 1.0:
+            # NVML's energy counter advances in steps of ~0.1 s: only a timed region of a second or more is resolved
+            # (tools/probe/step_trace.py measures joules per step over 120 steps)
             clocks["joule_per_step"] = (e_j1 - e_j0) / args.steps
             clocks["watt_avg"] = (e_j1 - e_j0) / max(t_wall1 - t_wall0, 1e-9)
         cfg = config_of(args, w, world, scaling, nch_global)

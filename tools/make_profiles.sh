@@ -11,6 +11,7 @@ ncu -i gpurun_out/prof_${R}_fzs512.ncu-rep --page raw --csv > profiles/${R}_ncu_
 python tools/sass_mix.py gpurun_out/prof_${R}_fused.ncu-rep 16000000 > profiles/${R}_k_fused_sass_mix.txt
 python tools/hot_code.py gpurun_out/prof_${R}_fused.ncu-rep >> profiles/${R}_k_fused_sass_mix.txt
 tail -1 gpurun_out/${R}_bench_n1.json > profiles/${R}_bench_n1.json
+tail -1 gpurun_out/${R}_bench_n1_steps20.json > profiles/${R}_bench_n1_steps20.json
 tail -1 gpurun_out/${R}_bench_reference.json > profiles/${R}_bench_reference.json
 python - <<'PY'
 import csv, json, subprocess

@@ -4,6 +4,7 @@ set -x
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -4 gpurun_out/r02_smoke.log
 timeout 1500 python -m pytest tests -x -q -m gpu -rs 2>&1 | tail -8 > gpurun_out/r02_tests.log; cat gpurun_out/r02_tests.log
 timeout 600 python bench.py > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; tail -2 gpurun_out/r02_bench_n1.err; cut -c1-300 gpurun_out/r02_bench_n1.json
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_steps20.json 2> gpurun_out/r02_bench_n1_steps20.err; cut -c1-300 gpurun_out/r02_bench_n1_steps20.json
 timeout 600 python bench.py --impl reference > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err; cut -c1-300 gpurun_out/r02_bench_reference.json
 CMD="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e"
 $CMD > gpurun_out/plain_n1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_n1.csv $CMD > gpurun_out/ncu_n1a.log 2>&1
