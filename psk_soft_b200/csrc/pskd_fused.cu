@@ -1387,6 +1387,18 @@ k_fused(const FusedParams prm)
         }
         fz_unit_end<S, PC>(prm, wofs);
     }
+#ifdef PSKD_FZ_PAD_CODE
+    // layout experiment (tools/probe): never-executed instructions between the kernel's hot code and its out-of-line stage functions
+    if (prm.n_units == -12345) {
+        unsigned acc = 0, t;
+#define PSKD_PAD1 asm volatile("mov.u32 %0, %%clock;" : "=r"(t)); acc ^= t;
+#define PSKD_PAD8 PSKD_PAD1 PSKD_PAD1 PSKD_PAD1 PSKD_PAD1 PSKD_PAD1 PSKD_PAD1 PSKD_PAD1 PSKD_PAD1
+#define PSKD_PAD64 PSKD_PAD8 PSKD_PAD8 PSKD_PAD8 PSKD_PAD8 PSKD_PAD8 PSKD_PAD8 PSKD_PAD8 PSKD_PAD8
+#pragma unroll
+        for (int i = 0; i < PSKD_FZ_PAD_CODE; i++) { PSKD_PAD8 }
+        prm.ticket[1] = (int)acc;
+    }
+#endif
 }
 
 // =============================================================================================
