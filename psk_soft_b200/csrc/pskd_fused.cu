@@ -1898,6 +1898,17 @@ k_fzs_cb(const FzsCbParams prm)
         }
         fzs_cb_end<PC>(prm, wofs);
     }
+#ifdef PSKD_FZS_CB_PAD_CODE
+    // layout experiment (tools/probe/ab_layout.sh): never-executed instructions between the loop body and the out-of-line stage functions
+    if (prm.n_units == -12345) {
+        unsigned acc = 0, t;
+#define PSKD_CBPAD1 asm volatile("mov.u32 %0, %%clock;" : "=r"(t)); acc ^= t;
+#define PSKD_CBPAD8 PSKD_CBPAD1 PSKD_CBPAD1 PSKD_CBPAD1 PSKD_CBPAD1 PSKD_CBPAD1 PSKD_CBPAD1 PSKD_CBPAD1 PSKD_CBPAD1
+#pragma unroll
+        for (int i = 0; i < PSKD_FZS_CB_PAD_CODE; i++) { PSKD_CBPAD8 }
+        prm.ticket[1] = (int)acc;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
