@@ -417,7 +417,7 @@ static __device__ __noinline__ void fz_back_literal(const unsigned wofs, const i
 // The buffers are addressed from the warp's shared-memory offset (not through generic pointer parameters: those cost
 // ~15 instructions per 32 symbols of address conversion and turn every access into a generic LD / ST).
 template <class L, int BPB, bool DIFF, bool HARD>
-static __device__ __noinline__ void fz_back_pairs(const unsigned wofs, const int lane, const int M, const int m) {
+static __device__ __forceinline__ void fz_back_pairs_body(const unsigned wofs, const int lane, const int M, const int m) {
     unsigned char* wb = fz_smem + wofs;
     const float2* __restrict__ th2  = reinterpret_cast<const float2*>(wb + L::OFF_TH);
     const float*  __restrict__ selx = reinterpret_cast<const float*>(wb + L::OFF_SEL);
@@ -492,6 +492,12 @@ static __device__ __noinline__ void fz_back_pairs(const unsigned wofs, const int
             if (badB) fz_back_literal<L>(wofs, iA + 1, M, BPB, DIFF ? 1 : 0);
         }
     }
+}
+
+// out of line (its own register allocation, compact code): what the stage code calls when the variant is only known at run time
+template <class L, int BPB, bool DIFF, bool HARD>
+static __device__ __noinline__ void fz_back_pairs(const unsigned wofs, const int lane, const int M, const int m) {
+    fz_back_pairs_body<L, BPB, DIFF, HARD>(wofs, lane, M, m);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -705,7 +711,10 @@ static __device__ FZ_HOT bool fz_chain_fast(const unsigned wofs, const int m)
 // (cpp/psk_soft.cpp:484-566) from selb[] (samples) and th[] (estimates) into the staging buffers
 // (soft, bits: the chain's buffers are dead by now), then the coalesced stores of phase / soft /
 // bits for symbols [kchain, kchain + m).
-template <class L>
+// BK >= 0: every channel of the launch has bits-per-symbol BK / 2 and differentialDecoding BK & 1, and no packed hard symbols are
+// asked for (launch_fused_t checks): the back loop is inlined into the kernel's loop body -- no dispatch, no call, and the hot code is
+// ONE contiguous run (see the placement note in profiles/r02_summary.md).  BK < 0: dispatch at run time.
+template <class L, int BK = -1>
 static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
 {
     unsigned char* wb = fz_smem + wofs;
@@ -718,8 +727,10 @@ static __device__ FZ_HOT void fz_back_block(const unsigned wofs, const int m)
     const int M = cx.M, bpb = cx.bpb, kchain = cx.kchain;
     const bool diff = cx.diff != 0;
     uint8_t* o_hard = cx.o_hard;
-    const bool hard = o_hard != nullptr && bpb > 0;
-    if (!hard) {
+    const bool hard = (BK < 0) && o_hard != nullptr && bpb > 0;
+    if (BK >= 0) {
+        fz_back_pairs_body<L, (BK >= 0 ? BK / 2 : 0), (BK >= 0 && (BK & 1) != 0), false>(wofs, lane, M, m);
+    } else if (!hard) {
         switch (bpb * 2 + (diff ? 1 : 0)) {
             case 6: fz_back_pairs<L, 3, false, false>(wofs, lane, M, m); break;
             case 7: fz_back_pairs<L, 3, true, false>(wofs, lane, M, m); break;
@@ -843,7 +854,7 @@ static __device__ __noinline__ bool fz_next_packet(const unsigned wofs, const in
 
 // fz_drain: consume buffered symbols: chain blocks of FZ_B (shorter at a packet end) followed by
 // the output stage; runs the packet epilogue / next prologue whenever a packet is exhausted.
-template <class L>
+template <class L, int BK = -1>
 static __device__ FZ_HOT void fz_drain(const unsigned wofs)
 {
     unsigned char* wb = fz_smem + wofs;
@@ -882,7 +893,7 @@ static __device__ FZ_HOT void fz_drain(const unsigned wofs)
         if (fast) done = fz_chain_fast<L>(wofs, m);
         if (!done) fz_chain_slow<L>(wofs, m);
         if (lane == 0) cx.blocks++;
-        fz_back_block<L>(wofs, m);
+        fz_back_block<L, BK>(wofs, m);
         const float2 prev_new = fz_sel_get(selx, 2 + m - 1);       // (the stages above leave the samples alone)
         // ---- drop the consumed symbols from the buffer ------------------------------------------------
         const int left = nbuf - m;
@@ -1359,7 +1370,7 @@ static __device__ FZ_HOT void fz_chunk(const unsigned wofs)
 // CT = resident CTAs per SM the register allocation aims at: 5 (96 registers) is the faster code per warp, 6 (80 registers,
 // 24 warps per SM) hides more latency and wins once a launch has enough channels to keep all of those warps busy
 // (launch_fused_t decides).
-template <int S, int PC, int CT>
+template <int S, int PC, int CT, int BK = -1>
 __global__ void __launch_bounds__(FZ_WARPS * 32, CT)
 k_fused(const FusedParams prm)
 {
@@ -1379,11 +1390,11 @@ k_fused(const FusedParams prm)
         if (u >= prm.n_units) break;
         const int nchunks = fz_unit_begin<S, PC>(prm, wofs, u);
         if (nchunks < 0) continue;
-        fz_drain<L>(wofs);             // packets without symbols before the first chunk (and units without any symbol)
+        fz_drain<L, BK>(wofs);         // packets without symbols before the first chunk (and units without any symbol)
         if (cx.a16) {
-            while (cx.c < nchunks) { fz_chunk<S, PC, true>(wofs); fz_drain<L>(wofs); }
+            while (cx.c < nchunks) { fz_chunk<S, PC, true>(wofs); fz_drain<L, BK>(wofs); }
         } else {
-            while (cx.c < nchunks) { fz_chunk<S, PC, false>(wofs); fz_drain<L>(wofs); }
+            while (cx.c < nchunks) { fz_chunk<S, PC, false>(wofs); fz_drain<L, BK>(wofs); }
         }
         fz_unit_end<S, PC>(prm, wofs);
     }
@@ -1914,7 +1925,7 @@ k_fzs_cb(const FzsCbParams prm)
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int S, int PC, int CT>
+template <int S, int PC, int CT, int BK = -1>
 static cudaError_t launch_fused_ct(const LaunchCtx& c, const FusedLaunch& f, const FusedParams& p, double alg_bytes) {
     using L = FzL<S, PC>;
     static const size_t pad = getenv("PSKD_FZ_PAD_SMEM") ? (size_t)atoi(getenv("PSKD_FZ_PAD_SMEM")) : 0;   // tuning: lowers occupancy
@@ -1922,7 +1933,7 @@ static cudaError_t launch_fused_ct(const LaunchCtx& c, const FusedLaunch& f, con
     const size_t smem = (size_t)L::BYTES * FZ_WARPS + pad;
     static KernelCfg cfg;                       // per device (function attributes and occupancy are per device)
     int ctas_per_sm = 0, n_sm = 0;
-    cudaError_t e = cfg.ensure(k_fused<S, PC, CT>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm, carve);
+    cudaError_t e = cfg.ensure(k_fused<S, PC, CT, BK>, smem, FZ_WARPS * 32, &ctas_per_sm, &n_sm, carve);
     if (e != cudaSuccess) return e;
     int grid = n_sm * ctas_per_sm;
     if (f.grid_share > 0.0 && f.grid_share < 1.0) grid = (int)(grid * f.grid_share + 0.999);   // co-resident launches share the SMs
@@ -1930,7 +1941,7 @@ static cudaError_t launch_fused_ct(const LaunchCtx& c, const FusedLaunch& f, con
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     c.prof->begin(S == 8 ? KID_FUSED : S == 9 ? KID_FUSED_S9 : S == 10 ? KID_FUSED_S10 : KID_FUSED_S16, c.stream, alg_bytes);
-    k_fused<S, PC, CT><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
+    k_fused<S, PC, CT, BK><<<grid, FZ_WARPS * 32, smem, c.stream>>>(p);
     c.prof->end(c.stream);
     (*c.launches)++;
     return cudaGetLastError();
@@ -1960,10 +1971,33 @@ static cudaError_t launch_fused_t(const LaunchCtx& c, const FusedLaunch& f) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     constexpr bool fits6 = ((size_t)L::BYTES * FZ_WARPS + 1024) * 6 <= 228 * 1024;               // shared memory of six CTAs (S = 8 only)
-    if constexpr (fits6) {
-        const bool six = force_ct ? (force_ct >= 6) : (f.n_list * 10 >= n_sm * 6 * FZ_WARPS * 11 && !(f.grid_share > 0.0 && f.grid_share < 1.0));
-        if (six) return launch_fused_ct<S, PC, 6>(c, f, p, ab);
+    bool six = false;
+    if constexpr (fits6) six = force_ct ? (force_ct >= 6) : (f.n_list * 10 >= n_sm * 6 * FZ_WARPS * 11 && !(f.grid_share > 0.0 && f.grid_share < 1.0));
+#ifndef PSKD_FZ_NO_BACK_SPEC
+    // the launch's channels share one back-stage variant (a uniform bank: the usual case) and no packed hard symbols are asked for:
+    // the kernel with that variant inlined (coherent BPSK / QPSK / 8-PSK at samplesPerBaud 8, phaseAvg <= 52)
+    if constexpr (S == 8 && PC == 52) {
+        int bk = -1;
+        if (!c.out_hard && f.h_list && f.n_list > 0) {
+            const ChanDesc& d0 = c.h_desc[f.h_list[0]];
+            bk = d0.bpb * 2 + (d0.D ? 1 : 0);
+            for (int i = 1; i < f.n_list && bk >= 0; i++) { const ChanDesc& d = c.h_desc[f.h_list[i]]; if (d.bpb * 2 + (d.D ? 1 : 0) != bk) bk = -1; }
+        }
+        if constexpr (fits6) {
+            if (six) {
+                if (bk == 6) return launch_fused_ct<S, PC, 6, 6>(c, f, p, ab);
+                if (bk == 4) return launch_fused_ct<S, PC, 6, 4>(c, f, p, ab);
+                if (bk == 2) return launch_fused_ct<S, PC, 6, 2>(c, f, p, ab);
+            }
+        }
+        if (!six) {
+            if (bk == 6) return launch_fused_ct<S, PC, PSKD_FZ_MIN_CTAS, 6>(c, f, p, ab);
+            if (bk == 4) return launch_fused_ct<S, PC, PSKD_FZ_MIN_CTAS, 4>(c, f, p, ab);
+            if (bk == 2) return launch_fused_ct<S, PC, PSKD_FZ_MIN_CTAS, 2>(c, f, p, ab);
+        }
     }
+#endif
+    if constexpr (fits6) { if (six) return launch_fused_ct<S, PC, 6>(c, f, p, ab); }
     return launch_fused_ct<S, PC, PSKD_FZ_MIN_CTAS>(c, f, p, ab);
 }
 
@@ -2053,6 +2087,7 @@ static cudaError_t launch_fzs_cb_t(const LaunchCtx& c, const TpCtl& tp, int n_un
 // one launch of the chain + back kernel: tp.items != null -> one unit per item, else one unit per channel
 cudaError_t launch_fzs_cb(const LaunchCtx& c, const TpCtl& tp, int n_units, double alg_bytes) {
     if (n_units <= 0) return cudaSuccess;
+    // (the chain + back kernel with the back-stage variant inlined, as k_fused has it, measured no gain: 1.90 vs 1.89 ms on the 512-channel shard)
     return c.Pmax_fzs <= 52 ? launch_fzs_cb_t<52>(c, tp, n_units, alg_bytes) : launch_fzs_cb_t<128>(c, tp, n_units, alg_bytes);
 }
 
