@@ -20,8 +20,10 @@ def _checkers(oracle):
     return out
 
 
-def _bank_run(pk, torch, table, n, seed, packet_len, pn=0.0, sigma=0.02, freq_max=2e-5, calls=1):
-    """generate the bank class by class in HBM (as bench.py does), run `calls` pskd_process calls over it"""
+def _bank_run(pk, torch, table, n, seed, packet_len, pn=0.0, sigma=0.02, freq_max=2e-5, calls=1, no_hard_calls=()):
+    """generate the bank class by class in HBM (as bench.py does), run `calls` pskd_process calls over it.  Calls listed in
+    `no_hard_calls` do not ask for the additional packed hard-symbol output -- exactly bench.py's call: a uniform bank then
+    runs the k_fused instance with its back-stage variant inlined (k_fused<S,PC,CT,BK>), the others the run-time dispatch."""
     nch = len(table)
     Smin = min(p["samplesPerBaud"] for p in table)
     cap = n // Smin + 8
@@ -39,15 +41,16 @@ def _bank_run(pk, torch, table, n, seed, packet_len, pn=0.0, sigma=0.02, freq_ma
     torch.cuda.synchronize()
     bank = pk.Bank(nch, table)
     outs = []
-    for _ in range(calls):
+    for j in range(calls):
         o = dict(soft=torch.zeros((nch, cap, 2), dtype=torch.float32, device="cuda"),
                  phase=torch.zeros((nch, cap), dtype=torch.float32, device="cuda"),
                  sidx=torch.zeros((nch, cap), dtype=torch.int16, device="cuda"),
-                 bits=torch.zeros((nch, cap * 3), dtype=torch.int16, device="cuda"),
-                 hard=torch.zeros((nch, cap), dtype=torch.uint8, device="cuda"))
+                 bits=torch.zeros((nch, cap * 3), dtype=torch.int16, device="cuda"))
+        if j not in no_hard_calls:
+            o["hard"] = torch.zeros((nch, cap), dtype=torch.uint8, device="cuda")
         rc, ns, nb = bank.process_raw(iq.data_ptr(), n, n, o["soft"].data_ptr(), o["bits"].data_ptr(), o["phase"].data_ptr(),
                                       o["sidx"].data_ptr(), cap, cap * 3, xdelta=0.01, packet_len=packet_len,
-                                      hard_ptr=o["hard"].data_ptr())
+                                      hard_ptr=o["hard"].data_ptr() if "hard" in o else None)
         assert rc == 0
         o["ns"], o["nb"] = ns, nb
         outs.append(o)
@@ -57,8 +60,11 @@ def _bank_run(pk, torch, table, n, seed, packet_len, pn=0.0, sigma=0.02, freq_ma
 
 def _channel(o, c):
     k, b = int(o["ns"][c]), int(o["nb"][c])
-    return dict(soft=o["soft"][c, :k].cpu().numpy().view(np.complex64).reshape(-1), phase=o["phase"][c, :k].cpu().numpy(),
-                sidx=o["sidx"][c, :k].cpu().numpy(), bits=o["bits"][c, :b].cpu().numpy(), hard=o["hard"][c, :k].cpu().numpy())
+    d = dict(soft=o["soft"][c, :k].cpu().numpy().view(np.complex64).reshape(-1), phase=o["phase"][c, :k].cpu().numpy(),
+             sidx=o["sidx"][c, :k].cpu().numpy(), bits=o["bits"][c, :b].cpu().numpy())
+    if "hard" in o:
+        d["hard"] = o["hard"][c, :k].cpu().numpy()
+    return d
 
 
 def _check_sampled(oracle, iq, outs, table, rows, packet_len, tag):
@@ -88,7 +94,9 @@ def test_bench_bank_full_shape(M, oracle_built):
     props = dict(samplesPerBaud=8, constelationSize=M, numAvg=100, phaseAvg=50, differentialDecoding=0)
     nch, n, pkt = 4096, 1_000_000, 64000
     table = [props] * nch
-    iq, outs, bank = _bank_run(pk, torch, table, n, seed=4, packet_len=pkt, calls=2)
+    # call 0 asks for the packed hard symbols too (run-time dispatch of the back stage), call 1 is bench.py's call (no hard
+    # output: the kernel instance with the bank's back-stage variant inlined, k_fused<8,52,6,BK> -- the benchmarked kernel)
+    iq, outs, bank = _bank_run(pk, torch, table, n, seed=4, packet_len=pkt, calls=2, no_hard_calls=(1,))
     K0, K1 = n // 8 - 99, n // 8
     assert (outs[0]["ns"] == K0).all() and (outs[1]["ns"] == K1).all()
     st = bank.stats()
