@@ -426,7 +426,8 @@ static __device__ __forceinline__ void fz_back_pairs_body(const unsigned wofs, c
     float4*   __restrict__ cst4 = reinterpret_cast<float4*>(wb + L::OFF_ALIAS);                    // soft staging [FZ_B]
     unsigned* __restrict__ bst  = reinterpret_cast<unsigned*>(wb + L::OFF_ALIAS + FZ_B * 8);       // bits staging [FZ_B * 3] int16
     unsigned short* __restrict__ hst2 = reinterpret_cast<unsigned short*>(wb + L::OFF_ALIAS + FZ_B * 8 + FZ_B * 6);   // packed hard symbols
-    const float ninv_m = (M == 8) ? -0.125f : (M == 4) ? -0.25f : (M == 2) ? -0.5f : -1.0f / (float)M;   // (the same floats, without the division)
+    // -1 / M (:494): BPB > 0 <=> constelationSize == 1 << BPB (bpb_of, pskd_api.cu): a compile-time constant for BPSK / QPSK / 8-PSK
+    const float ninv_m = (BPB > 0) ? (-1.0f / (float)(1 << (BPB > 0 ? BPB : 1))) : (-1.0f / (float)M);
     const bool inexact = (BPB == 0 && (M & (M - 1)) != 0);                 // -est/M not an exact multiply
     const int npairs = (m + 1) >> 1;
 #pragma unroll 1
