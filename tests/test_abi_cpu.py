@@ -65,3 +65,21 @@ def test_product_never_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for b in banned:
                     assert b not in txt, f"{os.path.join(dirpath, f)} references the oracle ({b})"
+
+
+def test_bench_clock_sampler_degrades_without_a_gpu():
+    """bench.py's clock / energy sampler (NVML every 5 ms, nvidia-smi as the fallback) must not take the bench down on a box
+    that has neither: it reports that it has no samples"""
+    import importlib.util
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.1)
+    s.stop()
+    out = s.summary(time.time() - 1.0, time.time())
+    assert "reasons" in out and "sm_mhz" in out
+    if out["sm_mhz"] is None:
+        assert s.energy_j() is None or isinstance(s.energy_j(), float)
